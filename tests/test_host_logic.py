@@ -1,0 +1,129 @@
+"""CPU: host-side logic - config/params mirrors, the C-ABI library's exports and error behaviour
+without a device, track sharding + the box gather over gloo (world_size 2)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_config_overlay_and_unknown_key(tmp_path):
+    from vittracker_b200 import config
+    c = config.load_cfg()
+    assert c.MODEL.BACKBONE.CHANNELS == 48 and c.MODEL.BACKBONE.HEADS == 1 and c.MODEL.HEAD.NUM_CHANNELS == 32
+    assert c.TEST.SEARCH_SIZE == 256 and c.TEST.SEARCH_FACTOR == 4.0 and c.TEST.TEMPLATE_SIZE == 128
+    assert config.default_cfg().TEST.SEARCH_SIZE == 320            # family default untouched
+    bad = tmp_path / "bad.yaml"
+    bad.write_text("MODEL:\n  NOT_A_KEY: 1\n")
+    with pytest.raises(ValueError, match="NOT_A_KEY not exist in config.py"):
+        config.update_config_from_file(str(bad), config.default_cfg())
+
+
+def test_parameters_bag():
+    from vittracker_b200 import parameters
+    p = parameters("vit_48_h32_noKD", save_dir="/tmp/vt")
+    assert (p.template_factor, p.template_size, p.search_factor, p.search_size) == (2.0, 128, 4.0, 256)
+    assert p.checkpoint == "/tmp/vt/checkpoints/train/vit_dist/vit_48_h32_noKD/OstrackDist_ep0300.pth.tar"
+    assert p.save_all_boxes is False and p.get("missing", 3) == 3 and p.has("cfg")
+
+
+def test_state_dict_names_match_oracle():
+    from oracle import vt_oracle as O
+    from vittracker_b200 import load_cfg
+    from vittracker_b200.weights import param_shapes, random_init_state_dict
+    a, b = param_shapes(load_cfg()), O.param_shapes()
+    assert a == b
+    sd = random_init_state_dict(load_cfg())
+    n = sum(v.numel() for k, v in sd.items() if v.is_floating_point() and "running" not in k)
+    assert n == 174403                                              # SURVEY: 174 403 parameters
+
+
+def test_library_exports_every_declared_symbol():
+    from vittracker_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "vittrack_b200.h")).read()
+    declared = set(re.findall(r"\b(vt_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.vt_abi_version() == 1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device failure path")
+def test_no_cpu_fallback():
+    from vittracker_b200 import _lib, load_cfg
+    lib = _lib.load()
+    h = C.c_void_p()
+    cfg = _lib.VtConfig(48, 1, 3, 4, 32, 16, 128, 256, 2.0, 4.0, 1, 0, 0, 0)
+    assert lib.vt_create(C.byref(cfg), C.byref(h)) == -6
+    assert b"no CPU fallback" in lib.vt_last_error(None)
+    from vittracker_b200.engine import Engine
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Engine(load_cfg())
+
+
+def test_unsupported_config_rejected():
+    from vittracker_b200 import _lib
+    lib = _lib.load()
+    h = C.c_void_p()
+    cfg = _lib.VtConfig(768, 12, 12, 4, 256, 16, 128, 256, 2.0, 4.0, 1, 0, 0, 0)
+    assert lib.vt_create(C.byref(cfg), C.byref(h)) == -5
+    assert lib.vt_create(None, C.byref(h)) == -1
+
+
+def test_shard_range_partitions():
+    from vittracker_b200.batched import shard_range
+    for total in (0, 1, 7, 8, 1024, 8191, 8192):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_tracker_clip_box_matches_oracle():
+    from oracle import vt_oracle as O
+    from vittracker_b200.tracker import clip_box
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        b = list(rng.uniform(-50, 400, size=4))
+        assert clip_box(b, 240, 320, margin=10) == O.clip_box(b, 240, 320, margin=10)
+
+
+_GLOO_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["VT_ROOT"])
+from vittracker_b200.batched import ShardedTracker, shard_range
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["VT_PORT"],
+                        rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+for total in (8, 7, 3):
+    sh = ShardedTracker(total)
+    lo, hi = sh.lo, sh.hi
+    local = torch.arange(lo, hi, dtype=torch.float64).unsqueeze(1) * torch.tensor([[1., 10., 100., 1000., 0.5]], dtype=torch.float64)
+    full = sh.gather(local)
+    want = torch.arange(0, total, dtype=torch.float64).unsqueeze(1) * torch.tensor([[1., 10., 100., 1000., 0.5]], dtype=torch.float64)
+    assert full.shape == (total, 5) and torch.equal(full, want), (total, full)
+dist.barrier()
+dist.destroy_process_group()
+print("OK", os.environ["RANK"])
+'''
+
+
+def test_sharded_gather_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", VT_ROOT=ROOT, VT_PORT=port, MASTER_ADDR="127.0.0.1")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0 and "OK" in out, out

@@ -1,0 +1,580 @@
+// C-ABI layer of libvittrack_b200.so: handle, weight ingestion (BN folding + layout packing),
+// workspace, and the entry points declared in include/vittrack_b200.h.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/vittrack_b200.h"
+#include "vt_internal.h"
+
+using namespace vt;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct HostTensor {
+    std::vector<float> data;
+    std::vector<int64_t> shape;
+};
+
+}  // namespace
+
+struct VtContext {
+    VtConfig cfg;
+    std::string err;
+    std::map<std::string, HostTensor> tensors;
+    bool finalized = false;
+    bool tracks_ready = false;
+    int64_t launches = 0;
+
+    float* d_weights = nullptr;       // packed model
+    size_t weights_floats = 0;
+    ModelW mw{};
+
+    int chunk = 0;
+    // chunk workspace
+    float* d_crop = nullptr;          // [chunk][3][256][256]
+    float* d_scratch = nullptr;       // stem intermediates
+    float* d_tokz = nullptr;          // [chunk][64][48]   (vt_forward only)
+    float* d_tokx = nullptr;          // [chunk][256][48]
+    float* d_tok = nullptr;           // [chunk][320][48]
+    // per-track state
+    double* d_state = nullptr;        // [max_tracks][4]
+    float* d_tmpl = nullptr;          // [max_tracks][64][48] cached template tokens (+pos)
+    int32_t* d_status = nullptr;      // [max_tracks]
+    float* d_maps = nullptr;          // [max_tracks][1280] score | size | offset of the last step
+    int last_first = 0, last_n = 0;
+    // optional per-stage timing (vt_profile_*)
+    struct ProfRec { int stage; int items; cudaEvent_t a, b; };
+    bool profiling = false;
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> evpool;
+};
+
+namespace {
+
+int fail(VtHandle h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define VT_CUDA(h, expr)                                                                         \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess) return fail(h, VT_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+const char* kTowers[3] = {"ctr", "offset", "size"};
+
+bool expected_shape(const VtConfig& c, const std::string& name, std::vector<int64_t>& shp) {
+    const int C = c.embed_dim, hc = c.head_channels;
+    char buf[128];
+    if (name == "pos_embed_z") { shp = {1, 64, C}; return true; }
+    if (name == "pos_embed_x") { shp = {1, 256, C}; return true; }
+    if (name == "norm.weight" || name == "norm.bias") { shp = {C}; return true; }
+    if (name == "tracker.output_window") { shp = {1, 1, 16, 16}; return true; }
+    const int ch[5] = {3, C / 8, C / 4, C / 2, C};
+    for (int i = 0; i < 4; ++i) {
+        snprintf(buf, sizeof buf, "patch_embed.net.%d.", 2 * i);
+        if (name.rfind(buf, 0) == 0) {
+            const std::string leaf = name.substr(strlen(buf));
+            if (leaf == "c.weight") { shp = {ch[i + 1], ch[i], 3, 3}; return true; }
+            if (leaf == "bn.weight" || leaf == "bn.bias" || leaf == "bn.running_mean" || leaf == "bn.running_var") { shp = {ch[i + 1]}; return true; }
+            return false;
+        }
+    }
+    for (int b = 0; b < c.depth; ++b) {
+        snprintf(buf, sizeof buf, "blocks.%d.", b);
+        if (name.rfind(buf, 0) == 0) {
+            const std::string leaf = name.substr(strlen(buf));
+            const int hid = c.mlp_ratio * C;
+            if (leaf == "norm1.weight" || leaf == "norm1.bias" || leaf == "norm2.weight" || leaf == "norm2.bias") { shp = {C}; return true; }
+            if (leaf == "attn.qkv.weight") { shp = {3 * C, C}; return true; }
+            if (leaf == "attn.qkv.bias") { shp = {3 * C}; return true; }
+            if (leaf == "attn.proj.weight") { shp = {C, C}; return true; }
+            if (leaf == "attn.proj.bias") { shp = {C}; return true; }
+            if (leaf == "mlp.fc1.weight") { shp = {hid, C}; return true; }
+            if (leaf == "mlp.fc1.bias") { shp = {hid}; return true; }
+            if (leaf == "mlp.fc2.weight") { shp = {C, hid}; return true; }
+            if (leaf == "mlp.fc2.bias") { shp = {C}; return true; }
+            return false;
+        }
+    }
+    const int hch[5] = {C, hc, hc / 2, hc / 4, hc / 8};
+    const int outs[3] = {1, 2, 2};
+    for (int t = 0; t < 3; ++t) {
+        for (int i = 0; i < 4; ++i) {
+            snprintf(buf, sizeof buf, "box_head.conv%d_%s.", i + 1, kTowers[t]);
+            if (name.rfind(buf, 0) == 0) {
+                const std::string leaf = name.substr(strlen(buf));
+                if (leaf == "0.weight") { shp = {hch[i + 1], hch[i], 3, 3}; return true; }
+                if (leaf == "0.bias" || leaf == "1.weight" || leaf == "1.bias" || leaf == "1.running_mean" || leaf == "1.running_var") { shp = {hch[i + 1]}; return true; }
+                return false;
+            }
+        }
+        snprintf(buf, sizeof buf, "box_head.conv5_%s.", kTowers[t]);
+        if (name.rfind(buf, 0) == 0) {
+            const std::string leaf = name.substr(strlen(buf));
+            if (leaf == "weight") { shp = {outs[t], hch[4], 1, 1}; return true; }
+            if (leaf == "bias") { shp = {outs[t]}; return true; }
+            return false;
+        }
+    }
+    return false;
+}
+
+struct Packer {
+    std::vector<float> buf;
+    size_t alloc(size_t n) {                     // 16-byte aligned slots
+        const size_t off = buf.size();
+        buf.resize(off + (n + 3) / 4 * 4, 0.f);
+        return off;
+    }
+};
+
+void free_all(VtHandle h) {
+    for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : h->evpool) cudaEventDestroy(e);
+    cudaFree(h->d_weights); cudaFree(h->d_crop); cudaFree(h->d_scratch); cudaFree(h->d_tokz);
+    cudaFree(h->d_tokx); cudaFree(h->d_tok); cudaFree(h->d_state); cudaFree(h->d_tmpl);
+    cudaFree(h->d_status); cudaFree(h->d_maps);
+}
+
+int check_ready(VtHandle h, bool need_tracks) {
+    if (!h) return VT_ERR_INVALID_ARG;
+    if (!h->finalized) return fail(h, VT_ERR_STATE, "weights not finalised: call vt_set_tensor for every tensor, then vt_finalize_weights");
+    if (need_tracks && !h->tracks_ready) return fail(h, VT_ERR_STATE, "tracks not initialised: call vt_tracks_init first");
+    return VT_OK;
+}
+
+int launch_fail(VtHandle h, int k, const char* where) {
+    if (k == -2) return fail(h, VT_ERR_UNSUPPORTED, "%s: blocks_impl %d is not available in this build", where, h->cfg.blocks_impl);
+    return fail(h, VT_ERR_CUDA, "%s: kernel launch failed: %s", where, cudaGetErrorString(cudaGetLastError()));
+}
+
+cudaEvent_t get_event(VtHandle h) {
+    if (!h->evpool.empty()) { cudaEvent_t e = h->evpool.back(); h->evpool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+// Launch one pipeline stage; when profiling is on, bracket it with events on the launching stream.
+#define VT_LAUNCH(h, stage, items, st, where, expr)                               \
+    do {                                                                          \
+        cudaEvent_t ea__ = nullptr, eb__ = nullptr;                               \
+        if ((h)->profiling) { ea__ = get_event(h); eb__ = get_event(h); cudaEventRecord(ea__, st); } \
+        const int k__ = (expr);                                                   \
+        if (k__ < 0) return launch_fail(h, k__, where);                           \
+        (h)->launches += k__;                                                     \
+        if ((h)->profiling) { cudaEventRecord(eb__, st); (h)->prof.push_back({stage, items, ea__, eb__}); } \
+    } while (0)
+
+int run_blocks(VtHandle h, const float* tokz, int zs, const float* tokx, int xs, float* out, int n, float* taps,
+               size_t tap_stride, cudaStream_t st) {
+    if (h->cfg.blocks_impl == VT_BLOCKS_SIMT_FP32)
+        return launch_blocks_simt(tokz, zs, tokx, xs, out, n, h->mw, taps, tap_stride, st);
+    return -2;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vt_abi_version(void) { return VT_ABI_VERSION; }
+
+const char* vt_last_error(VtHandle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int vt_create(const VtConfig* cfg, VtHandle* out) {
+    if (!cfg || !out) return fail(nullptr, VT_ERR_INVALID_ARG, "vt_create: null argument");
+    *out = nullptr;
+    if (cfg->embed_dim != kC || cfg->num_heads != 1 || cfg->depth != kDepth || cfg->mlp_ratio != 4 ||
+        cfg->head_channels != kHeadC || cfg->stride != 16 || cfg->template_size != kTz || cfg->search_size != kSx)
+        return fail(nullptr, VT_ERR_UNSUPPORTED,
+                    "unsupported configuration (this build has kernels for vit_48_h32: C=48, heads=1, depth=3, "
+                    "mlp_ratio=4, head=32, stride=16, template 128, search 256)");
+    if (cfg->max_tracks < 1 || !(cfg->template_factor > 0) || !(cfg->search_factor > 0))
+        return fail(nullptr, VT_ERR_INVALID_ARG, "vt_create: max_tracks >= 1 and positive crop factors required");
+    if (cfg->blocks_impl != VT_BLOCKS_SIMT_FP32 && cfg->blocks_impl != VT_BLOCKS_TCGEN05)
+        return fail(nullptr, VT_ERR_INVALID_ARG, "vt_create: unknown blocks_impl %d", cfg->blocks_impl);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, VT_ERR_NO_DEVICE, "no CUDA device: libvittrack_b200 has no CPU fallback");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, VT_ERR_INVALID_ARG, "vt_create: device %d out of range", cfg->device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail(nullptr, VT_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major < 10) return fail(nullptr, VT_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+
+    VtHandle h = new VtContext();
+    h->cfg = *cfg;
+    h->chunk = cfg->chunk_tracks > 0 ? cfg->chunk_tracks : 256;
+    if (h->chunk > cfg->max_tracks) h->chunk = cfg->max_tracks;
+    if (cudaSetDevice(cfg->device) != cudaSuccess) { delete h; return fail(nullptr, VT_ERR_CUDA, "cudaSetDevice failed"); }
+    const size_t ch = h->chunk, mt = cfg->max_tracks;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    A((void**)&h->d_crop, ch * 3 * kSx * kSx * sizeof(float));
+    A((void**)&h->d_scratch, ch * stem_scratch_floats(kSx) * sizeof(float));
+    A((void**)&h->d_tokz, ch * kNz * kC * sizeof(float));
+    A((void**)&h->d_tokx, ch * kNx * kC * sizeof(float));
+    A((void**)&h->d_tok, ch * kN * kC * sizeof(float));
+    A((void**)&h->d_state, mt * 4 * sizeof(double));
+    A((void**)&h->d_tmpl, mt * kNz * kC * sizeof(float));
+    A((void**)&h->d_status, mt * sizeof(int32_t));
+    A((void**)&h->d_maps, mt * 1280 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(h->d_state, 0, mt * 4 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemset(h->d_status, 0, mt * sizeof(int32_t));
+    if (e != cudaSuccess) {
+        fail(nullptr, VT_ERR_CUDA, "vt_create: device allocation failed: %s", cudaGetErrorString(e));
+        free_all(h); delete h;
+        return VT_ERR_CUDA;
+    }
+    *out = h;
+    return VT_OK;
+}
+
+int vt_destroy(VtHandle h) {
+    if (!h) return VT_ERR_INVALID_ARG;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    free_all(h);
+    delete h;
+    return VT_OK;
+}
+
+int vt_set_tensor(VtHandle h, const char* name, const float* data_host, const int64_t* shape, int32_t ndim) {
+    if (!h || !name || ndim < 0 || ndim > 8 || (ndim > 0 && !shape)) return h ? fail(h, VT_ERR_INVALID_ARG, "vt_set_tensor: bad argument") : VT_ERR_INVALID_ARG;
+    const std::string nm(name);
+    const char* nbt = "num_batches_tracked";
+    if (nm.size() >= strlen(nbt) && nm.compare(nm.size() - strlen(nbt), strlen(nbt), nbt) == 0) return VT_OK;   // accepted, unused in eval
+    std::vector<int64_t> want;
+    if (!expected_shape(h->cfg, nm, want)) return fail(h, VT_ERR_WEIGHTS, "unknown tensor '%s' (ignored, as load_state_dict(strict=False) would)", name);
+    if (!data_host) return fail(h, VT_ERR_INVALID_ARG, "vt_set_tensor: null data for '%s'", name);
+    std::vector<int64_t> got(shape, shape + ndim);
+    if (got != want) {
+        std::string g, w;
+        for (auto v : got) g += std::to_string(v) + ",";
+        for (auto v : want) w += std::to_string(v) + ",";
+        return fail(h, VT_ERR_WEIGHTS, "tensor '%s': shape (%s) does not match expected (%s)", name, g.c_str(), w.c_str());
+    }
+    size_t n = 1;
+    for (auto v : got) n *= (size_t)v;
+    HostTensor& t = h->tensors[nm];
+    t.shape = got;
+    t.data.assign(data_host, data_host + n);
+    h->finalized = false;
+    return VT_OK;
+}
+
+int vt_finalize_weights(VtHandle h, void* stream) {
+    if (!h) return VT_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    VT_CUDA(h, cudaSetDevice(h->cfg.device));
+    std::string missing;
+    auto T = [&](const std::string& n) -> const float* {
+        auto it = h->tensors.find(n);
+        if (it == h->tensors.end()) { if (missing.size() < 300) missing += n + " "; return nullptr; }
+        return it->second.data.data();
+    };
+    Packer pk;
+    auto slot = [&](size_t n) { return pk.alloc(n); };
+    const double eps = 1e-5;     // BatchNorm2d default eps
+
+    // ---- stem: fold BN (Conv2d_BN.fuse, vit_dist.py:22-33), repack [co][ci][3][3] -> [ci][ky][kx][co]
+    const int ch[5] = {3, 6, 12, 24, 48};
+    size_t stem_w[4], stem_b[4];
+    for (int l = 0; l < 4; ++l) {
+        const std::string p = "patch_embed.net." + std::to_string(2 * l) + ".";
+        const float *w = T(p + "c.weight"), *g = T(p + "bn.weight"), *b = T(p + "bn.bias"), *m = T(p + "bn.running_mean"), *v = T(p + "bn.running_var");
+        const int ci_n = ch[l], co_n = ch[l + 1];
+        stem_w[l] = slot((size_t)ci_n * 9 * co_n);
+        stem_b[l] = slot(co_n);
+        if (!(w && g && b && m && v)) continue;
+        for (int co = 0; co < co_n; ++co) {
+            const double s = (double)g[co] / sqrt((double)v[co] + eps);
+            pk.buf[stem_b[l] + co] = (float)((double)b[co] - (double)m[co] * s);
+            for (int ci = 0; ci < ci_n; ++ci)
+                for (int k = 0; k < 9; ++k)
+                    pk.buf[stem_w[l] + ((size_t)ci * 9 + k) * co_n + co] = (float)((double)w[((size_t)co * ci_n + ci) * 9 + k] * s);
+        }
+    }
+    // ---- blocks: Linear weights [out][in] -> K-major [in][out]
+    struct BOff { size_t ln1g, ln1b, wqkv, bqkv, wproj, bproj, ln2g, ln2b, wfc1, bfc1, wfc2, bfc2; } bo[kDepth];
+    auto copyv = [&](size_t o, const float* src, size_t n) { if (src) memcpy(&pk.buf[o], src, n * sizeof(float)); };
+    auto transp = [&](size_t o, const float* src, int rows_out, int cols_in) {     // src [out][in] -> dst [in][out]
+        if (!src) return;
+        for (int r = 0; r < rows_out; ++r)
+            for (int c = 0; c < cols_in; ++c) pk.buf[o + (size_t)c * rows_out + r] = src[(size_t)r * cols_in + c];
+    };
+    for (int b = 0; b < kDepth; ++b) {
+        const std::string p = "blocks." + std::to_string(b) + ".";
+        bo[b].ln1g = slot(kC); copyv(bo[b].ln1g, T(p + "norm1.weight"), kC);
+        bo[b].ln1b = slot(kC); copyv(bo[b].ln1b, T(p + "norm1.bias"), kC);
+        bo[b].wqkv = slot(kC * 3 * kC); transp(bo[b].wqkv, T(p + "attn.qkv.weight"), 3 * kC, kC);
+        bo[b].bqkv = slot(3 * kC); copyv(bo[b].bqkv, T(p + "attn.qkv.bias"), 3 * kC);
+        bo[b].wproj = slot(kC * kC); transp(bo[b].wproj, T(p + "attn.proj.weight"), kC, kC);
+        bo[b].bproj = slot(kC); copyv(bo[b].bproj, T(p + "attn.proj.bias"), kC);
+        bo[b].ln2g = slot(kC); copyv(bo[b].ln2g, T(p + "norm2.weight"), kC);
+        bo[b].ln2b = slot(kC); copyv(bo[b].ln2b, T(p + "norm2.bias"), kC);
+        bo[b].wfc1 = slot(kC * kHid); transp(bo[b].wfc1, T(p + "mlp.fc1.weight"), kHid, kC);
+        bo[b].bfc1 = slot(kHid); copyv(bo[b].bfc1, T(p + "mlp.fc1.bias"), kHid);
+        bo[b].wfc2 = slot(kHid * kC); transp(bo[b].wfc2, T(p + "mlp.fc2.weight"), kC, kHid);
+        bo[b].bfc2 = slot(kC); copyv(bo[b].bfc2, T(p + "mlp.fc2.bias"), kC);
+    }
+    const size_t o_ng = slot(kC), o_nb = slot(kC), o_pz = slot(kNz * kC), o_px = slot(kNx * kC);
+    copyv(o_ng, T("norm.weight"), kC); copyv(o_nb, T("norm.bias"), kC);
+    copyv(o_pz, T("pos_embed_z"), kNz * kC); copyv(o_px, T("pos_embed_x"), kNx * kC);
+
+    // ---- head: conv(+bias) -> BN folded; layer i weights laid out [ci][k][tower][co_t]
+    const int hch[5] = {kC, kHeadC, kHeadC / 2, kHeadC / 4, kHeadC / 8};
+    size_t hw[5], hb[5];
+    for (int i = 0; i < 4; ++i) {
+        const int ci_n = hch[i], co_n = hch[i + 1];
+        hw[i] = slot((size_t)ci_n * 9 * 3 * co_n);
+        hb[i] = slot(3 * co_n);
+        for (int t = 0; t < 3; ++t) {
+            const std::string p = std::string("box_head.conv") + std::to_string(i + 1) + "_" + kTowers[t] + ".";
+            const float *w = T(p + "0.weight"), *cb = T(p + "0.bias"), *g = T(p + "1.weight"), *b = T(p + "1.bias"), *m = T(p + "1.running_mean"), *v = T(p + "1.running_var");
+            if (!(w && cb && g && b && m && v)) continue;
+            for (int co = 0; co < co_n; ++co) {
+                const double s = (double)g[co] / sqrt((double)v[co] + eps);
+                pk.buf[hb[i] + t * co_n + co] = (float)(((double)cb[co] - (double)m[co]) * s + (double)b[co]);
+                for (int ci = 0; ci < ci_n; ++ci)
+                    for (int k = 0; k < 9; ++k)
+                        pk.buf[hw[i] + (((size_t)ci * 9 + k) * 3 + t) * co_n + co] = (float)((double)w[((size_t)co * ci_n + ci) * 9 + k] * s);
+            }
+        }
+    }
+    hw[4] = slot(3 * 4 * 2); hb[4] = slot(3 * 2);
+    for (int t = 0; t < 3; ++t) {
+        const std::string p = std::string("box_head.conv5_") + kTowers[t] + ".";
+        const float *w = T(p + "weight"), *b = T(p + "bias");
+        if (!(w && b)) continue;
+        const int outs = t == 0 ? 1 : 2;
+        for (int o = 0; o < outs; ++o) {
+            pk.buf[hb[4] + t * 2 + o] = b[o];
+            for (int c = 0; c < 4; ++c) pk.buf[hw[4] + (t * 4 + c) * 2 + o] = w[o * 4 + c];
+        }
+    }
+    if (!missing.empty()) return fail(h, VT_ERR_WEIGHTS, "missing tensors: %s", missing.c_str());
+
+    // ---- Hann window (hann.py:6-16) and normalisation table (data_utils.py:8-14) -----------------
+    const size_t o_hann = slot(256), o_lut = slot(768);
+    auto it = h->tensors.find("tracker.output_window");
+    if (it != h->tensors.end()) {
+        copyv(o_hann, it->second.data.data(), 256);
+    } else {
+        float w1[16];
+        const float step = (float)(2.0 * M_PI / 17.0);
+        for (int k = 0; k < 16; ++k) w1[k] = 0.5f * (1.f - cosf(step * (float)(k + 1)));
+        for (int y = 0; y < 16; ++y)
+            for (int x = 0; x < 16; ++x) pk.buf[o_hann + y * 16 + x] = w1[y] * w1[x];
+    }
+    {
+        const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+        for (int c = 0; c < 3; ++c)
+            for (int v = 0; v < 256; ++v) {
+                volatile float a = (float)v / 255.0f;        // (x / 255.0) - mean) / std, each step rounded to fp32
+                volatile float d = a - mean[c];
+                volatile float r = d / stdv[c];
+                pk.buf[o_lut + c * 256 + v] = r;
+            }
+    }
+
+    if (h->d_weights && h->weights_floats < pk.buf.size()) { cudaFree(h->d_weights); h->d_weights = nullptr; }
+    if (!h->d_weights) {
+        VT_CUDA(h, cudaMalloc((void**)&h->d_weights, pk.buf.size() * sizeof(float)));
+        h->weights_floats = pk.buf.size();
+    }
+    VT_CUDA(h, cudaMemcpyAsync(h->d_weights, pk.buf.data(), pk.buf.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    VT_CUDA(h, cudaStreamSynchronize(st));          // pk.buf is a local
+    const float* base = h->d_weights;
+    ModelW& m = h->mw;
+    for (int l = 0; l < 4; ++l) { m.stem[l].w = base + stem_w[l]; m.stem[l].b = base + stem_b[l]; }
+    for (int b = 0; b < kDepth; ++b) {
+        BlockW& B = m.blk[b];
+        B.ln1_g = base + bo[b].ln1g; B.ln1_b = base + bo[b].ln1b; B.wqkv = base + bo[b].wqkv; B.bqkv = base + bo[b].bqkv;
+        B.wproj = base + bo[b].wproj; B.bproj = base + bo[b].bproj; B.ln2_g = base + bo[b].ln2g; B.ln2_b = base + bo[b].ln2b;
+        B.wfc1 = base + bo[b].wfc1; B.bfc1 = base + bo[b].bfc1; B.wfc2 = base + bo[b].wfc2; B.bfc2 = base + bo[b].bfc2;
+    }
+    m.norm_g = base + o_ng; m.norm_b = base + o_nb; m.pos_z = base + o_pz; m.pos_x = base + o_px;
+    m.head.w1 = base + hw[0]; m.head.b1 = base + hb[0]; m.head.w2 = base + hw[1]; m.head.b2 = base + hb[1];
+    m.head.w3 = base + hw[2]; m.head.b3 = base + hb[2]; m.head.w4 = base + hw[3]; m.head.b4 = base + hb[3];
+    m.head.w5 = base + hw[4]; m.head.b5 = base + hb[4];
+    m.hann = base + o_hann; m.lut = base + o_lut;
+    h->finalized = true;
+    return VT_OK;
+}
+
+int vt_crop_normalize(VtHandle h, const uint8_t* frames, const int64_t* frame_offsets, const int32_t* frame_hw,
+                      const double* boxes_xywh, double factor, int32_t out_size, int32_t n, float* out_nchw,
+                      uint8_t* out_u8_hwc, uint8_t* out_mask, double* out_resize_factor, int32_t* out_status,
+                      void* stream) {
+    int rc = check_ready(h, false);
+    if (rc) return rc;
+    if (!frames || !frame_offsets || !frame_hw || !boxes_xywh || !out_nchw || n < 0) return fail(h, VT_ERR_INVALID_ARG, "vt_crop_normalize: null pointer or negative n");
+    if (out_size != 128 && out_size != 256) return fail(h, VT_ERR_UNSUPPORTED, "vt_crop_normalize: out_size must be 128 or 256");
+    if (!(factor > 0)) return fail(h, VT_ERR_INVALID_ARG, "vt_crop_normalize: factor must be positive");
+    VT_CUDA(h, cudaSetDevice(h->cfg.device));
+    const int k = launch_crop_normalize(frames, frame_offsets, frame_hw, boxes_xywh, factor, out_size, n, h->mw.lut, out_nchw,
+                                        out_u8_hwc, out_mask, out_resize_factor, out_status, (cudaStream_t)stream);
+    if (k < 0) return fail(h, VT_ERR_CUDA, "crop kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    h->launches += k;
+    return VT_OK;
+}
+
+int vt_forward(VtHandle h, const float* z, const float* x, int32_t n, float* pred_boxes, float* score_map,
+               float* size_map, float* offset_map, float* taps, void* stream) {
+    int rc = check_ready(h, false);
+    if (rc) return rc;
+    if (!z || !x || n < 0) return fail(h, VT_ERR_INVALID_ARG, "vt_forward: null input or negative n");
+    cudaStream_t st = (cudaStream_t)stream;
+    VT_CUDA(h, cudaSetDevice(h->cfg.device));
+    const size_t tap_stride = (size_t)n * kN * kC;
+    for (int first = 0; first < n; first += h->chunk) {
+        const int m = (n - first < h->chunk) ? n - first : h->chunk;
+        VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_forward/stem(z)", launch_stem(z + (size_t)first * 3 * kTz * kTz, kTz, m, h->mw, h->d_scratch, h->d_tokz, kNz, 0, st));
+        VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_forward/stem(x)", launch_stem(x + (size_t)first * 3 * kSx * kSx, kSx, m, h->mw, h->d_scratch, h->d_tokx, kNx, 0, st));
+        VT_LAUNCH(h, VT_STAGE_BLOCKS, m, st, "vt_forward/blocks", run_blocks(h, h->d_tokz, kNz, h->d_tokx, kNx, h->d_tok, m,
+                                                      taps ? taps + (size_t)first * kN * kC : nullptr, tap_stride, st));
+        HeadArgs a{};
+        a.tokens = h->d_tok; a.n = m;
+        a.pred_boxes = pred_boxes ? pred_boxes + (size_t)first * 4 : nullptr;
+        a.score_map = score_map ? score_map + (size_t)first * 256 : nullptr;
+        a.size_map = size_map ? size_map + (size_t)first * 512 : nullptr;
+        a.offset_map = offset_map ? offset_map + (size_t)first * 512 : nullptr;
+        a.tokens_norm = taps ? taps + (size_t)(kDepth + 1) * tap_stride + (size_t)first * kN * kC : nullptr;
+        VT_LAUNCH(h, VT_STAGE_HEAD, m, st, "vt_forward/head", launch_head(a, h->mw, st));
+    }
+    return VT_OK;
+}
+
+int vt_cal_bbox(VtHandle h, const float* score, const float* size_map, const float* offset_map, int32_t n,
+                float* boxes, void* stream) {
+    if (!h) return VT_ERR_INVALID_ARG;
+    if (!score || !size_map || !offset_map || !boxes || n < 0) return fail(h, VT_ERR_INVALID_ARG, "vt_cal_bbox: null pointer or negative n");
+    VT_CUDA(h, cudaSetDevice(h->cfg.device));
+    const int k = launch_cal_bbox(score, size_map, offset_map, n, boxes, (cudaStream_t)stream);
+    if (k < 0) return fail(h, VT_ERR_CUDA, "cal_bbox launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    h->launches += k;
+    return VT_OK;
+}
+
+int vt_tracks_init(VtHandle h, const uint8_t* frames, const int64_t* frame_offsets, const int32_t* frame_hw,
+                   const double* boxes_xywh, int32_t first, int32_t n, int32_t* out_status, void* stream) {
+    int rc = check_ready(h, false);
+    if (rc) return rc;
+    if (!frames || !frame_offsets || !frame_hw || !boxes_xywh) return fail(h, VT_ERR_INVALID_ARG, "vt_tracks_init: null pointer");
+    if (first < 0 || n < 0 || first + n > h->cfg.max_tracks) return fail(h, VT_ERR_INVALID_ARG, "vt_tracks_init: tracks [%d, %d) exceed max_tracks %d", first, first + n, h->cfg.max_tracks);
+    cudaStream_t st = (cudaStream_t)stream;
+    VT_CUDA(h, cudaSetDevice(h->cfg.device));
+    for (int c0 = 0; c0 < n; c0 += h->chunk) {
+        const int m = (n - c0 < h->chunk) ? n - c0 : h->chunk;
+        VT_LAUNCH(h, VT_STAGE_CROP, m, st, "vt_tracks_init/crop", launch_crop_normalize(frames, frame_offsets + c0, frame_hw + 2 * c0, boxes_xywh + 4 * c0,
+                                                                 h->cfg.template_factor, kTz, m, h->mw.lut, h->d_crop, nullptr, nullptr,
+                                                                 nullptr, h->d_status + first + c0, st));
+        VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_tracks_init/stem", launch_stem(h->d_crop, kTz, m, h->mw, h->d_scratch,
+                                                       h->d_tmpl + (size_t)(first + c0) * kNz * kC, kNz, 0, st));
+    }
+    VT_CUDA(h, cudaMemcpyAsync(h->d_state + (size_t)first * 4, boxes_xywh, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (out_status) VT_CUDA(h, cudaMemcpyAsync(out_status, h->d_status + first, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    h->tracks_ready = true;
+    return VT_OK;
+}
+
+int vt_tracks_step(VtHandle h, const uint8_t* frames, const int64_t* frame_offsets, const int32_t* frame_hw,
+                   int32_t first, int32_t n, double* out_boxes, double* out_detail, int32_t update_state, void* stream) {
+    int rc = check_ready(h, true);
+    if (rc) return rc;
+    if (!frames || !frame_offsets || !frame_hw || !out_boxes) return fail(h, VT_ERR_INVALID_ARG, "vt_tracks_step: null pointer");
+    if (first < 0 || n < 0 || first + n > h->cfg.max_tracks) return fail(h, VT_ERR_INVALID_ARG, "vt_tracks_step: tracks [%d, %d) exceed max_tracks %d", first, first + n, h->cfg.max_tracks);
+    cudaStream_t st = (cudaStream_t)stream;
+    VT_CUDA(h, cudaSetDevice(h->cfg.device));
+    for (int c0 = 0; c0 < n; c0 += h->chunk) {
+        const int m = (n - c0 < h->chunk) ? n - c0 : h->chunk;
+        const int t0 = first + c0;
+        VT_LAUNCH(h, VT_STAGE_CROP, m, st, "vt_tracks_step/crop", launch_crop_normalize(frames, frame_offsets + c0, frame_hw + 2 * c0, h->d_state + (size_t)t0 * 4,
+                                                                 h->cfg.search_factor, kSx, m, h->mw.lut, h->d_crop, nullptr, nullptr,
+                                                                 nullptr, h->d_status + t0, st));
+        VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_tracks_step/stem", launch_stem(h->d_crop, kSx, m, h->mw, h->d_scratch, h->d_tokx, kNx, 0, st));
+        VT_LAUNCH(h, VT_STAGE_BLOCKS, m, st, "vt_tracks_step/blocks", run_blocks(h, h->d_tmpl + (size_t)t0 * kNz * kC, kNz, h->d_tokx, kNx, h->d_tok, m, nullptr, 0, st));
+        HeadArgs a{};
+        a.tokens = h->d_tok; a.n = m;
+        // maps of the last step are kept planar per array: score [max][256] | size [max][512] | offset [max][512]
+        a.score_map = h->d_maps + (size_t)t0 * 256;
+        a.size_map = h->d_maps + (size_t)h->cfg.max_tracks * 256 + (size_t)t0 * 512;
+        a.offset_map = h->d_maps + (size_t)h->cfg.max_tracks * 768 + (size_t)t0 * 512;
+        a.state = h->d_state + (size_t)t0 * 4;
+        a.frame_hw = frame_hw + 2 * c0;
+        a.status = h->d_status + t0;
+        a.out_boxes = out_boxes + (size_t)c0 * 5;
+        a.out_detail = out_detail ? out_detail + (size_t)c0 * 8 : nullptr;
+        a.update_state = update_state;
+        a.search_factor = h->cfg.search_factor;
+        VT_LAUNCH(h, VT_STAGE_HEAD, m, st, "vt_tracks_step/head", launch_head(a, h->mw, st));
+    }
+    h->last_first = first; h->last_n = n;
+    return VT_OK;
+}
+
+int vt_tracks_get_state(VtHandle h, double* boxes_xywh, int32_t first, int32_t n, void* stream) {
+    if (!h) return VT_ERR_INVALID_ARG;
+    if (!boxes_xywh || first < 0 || n < 0 || first + n > h->cfg.max_tracks) return fail(h, VT_ERR_INVALID_ARG, "vt_tracks_get_state: bad range");
+    VT_CUDA(h, cudaMemcpyAsync(boxes_xywh, h->d_state + (size_t)first * 4, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return VT_OK;
+}
+
+int vt_tracks_set_state(VtHandle h, const double* boxes_xywh, int32_t first, int32_t n, void* stream) {
+    if (!h) return VT_ERR_INVALID_ARG;
+    if (!boxes_xywh || first < 0 || n < 0 || first + n > h->cfg.max_tracks) return fail(h, VT_ERR_INVALID_ARG, "vt_tracks_set_state: bad range");
+    VT_CUDA(h, cudaMemcpyAsync(h->d_state + (size_t)first * 4, boxes_xywh, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return VT_OK;
+}
+
+int vt_tracks_last_maps(VtHandle h, int32_t first, int32_t n, float* score_map, float* size_map, float* offset_map, void* stream) {
+    if (!h) return VT_ERR_INVALID_ARG;
+    if (first < h->last_first || n < 0 || first + n > h->last_first + h->last_n) return fail(h, VT_ERR_STATE, "vt_tracks_last_maps: tracks [%d, %d) were not part of the last step", first, first + n);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t mt = h->cfg.max_tracks;
+    if (score_map) VT_CUDA(h, cudaMemcpyAsync(score_map, h->d_maps + (size_t)first * 256, (size_t)n * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (size_map) VT_CUDA(h, cudaMemcpyAsync(size_map, h->d_maps + mt * 256 + (size_t)first * 512, (size_t)n * 512 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (offset_map) VT_CUDA(h, cudaMemcpyAsync(offset_map, h->d_maps + mt * 768 + (size_t)first * 512, (size_t)n * 512 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return VT_OK;
+}
+
+int64_t vt_launch_count(VtHandle h) { return h ? h->launches : 0; }
+
+int vt_profile_enable(VtHandle h, int32_t enable) {
+    if (!h) return VT_ERR_INVALID_ARG;
+    h->profiling = enable != 0;
+    return VT_OK;
+}
+
+int vt_profile_read(VtHandle h, double* stage_ms, int64_t* stage_launches, int64_t* stage_items) {
+    if (!h || !stage_ms || !stage_launches || !stage_items) return h ? fail(h, VT_ERR_INVALID_ARG, "vt_profile_read: null pointer") : VT_ERR_INVALID_ARG;
+    for (int i = 0; i < VT_NUM_STAGES; ++i) { stage_ms[i] = 0.0; stage_launches[i] = 0; stage_items[i] = 0; }
+    for (auto& r : h->prof) {
+        VT_CUDA(h, cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        VT_CUDA(h, cudaEventElapsedTime(&ms, r.a, r.b));
+        if (r.stage >= 0 && r.stage < VT_NUM_STAGES) { stage_ms[r.stage] += ms; stage_launches[r.stage] += 1; stage_items[r.stage] += r.items; }
+        h->evpool.push_back(r.a); h->evpool.push_back(r.b);
+    }
+    h->prof.clear();
+    return VT_OK;
+}
+
+}  // extern "C"

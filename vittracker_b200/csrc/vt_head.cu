@@ -1,0 +1,323 @@
+// K4 + K5: final LayerNorm on the search tokens, CENTER head (three conv towers) and the tracker's
+// post-processing, one CTA per track with every activation resident in shared memory.
+//   forward_head        lib/models/vit_dist/vit_dist.py:94,122-153
+//   CenterPredictor     lib/models/layers/head.py:98-201 (conv+bias -> BN(eval) -> ReLU x4, conv1x1,
+//                       sigmoid+clamp on ctr/size, raw offset; BN folded at weight-pack time)
+//   cal_bbox            lib/models/layers/head.py:142-160 (first arg-max wins)
+//   track() epilogue    lib/test/tracker/vit_dist.py:103-111,147-156 + lib/utils/box_ops.py:97-106
+// The three towers' first convolutions share their input and are merged into one 48->96 layer whose
+// 166 KB of weights are streamed through a double-buffered cp.async ring; later layers reuse the ring.
+#include "vt_geom.cuh"
+#include "vt_internal.h"
+
+namespace vt {
+
+constexpr int kHeadThreads = 256;
+constexpr int kPlane = 18 * 18;                      // zero-bordered 16x16 plane
+constexpr int kWChunk = 3456;                        // floats per streamed weight chunk
+constexpr int kOffFeat = 0;                          // [48][324]  feat, later conv2 output
+constexpr int kOffOut1 = kOffFeat + 48 * kPlane;     // [96][324]  conv1 output, later conv3/conv4 outputs
+constexpr int kOffW = kOffOut1 + 96 * kPlane;        // 2 x kWChunk
+constexpr int kOffBias = kOffW + 2 * kWChunk;        // b1[96] b2[48] b3[24] b4[12] w5[24] b5[6] -> 256
+constexpr int kOffMaps = kOffBias + 256;             // score[256] size[2][256] offset[2][256] resp[256]
+constexpr int kOffRed = kOffMaps + 6 * 256;          // reduction scratch (32 floats)
+constexpr int kHeadFloats = kOffRed + 32;
+constexpr size_t kHeadSmemBytes = (size_t)kHeadFloats * sizeof(float);
+static_assert(kHeadSmemBytes <= 227 * 1024, "head smem");
+
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src_gmem) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// One 3x3 / stride 1 / pad 1 layer on a 16x16 map.  Thread = 4 horizontally adjacent pixels x QT output
+// channels of group g (g = tower when TOWER_IN, else an arbitrary slice of the merged output axis).
+// Weights are streamed from global memory in chunks of CI_CHUNK input channels: [ci][ky*3+kx][NG*QT].
+template <int CIN, int QT, int NG, bool TOWER_IN, int CI_CHUNK>
+__device__ __forceinline__ void head_conv(const float* in, float* outp, const float* __restrict__ wg,
+                                          const float* bias, float* wbuf) {
+    constexpr int kCout = NG * QT;
+    constexpr int kChunkFloats = CI_CHUNK * 9 * kCout;
+    constexpr int kChunks = CIN / CI_CHUNK;
+    static_assert(kChunkFloats <= kWChunk && kChunkFloats % 4 == 0 && CIN % CI_CHUNK == 0, "chunking");
+    const int tid = threadIdx.x;
+    const int pg = tid & 63, g = tid >> 6;
+    const bool active = g < NG;
+    const int y = pg >> 2, x0 = (pg & 3) * 4;
+    const float* inb = in + (TOWER_IN && active ? g * CIN * kPlane : 0) + y * 18 + x0;
+
+    float acc[4][QT];
+#pragma unroll
+    for (int q = 0; q < QT; ++q) {
+        const float b = active ? bias[g * QT + q] : 0.f;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc[p][q] = b;
+    }
+    auto issue = [&](int c) {
+        float* dst = wbuf + (c & 1) * kWChunk;
+        const float* src = wg + (size_t)c * kChunkFloats;
+        for (int i = tid * 4; i < kChunkFloats; i += kHeadThreads * 4) cp_async16(dst + i, src + i);
+        cp_async_commit();
+    };
+    issue(0);
+#pragma unroll 1
+    for (int c = 0; c < kChunks; ++c) {
+        if (c + 1 < kChunks) { issue(c + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        __syncthreads();
+        if (active) {
+            const float* wc = wbuf + (c & 1) * kWChunk + g * QT;
+#pragma unroll 1
+            for (int cl = 0; cl < CI_CHUNK; ++cl) {
+                const float* ip = inb + (c * CI_CHUNK + cl) * kPlane;
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    float xi[6];
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) xi[j] = ip[ky * 18 + j];
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const float* wp = wc + (cl * 9 + ky * 3 + kx) * kCout;
+                        float wv[QT];
+#pragma unroll
+                        for (int q = 0; q < QT; q += 4) {
+                            const float4 t = *reinterpret_cast<const float4*>(wp + q);
+                            wv[q] = t.x; wv[q + 1] = t.y; wv[q + 2] = t.z; wv[q + 3] = t.w;
+                        }
+#pragma unroll
+                        for (int p = 0; p < 4; ++p)
+#pragma unroll
+                            for (int q = 0; q < QT; ++q) acc[p][q] = fmaf(xi[p + kx], wv[q], acc[p][q]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (active) {
+#pragma unroll
+        for (int q = 0; q < QT; ++q) {
+            float* op = outp + (g * QT + q) * kPlane + (y + 1) * 18 + x0 + 1;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) op[p] = fmaxf(acc[p][q], 0.f);          // ReLU
+        }
+    }
+    __syncthreads();
+}
+
+// arg-max with first-index tie-break over 256 values (one per thread); result broadcast to all threads.
+__device__ __forceinline__ void block_argmax256(float v, int idx, float* red, float& best, int& best_idx) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = v; red[8 + (threadIdx.x >> 5)] = __int_as_float(idx); }
+    __syncthreads();
+    best = red[0]; best_idx = __float_as_int(red[8]);
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+        const float ov = red[k]; const int oi = __float_as_int(red[8 + k]);
+        if (ov > best || (ov == best && oi < best_idx)) { best = ov; best_idx = oi; }
+    }
+}
+
+__device__ __forceinline__ float sigmoid_clamp(float v) {
+    const float s = 1.f / (1.f + expf(-v));
+    return fminf(fmaxf(s, 1e-4f), 0.9999f);               // torch.clamp(x.sigmoid_(), 1e-4, 1 - 1e-4)
+}
+
+__global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(HeadArgs a, ModelW w) {
+    extern __shared__ __align__(16) float smem[];
+    float* feat = smem + kOffFeat;
+    float* out1 = smem + kOffOut1;
+    float* wbuf = smem + kOffW;
+    float* sb = smem + kOffBias;
+    float* maps = smem + kOffMaps;
+    float* red = smem + kOffRed;
+    const int trk = blockIdx.x;
+    const int tid = threadIdx.x;
+
+    // zero the activation planes once: layer outputs only ever write interiors, borders stay zero
+    for (int i = tid * 4; i < kOffW; i += kHeadThreads * 4) *reinterpret_cast<float4*>(smem + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < 96) sb[tid] = w.head.b1[tid];
+    if (tid < 48) sb[96 + tid] = w.head.b2[tid];
+    if (tid < 24) sb[144 + tid] = w.head.b3[tid];
+    if (tid < 12) sb[168 + tid] = w.head.b4[tid];
+    if (tid < 24) sb[180 + tid] = w.head.w5[tid];
+    if (tid < 6) sb[204 + tid] = w.head.b5[tid];
+    __syncthreads();
+
+    // ---- final LayerNorm (vit_dist.py:94) on search token `tid`; tokens -> (C,16,16) (vit_dist.py:126-129)
+    {
+        auto norm_row = [&](int row, float (&y)[kC]) {
+            const float* src = a.tokens + ((size_t)trk * kN + row) * kC;
+            float x[kC];
+#pragma unroll
+            for (int k = 0; k < kC; k += 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src + k));
+                x[k] = v.x; x[k + 1] = v.y; x[k + 2] = v.z; x[k + 3] = v.w;
+            }
+            float mean = 0.f;
+#pragma unroll
+            for (int k = 0; k < kC; ++k) mean += x[k];
+            mean *= (1.f / kC);
+            float var = 0.f;
+#pragma unroll
+            for (int k = 0; k < kC; ++k) { const float d = x[k] - mean; var = fmaf(d, d, var); }
+            const float rstd = rsqrtf(var * (1.f / kC) + kLnEps);
+#pragma unroll
+            for (int k = 0; k < kC; ++k) y[k] = (x[k] - mean) * rstd * __ldg(w.norm_g + k) + __ldg(w.norm_b + k);
+            if (a.tokens_norm) {
+                float* t = a.tokens_norm + ((size_t)trk * kN + row) * kC;
+#pragma unroll
+                for (int k = 0; k < kC; k += 4) *reinterpret_cast<float4*>(t + k) = make_float4(y[k], y[k + 1], y[k + 2], y[k + 3]);
+            }
+        };
+        float y[kC];
+        norm_row(kNz + tid, y);
+        const int py = tid >> 4, px = tid & 15;
+#pragma unroll
+        for (int k = 0; k < kC; ++k) feat[k * kPlane + (py + 1) * 18 + px + 1] = y[k];
+        if (a.tokens_norm && tid < kNz) { float yz[kC]; norm_row(tid, yz); }
+    }
+    __syncthreads();
+
+    // ---- conv towers ---------------------------------------------------------------------------
+    head_conv<48, 24, 4, false, 4>(feat, out1, w.head.w1, sb, wbuf);               // 48 -> 3x32 (merged)
+    float* out2 = feat;                                                            // [3][16] planes
+    head_conv<32, 16, 3, true, 8>(out1, out2, w.head.w2, sb + 96, wbuf);           // 32 -> 16 per tower
+    float* out3 = out1;                                                            // [3][8] planes
+    head_conv<16, 8, 3, true, 16>(out2, out3, w.head.w3, sb + 144, wbuf);          // 16 -> 8
+    float* out4 = out1 + 24 * kPlane;                                              // [3][4] planes
+    head_conv<8, 4, 3, true, 8>(out3, out4, w.head.w4, sb + 168, wbuf);            // 8 -> 4
+
+    // ---- conv5 (1x1) + sigmoid/clamp: thread = pixel ---------------------------------------------
+    float* m_score = maps; float* m_size = maps + 256; float* m_off = maps + 768; float* m_resp = maps + 1280;
+    {
+        const int py = tid >> 4, px = tid & 15;
+        const float* ip = out4 + (py + 1) * 18 + px + 1;
+        const float* w5 = sb + 180; const float* b5 = sb + 204;
+        float o[3][2];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            o[t][0] = b5[t * 2]; o[t][1] = b5[t * 2 + 1];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float v = ip[(t * 4 + c) * kPlane];
+                o[t][0] = fmaf(v, w5[(t * 4 + c) * 2], o[t][0]);
+                o[t][1] = fmaf(v, w5[(t * 4 + c) * 2 + 1], o[t][1]);
+            }
+        }
+        const float sc = sigmoid_clamp(o[0][0]);
+        const float sw = sigmoid_clamp(o[2][0]), sh = sigmoid_clamp(o[2][1]);
+        m_score[tid] = sc; m_size[tid] = sw; m_size[256 + tid] = sh;
+        m_off[tid] = o[1][0]; m_off[256 + tid] = o[1][1];
+        m_resp[tid] = __ldg(w.hann + tid) * sc;                               // output_window * score_map
+        if (a.score_map) a.score_map[(size_t)trk * 256 + tid] = sc;
+        if (a.size_map) { a.size_map[(size_t)trk * 512 + tid] = sw; a.size_map[(size_t)trk * 512 + 256 + tid] = sh; }
+        if (a.offset_map) { a.offset_map[(size_t)trk * 512 + tid] = o[1][0]; a.offset_map[(size_t)trk * 512 + 256 + tid] = o[1][1]; }
+    }
+    __syncthreads();
+
+    // ---- cal_bbox on the raw score (forward's pred_boxes) and on the windowed response (tracker) ----
+    float raw_max; int raw_idx;
+    block_argmax256(m_score[tid], tid, red, raw_max, raw_idx);
+    float win_max; int win_idx;
+    block_argmax256(m_resp[tid], tid, red, win_max, win_idx);
+    if (tid != 0) return;
+
+    if (a.pred_boxes) {
+        float* pb = a.pred_boxes + (size_t)trk * 4;
+        pb[0] = ((float)(raw_idx & 15) + m_off[raw_idx]) / 16.f;
+        pb[1] = ((float)(raw_idx >> 4) + m_off[256 + raw_idx]) / 16.f;
+        pb[2] = m_size[raw_idx];
+        pb[3] = m_size[256 + raw_idx];
+    }
+    if (a.state) {
+        double* st = a.state + (size_t)trk * 4;
+        const double sx = st[0], sy = st[1], sw = st[2], sh = st[3];
+        const int H = a.frame_hw[2 * trk], W = a.frame_hw[2 * trk + 1];
+        const CropGeom g = crop_geometry(sx, sy, sw, sh, a.search_factor, kSx, H, W);
+        const int status = a.status ? a.status[trk] : g.status;
+        double* ob = a.out_boxes + (size_t)trk * 5;
+        double* od = a.out_detail ? a.out_detail + (size_t)trk * 8 : nullptr;
+        if (status != 0) {            // the reference raises here; keep the state and flag the track
+            ob[0] = sx; ob[1] = sy; ob[2] = sw; ob[3] = sh; ob[4] = -1.0;
+            if (od) { od[0] = od[1] = od[2] = od[3] = 0.0; od[4] = g.resize_factor; od[5] = -1.0; od[6] = (double)status; od[7] = 0.0; }
+            return;
+        }
+        // pred_box = (pred_boxes.mean(0) * search_size / resize_factor).tolist()   (fp32 on the device)
+        const float rf32 = (float)g.resize_factor;
+        const float bx = ((float)(win_idx & 15) + m_off[win_idx]) / 16.f;
+        const float by = ((float)(win_idx >> 4) + m_off[256 + win_idx]) / 16.f;
+        const float pcx = __fdiv_rn(__fmul_rn(bx, 256.f), rf32);
+        const float pcy = __fdiv_rn(__fmul_rn(by, 256.f), rf32);
+        const float pw = __fdiv_rn(__fmul_rn(m_size[win_idx], 256.f), rf32);
+        const float ph = __fdiv_rn(__fmul_rn(m_size[256 + win_idx], 256.f), rf32);
+        // map_box_back (float64, Python semantics)
+        const double cx_prev = __dadd_rn(sx, __dmul_rn(0.5, sw)), cy_prev = __dadd_rn(sy, __dmul_rn(0.5, sh));
+        const double half_side = __ddiv_rn(__dmul_rn(0.5, (double)kSx), g.resize_factor);
+        const double cx_real = __dadd_rn((double)pcx, __dsub_rn(cx_prev, half_side));
+        const double cy_real = __dadd_rn((double)pcy, __dsub_rn(cy_prev, half_side));
+        double x1 = __dsub_rn(cx_real, __dmul_rn(0.5, (double)pw));
+        double y1 = __dsub_rn(cy_real, __dmul_rn(0.5, (double)ph));
+        double bw = (double)pw, bh = (double)ph;
+        // clip_box(box, H, W, margin=10)
+        double x2 = __dadd_rn(x1, bw), y2 = __dadd_rn(y1, bh);
+        x1 = fmin(fmax(0.0, x1), (double)(W - 10));
+        x2 = fmin(fmax(10.0, x2), (double)W);
+        y1 = fmin(fmax(0.0, y1), (double)(H - 10));
+        y2 = fmin(fmax(10.0, y2), (double)H);
+        bw = fmax(10.0, __dsub_rn(x2, x1));
+        bh = fmax(10.0, __dsub_rn(y2, y1));
+        ob[0] = x1; ob[1] = y1; ob[2] = bw; ob[3] = bh; ob[4] = (double)raw_max;
+        if (od) {
+            od[0] = (double)pcx; od[1] = (double)pcy; od[2] = (double)pw; od[3] = (double)ph;
+            od[4] = g.resize_factor; od[5] = (double)win_idx; od[6] = 0.0; od[7] = (double)win_max;
+        }
+        if (a.update_state) { st[0] = x1; st[1] = y1; st[2] = bw; st[3] = bh; }
+    }
+}
+
+int launch_head(const HeadArgs& a, const ModelW& w, cudaStream_t st) {
+    if (a.n <= 0) return 0;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmemBytes) != cudaSuccess) return -1;
+        configured = true;
+    }
+    head_kernel<<<a.n, kHeadThreads, kHeadSmemBytes, st>>>(a, w);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// box_head.cal_bbox(score, size_map, offset_map) on caller-provided maps (head.py:142-160).
+__global__ void __launch_bounds__(256) cal_bbox_kernel(const float* __restrict__ score, const float* __restrict__ size_map,
+                                                      const float* __restrict__ offset_map, float* __restrict__ boxes) {
+    __shared__ float red[32];
+    const int trk = blockIdx.x, tid = threadIdx.x;
+    float best; int idx;
+    block_argmax256(score[(size_t)trk * 256 + tid], tid, red, best, idx);
+    if (tid == 0) {
+        const float* sz = size_map + (size_t)trk * 512;
+        const float* of = offset_map + (size_t)trk * 512;
+        float* pb = boxes + (size_t)trk * 4;
+        pb[0] = ((float)(idx & 15) + of[idx]) / 16.f;
+        pb[1] = ((float)(idx >> 4) + of[256 + idx]) / 16.f;
+        pb[2] = sz[idx];
+        pb[3] = sz[256 + idx];
+    }
+}
+
+int launch_cal_bbox(const float* score, const float* size_map, const float* offset_map, int n, float* boxes,
+                    cudaStream_t st) {
+    if (n <= 0) return 0;
+    cal_bbox_kernel<<<n, 256, 0, st>>>(score, size_map, offset_map, boxes);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+}  // namespace vt

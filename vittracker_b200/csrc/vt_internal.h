@@ -1,0 +1,91 @@
+// Internal declarations shared by the kernels and the C-ABI layer of libvittrack_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vt {
+
+// ---- vit_48_h32_noKD dimensions (experiments/vit_dist/vit_48_h32_noKD.yaml) -------------------
+constexpr int kC = 48;          // embed dim
+constexpr int kNz = 64;         // template tokens (128/16)^2
+constexpr int kNx = 256;        // search tokens   (256/16)^2
+constexpr int kN = kNz + kNx;   // 320
+constexpr int kHid = 192;       // MLP hidden
+constexpr int kDepth = 3;
+constexpr int kFeat = 16;       // search feature map side
+constexpr int kHeadC = 32;      // head tower width
+constexpr int kTz = 128;        // template crop side
+constexpr int kSx = 256;        // search crop side
+constexpr float kLnEps = 1e-5f;
+
+// ---- packed weights (device, fp32) --------------------------------------------------------------
+struct StemLayerW {          // conv3x3 s2 p1 with BN folded
+    const float* w;          // [cin][3][3][cout]
+    const float* b;          // [cout]
+};
+
+struct BlockW {              // timm Block, weights stored K-major ("transposed": [in][out])
+    const float *ln1_g, *ln1_b;
+    const float *wqkv, *bqkv;      // [48][144], [144]
+    const float *wproj, *bproj;    // [48][48], [48]
+    const float *ln2_g, *ln2_b;
+    const float *wfc1, *bfc1;      // [48][192], [192]
+    const float *wfc2, *bfc2;      // [192][48], [48]
+};
+
+struct HeadW {               // CENTER head, BN folded, towers ordered ctr, offset, size
+    const float *w1, *b1;    // [48][9][96], [96]      (3 towers x 32 merged on the output axis)
+    const float *w2, *b2;    // [32][9][3][16], [48]
+    const float *w3, *b3;    // [16][9][3][8],  [24]
+    const float *w4, *b4;    // [8][9][3][4],   [12]
+    const float *w5, *b5;    // [3][4][2] (ctr uses column 0), [3][2]
+};
+
+struct ModelW {
+    StemLayerW stem[4];
+    BlockW blk[kDepth];
+    const float *norm_g, *norm_b;
+    const float *pos_z, *pos_x;    // [64][48], [256][48]
+    HeadW head;
+    const float* hann;             // [256] fp32 window (lib/test/utils/hann.py)
+    const float* lut;              // [3][256] normalisation table ((v/255 - mean)/std)
+};
+
+// ---- kernel launchers (each returns the number of kernels it launched, or <0 on a CUDA error) -----
+int launch_crop_normalize(const uint8_t* frames, const int64_t* frame_offsets, const int32_t* frame_hw,
+                          const double* boxes, double factor, int S, int n, const float* lut,
+                          float* out_nchw, uint8_t* out_u8, uint8_t* out_mask, double* out_rf,
+                          int32_t* out_status, cudaStream_t st);
+
+// Stem on `n` images of side S (128 or 256): in NCHW fp32 -> tokens[(b*tok_stride) + tok_off + t][48] (+pos).
+// scratch must hold n * stem_scratch_floats(S) floats.
+size_t stem_scratch_floats(int S);
+int launch_stem(const float* img, int S, int n, const ModelW& w, float* scratch, float* tokens,
+                int tok_stride_rows, int tok_off, cudaStream_t st);
+
+// ViT blocks (fp32 SIMT): tokens_z [n][64][48] (stride z_stride rows per track), tokens_x likewise; in place
+// result written to out [n][320][48]; taps (or null) receives [depth][n][320][48].
+int launch_blocks_simt(const float* tok_z, int z_stride_rows, const float* tok_x, int x_stride_rows,
+                       float* out, int n, const ModelW& w, float* taps, size_t tap_stride, cudaStream_t st);
+
+struct HeadArgs {
+    const float* tokens;      // [n][320][48] block output (pre final-norm)
+    int n;
+    // forward outputs (nullable)
+    float *pred_boxes, *score_map, *size_map, *offset_map;   // [n][4], [n][256], [n][2][256], [n][2][256]
+    float* tokens_norm;       // [n][320][48] tap (nullable)
+    // tracker outputs (nullable as a group: enabled when state != nullptr)
+    double* state;            // [n][4] previous boxes, updated in place when update_state
+    const int32_t* frame_hw;  // [n][2]
+    const int32_t* status;    // [n] VT_TRACK_* from the crop stage (nullable)
+    double* out_boxes;        // [n][5]
+    double* out_detail;       // [n][8] (nullable)
+    int update_state;
+    double search_factor;
+};
+int launch_head(const HeadArgs& a, const ModelW& w, cudaStream_t st);
+
+int launch_cal_bbox(const float* score, const float* size_map, const float* offset_map, int n, float* boxes,
+                    cudaStream_t st);
+
+}  // namespace vt

@@ -1,0 +1,199 @@
+// K2: LeViT-style conv stem - 4x [conv3x3 stride 2 pad 1 (no bias) + BatchNorm(eval)], Hardswish
+// after the first three (lib/models/vit_dist/vit_dist.py:10-54), BN folded into the convolution
+// at weight-pack time, fp32 direct convolution on CUDA cores.
+//
+// One templated tile kernel serves all four layers.  A CTA stages a (2*TH+1) x (2*TW+1) x CIN
+// input tile in shared memory with even and odd columns de-interleaved, so that the stride-2 reads
+// of a warp (lanes = consecutive output columns) are stride-1 and bank-conflict free.  Weights sit
+// in shared memory as [cin][ky][kx][cout]; a thread owns P output pixels x QG output channels and
+// reads its weights with broadcast vector loads.  The last layer writes tokens (row = y*16+x,
+// token-major [token][48]) with the positional embedding added (vit_dist.py:53,81-82).
+#include "vt_internal.h"
+
+namespace vt {
+
+template <int CIN, int COUT, int QG, int P, int TW, int TH>
+struct ConvCfg {
+    static constexpr int kPixGroups = TW * TH / P;
+    static constexpr int kChGroups = COUT / QG;
+    static constexpr int kThreads = kPixGroups * kChGroups;
+    static constexpr int kInRows = 2 * TH + 1;
+    static constexpr int kEven = TW + 1;                   // even input columns 0,2,..,2*TW
+    static constexpr int kPitchRaw = 2 * TW + 1;
+    // TW == 16: two output rows share a warp -> row pitch must be == 8 (mod 16) to stay conflict free
+    static constexpr int kPitch = (TW == 32) ? kPitchRaw : ((kPitchRaw - 8 + 15) / 16 * 16 + 8);
+    static constexpr int kTileFloats = (CIN * kInRows * kPitch + 3) / 4 * 4;   // keeps the weights 16-byte aligned
+    static constexpr int kWFloats = CIN * 9 * COUT;
+    static constexpr size_t kSmemBytes = (size_t)(kTileFloats + kWFloats + COUT) * sizeof(float);
+    static_assert(kPixGroups % 32 == 0, "channel group must be warp uniform");
+    static_assert(32 % TW == 0 && (TW == 16 || TW == 32), "tile width");
+    static_assert(COUT % QG == 0 && QG % 2 == 0, "channel grouping");
+};
+
+template <int CIN, int COUT, int QG, int P, int TW, int TH, bool HSWISH, bool TOKENS>
+__global__ void __launch_bounds__(ConvCfg<CIN, COUT, QG, P, TW, TH>::kThreads)
+conv3x3s2_kernel(const float* __restrict__ in, int Hin, int Win, const float* __restrict__ wg,
+                 const float* __restrict__ bg, float* __restrict__ out, const float* __restrict__ pos,
+                 int tok_stride_rows, int tok_off) {
+    using K = ConvCfg<CIN, COUT, QG, P, TW, TH>;
+    extern __shared__ __align__(16) float smem[];
+    float* tile = smem;
+    float* ws = smem + K::kTileFloats;
+    float* bs = ws + K::kWFloats;
+
+    const int Hout = Hin >> 1, Wout = Win >> 1;
+    const int tiles_x = (Wout + TW - 1) / TW;
+    const int tx0 = (blockIdx.x % tiles_x) * TW;
+    const int ty0 = (blockIdx.x / tiles_x) * TH;
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < K::kWFloats; i += K::kThreads) ws[i] = wg[i];
+    for (int i = tid; i < COUT; i += K::kThreads) bs[i] = bg[i];
+
+    // stage the input tile: tile column c <-> input column 2*tx0 - 1 + c, row r <-> 2*ty0 - 1 + r
+    const float* inb = in + (size_t)b * CIN * Hin * Win;
+    const int ix0 = 2 * tx0 - 1, iy0 = 2 * ty0 - 1;
+    for (int i = tid; i < CIN * K::kInRows * K::kPitchRaw; i += K::kThreads) {
+        const int c = i % K::kPitchRaw;
+        const int r = (i / K::kPitchRaw) % K::kInRows;
+        const int ci = i / (K::kPitchRaw * K::kInRows);
+        const int gx = ix0 + c, gy = iy0 + r;
+        float v = 0.f;
+        if (gx >= 0 && gx < Win && gy >= 0 && gy < Hin) v = __ldg(inb + ((size_t)ci * Hin + gy) * Win + gx);
+        const int slot = (c & 1) ? (K::kEven + (c >> 1)) : (c >> 1);
+        tile[(ci * K::kInRows + r) * K::kPitch + slot] = v;
+    }
+    __syncthreads();
+
+    const int cg = tid / K::kPixGroups;                 // warp-uniform channel group
+    const int pg = tid % K::kPixGroups;
+    const int lane = pg & 31, wq = pg >> 5;
+    constexpr int kRowsPerWarp = 32 / TW;
+    const int lx = lane % TW;
+    int ly[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) ly[p] = (wq * P + p) * kRowsPerWarp + lane / TW;
+
+    float acc[P][QG];
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+#pragma unroll
+        for (int q = 0; q < QG; ++q) acc[p][q] = bs[cg * QG + q];
+
+#pragma unroll 1
+    for (int ci = 0; ci < CIN; ++ci) {
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            float xin[P][3];
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const float* row = tile + (ci * K::kInRows + 2 * ly[p] + ky) * K::kPitch;
+                xin[p][0] = row[lx];                     // input col 2x   (even slot x)
+                xin[p][1] = row[K::kEven + lx];          // input col 2x+1 (odd slot x)
+                xin[p][2] = row[lx + 1];                 // input col 2x+2 (even slot x+1)
+            }
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float* wp = ws + ((ci * 3 + ky) * 3 + kx) * COUT + cg * QG;
+                float wv[QG];
+                if constexpr (QG % 4 == 0 && (COUT % 4) == 0) {
+#pragma unroll
+                    for (int q = 0; q < QG; q += 4) {
+                        const float4 t = *reinterpret_cast<const float4*>(wp + q);
+                        wv[q] = t.x; wv[q + 1] = t.y; wv[q + 2] = t.z; wv[q + 3] = t.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < QG; q += 2) {
+                        const float2 t = *reinterpret_cast<const float2*>(wp + q);
+                        wv[q] = t.x; wv[q + 1] = t.y;
+                    }
+                }
+#pragma unroll
+                for (int p = 0; p < P; ++p)
+#pragma unroll
+                    for (int q = 0; q < QG; ++q) acc[p][q] = fmaf(xin[p][kx], wv[q], acc[p][q]);
+            }
+        }
+    }
+
+    const int ox = tx0 + lx;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        const int oy = ty0 + ly[p];
+        if (ox >= Wout || oy >= Hout) continue;
+#pragma unroll
+        for (int q = 0; q < QG; ++q) {
+            float v = acc[p][q];
+            if (HSWISH) v = v * fminf(fmaxf(v + 3.f, 0.f), 6.f) / 6.f;     // x * relu6(x + 3) / 6
+            acc[p][q] = v;
+        }
+        if (TOKENS) {
+            const int t = oy * Wout + ox;
+            float* o = out + ((size_t)b * tok_stride_rows + tok_off + t) * COUT + cg * QG;
+            const float* pe = pos + (size_t)t * COUT + cg * QG;
+#pragma unroll
+            for (int q = 0; q < QG; q += 4) {
+                const float4 e = *reinterpret_cast<const float4*>(pe + q);
+                float4 r = make_float4(acc[p][q] + e.x, acc[p][q + 1] + e.y, acc[p][q + 2] + e.z, acc[p][q + 3] + e.w);
+                *reinterpret_cast<float4*>(o + q) = r;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < QG; ++q)
+                out[(((size_t)b * COUT + cg * QG + q) * Hout + oy) * Wout + ox] = acc[p][q];
+        }
+    }
+}
+
+template <int CIN, int COUT, int QG, int P, int TW, int TH, bool HSWISH, bool TOKENS>
+static int run_conv(const float* in, int Hin, int n, const StemLayerW& w, float* out, const float* pos,
+                    int tok_stride_rows, int tok_off, cudaStream_t st) {
+    using K = ConvCfg<CIN, COUT, QG, P, TW, TH>;
+    auto kern = conv3x3s2_kernel<CIN, COUT, QG, P, TW, TH, HSWISH, TOKENS>;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::kSmemBytes) != cudaSuccess) return -1;
+        configured = true;
+    }
+    const int Hout = Hin / 2;
+    const int tiles = ((Hout + TW - 1) / TW) * ((Hout + TH - 1) / TH);
+    int launched = 0;
+    for (int first = 0; first < n; first += 32768) {
+        const int m = min(32768, n - first);
+        dim3 grid(tiles, m);
+        const float* inp = in + (size_t)first * CIN * Hin * Hin;
+        float* o = TOKENS ? out + (size_t)first * tok_stride_rows * COUT : out + (size_t)first * COUT * Hout * Hout;
+        kern<<<grid, K::kThreads, K::kSmemBytes, st>>>(inp, Hin, Hin, w.w, w.b, o, pos, tok_stride_rows, tok_off);
+        ++launched;
+    }
+    return cudaGetLastError() == cudaSuccess ? launched : -1;
+}
+
+size_t stem_scratch_floats(int S) {
+    // conv1 out 6 x S/2 x S/2, conv2 out 12 x S/4 x S/4, conv3 out 24 x S/8 x S/8
+    return (size_t)6 * (S / 2) * (S / 2) + (size_t)12 * (S / 4) * (S / 4) + (size_t)24 * (S / 8) * (S / 8);
+}
+
+int launch_stem(const float* img, int S, int n, const ModelW& w, float* scratch, float* tokens,
+                int tok_stride_rows, int tok_off, cudaStream_t st) {
+    if (n <= 0) return 0;
+    float* a1 = scratch;
+    float* a2 = a1 + (size_t)n * 6 * (S / 2) * (S / 2);
+    float* a3 = a2 + (size_t)n * 12 * (S / 4) * (S / 4);
+    const float* pos = (S == kSx) ? w.pos_x : w.pos_z;
+    int total = 0, r;
+    //                CIN COUT QG P  TW  TH  hswish tokens
+    if ((r = run_conv<3, 6, 6, 4, 32, 32, true, false>(img, S, n, w.stem[0], a1, nullptr, 0, 0, st)) < 0) return r;
+    total += r;
+    if ((r = run_conv<6, 12, 12, 2, 32, 16, true, false>(a1, S / 2, n, w.stem[1], a2, nullptr, 0, 0, st)) < 0) return r;
+    total += r;
+    if ((r = run_conv<12, 24, 12, 2, 32, 8, true, false>(a2, S / 4, n, w.stem[2], a3, nullptr, 0, 0, st)) < 0) return r;
+    total += r;
+    if ((r = run_conv<24, 48, 12, 4, 16, 16, false, true>(a3, S / 8, n, w.stem[3], tokens, pos, tok_stride_rows, tok_off, st)) < 0) return r;
+    total += r;
+    return total;
+}
+
+}  // namespace vt
