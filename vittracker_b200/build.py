@@ -37,7 +37,7 @@ def _sources():
 
 def _digest() -> str:
     h = hashlib.sha256()
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(f for f in NVCC_FLAGS if f != INCLUDE).encode())
     files = sorted(os.listdir(CSRC)) + [os.path.join(INCLUDE, f) for f in sorted(os.listdir(INCLUDE))]
     for f in files:
         p = f if os.path.isabs(f) else os.path.join(CSRC, f)
