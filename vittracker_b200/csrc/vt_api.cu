@@ -1,5 +1,6 @@
 // C-ABI layer of libvittrack_b200.so: handle, weight ingestion (BN folding + layout packing),
 // workspace, and the entry points declared in include/vittrack_b200.h.
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -38,12 +39,13 @@ struct VtContext {
     ModelW mw{};
 
     int chunk = 0;
+    int num_sms = 148;
     // chunk workspace
     float* d_crop = nullptr;          // [chunk][3][256][256]
     float* d_scratch = nullptr;       // stem intermediates
     float* d_tokz = nullptr;          // [chunk][64][48]   (vt_forward only)
-    float* d_tokx = nullptr;          // [chunk][256][48]
-    float* d_tok = nullptr;           // [chunk][320][48]
+    float* d_tokx = nullptr;          // [max_tracks][256][48]
+    float* d_tok = nullptr;           // [max_tracks][320][48]
     // per-track state
     double* d_state = nullptr;        // [max_tracks][4]
     float* d_tmpl = nullptr;          // [max_tracks][64][48] cached template tokens (+pos)
@@ -185,7 +187,7 @@ int run_blocks(VtHandle h, const float* tokz, int zs, const float* tokx, int xs,
                size_t tap_stride, cudaStream_t st) {
     if (h->cfg.blocks_impl == VT_BLOCKS_SIMT_FP32)
         return launch_blocks_simt(tokz, zs, tokx, xs, out, n, h->mw, taps, tap_stride, st);
-    return -2;
+    return launch_blocks_tc(tokz, zs, tokx, xs, out, n, h->mw, taps, tap_stride, h->num_sms, st);
 }
 
 }  // namespace
@@ -220,6 +222,7 @@ int vt_create(const VtConfig* cfg, VtHandle* out) {
 
     VtHandle h = new VtContext();
     h->cfg = *cfg;
+    h->num_sms = prop.multiProcessorCount;
     h->chunk = cfg->chunk_tracks > 0 ? cfg->chunk_tracks : 256;
     if (h->chunk > cfg->max_tracks) h->chunk = cfg->max_tracks;
     if (cudaSetDevice(cfg->device) != cudaSuccess) { delete h; return fail(nullptr, VT_ERR_CUDA, "cudaSetDevice failed"); }
@@ -229,8 +232,8 @@ int vt_create(const VtConfig* cfg, VtHandle* out) {
     A((void**)&h->d_crop, ch * 3 * kSx * kSx * sizeof(float));
     A((void**)&h->d_scratch, ch * stem_scratch_floats(kSx) * sizeof(float));
     A((void**)&h->d_tokz, ch * kNz * kC * sizeof(float));
-    A((void**)&h->d_tokx, ch * kNx * kC * sizeof(float));
-    A((void**)&h->d_tok, ch * kN * kC * sizeof(float));
+    A((void**)&h->d_tokx, mt * kNx * kC * sizeof(float));     // whole-step buffers: blocks + head run once per step
+    A((void**)&h->d_tok, mt * kN * kC * sizeof(float));
     A((void**)&h->d_state, mt * 4 * sizeof(double));
     A((void**)&h->d_tmpl, mt * kNz * kC * sizeof(float));
     A((void**)&h->d_status, mt * sizeof(int32_t));
@@ -334,6 +337,37 @@ int vt_finalize_weights(VtHandle h, void* stream) {
         bo[b].wfc2 = slot(kHid * kC); transp(bo[b].wfc2, T(p + "mlp.fc2.weight"), kC, kHid);
         bo[b].bfc2 = slot(kC); copyv(bo[b].bfc2, T(p + "mlp.fc2.bias"), kC);
     }
+    // ---- tensor-core operands: fp16 hi/lo split, UMMA no-swizzle K-major [k/8][n][8] ------------------
+    size_t tc_wa[kDepth], tc_wb[kDepth], tc_par[kDepth];
+    auto pack_kmajor = [&](uint8_t* dst_hi, uint8_t* dst_lo, const float* W, int N, int K) {   // W: [N][K] (torch Linear weight)
+        for (int n = 0; n < N; ++n)
+            for (int k = 0; k < K; ++k) {
+                const float v = W[(size_t)n * K + k];
+                const __half hi = __float2half_rn(v);
+                const __half lo = __float2half_rn(v - __half2float(hi));
+                const size_t off = ((size_t)(k / 8) * N + n) * 16 + (k % 8) * 2;
+                memcpy(dst_hi + off, &hi, 2);
+                memcpy(dst_lo + off, &lo, 2);
+            }
+    };
+    for (int b = 0; b < kDepth; ++b) {
+        const std::string p = "blocks." + std::to_string(b) + ".";
+        tc_wa[b] = slot(kTcWaBytes / 4); tc_wb[b] = slot(kTcWbBytes / 4); tc_par[b] = slot(kTcParFloats);
+        const float *wqkv = T(p + "attn.qkv.weight"), *wproj = T(p + "attn.proj.weight"), *w1 = T(p + "mlp.fc1.weight"), *w2 = T(p + "mlp.fc2.weight");
+        if (!(wqkv && wproj && w1 && w2)) continue;
+        uint8_t* wa = reinterpret_cast<uint8_t*>(&pk.buf[tc_wa[b]]);
+        uint8_t* wb = reinterpret_cast<uint8_t*>(&pk.buf[tc_wb[b]]);
+        pack_kmajor(wa, wa + 13824, wqkv, 144, 48);
+        pack_kmajor(wa + 27648, wa + 27648 + 4608, wproj, 48, 48);
+        pack_kmajor(wb, wb + 18432, w1, 192, 48);
+        pack_kmajor(wb + 36864, wb + 36864 + 18432, w2, 48, 192);
+        float* par = &pk.buf[tc_par[b]];
+        const float* src[8] = {T(p + "norm1.weight"), T(p + "norm1.bias"), T(p + "attn.qkv.bias"), T(p + "attn.proj.bias"),
+                               T(p + "norm2.weight"), T(p + "norm2.bias"), T(p + "mlp.fc1.bias"), T(p + "mlp.fc2.bias")};
+        const int cnt[8] = {48, 48, 144, 48, 48, 48, 192, 48};
+        int o = 0;
+        for (int i = 0; i < 8; ++i) { if (src[i]) memcpy(par + o, src[i], cnt[i] * sizeof(float)); o += cnt[i]; }
+    }
     const size_t o_ng = slot(kC), o_nb = slot(kC), o_pz = slot(kNz * kC), o_px = slot(kNx * kC);
     copyv(o_ng, T("norm.weight"), kC); copyv(o_nb, T("norm.bias"), kC);
     copyv(o_pz, T("pos_embed_z"), kNz * kC); copyv(o_px, T("pos_embed_x"), kNx * kC);
@@ -409,6 +443,11 @@ int vt_finalize_weights(VtHandle h, void* stream) {
         B.ln1_g = base + bo[b].ln1g; B.ln1_b = base + bo[b].ln1b; B.wqkv = base + bo[b].wqkv; B.bqkv = base + bo[b].bqkv;
         B.wproj = base + bo[b].wproj; B.bproj = base + bo[b].bproj; B.ln2_g = base + bo[b].ln2g; B.ln2_b = base + bo[b].ln2b;
         B.wfc1 = base + bo[b].wfc1; B.bfc1 = base + bo[b].bfc1; B.wfc2 = base + bo[b].wfc2; B.bfc2 = base + bo[b].bfc2;
+    }
+    for (int b = 0; b < kDepth; ++b) {
+        m.tc[b].wa = reinterpret_cast<const uint8_t*>(base + tc_wa[b]);
+        m.tc[b].wb = reinterpret_cast<const uint8_t*>(base + tc_wb[b]);
+        m.tc[b].par = base + tc_par[b];
     }
     m.norm_g = base + o_ng; m.norm_b = base + o_nb; m.pos_z = base + o_pz; m.pos_x = base + o_px;
     m.head.w1 = base + hw[0]; m.head.b1 = base + hb[0]; m.head.w2 = base + hw[1]; m.head.b2 = base + hb[1];
@@ -503,25 +542,31 @@ int vt_tracks_step(VtHandle h, const uint8_t* frames, const int64_t* frame_offse
     if (first < 0 || n < 0 || first + n > h->cfg.max_tracks) return fail(h, VT_ERR_INVALID_ARG, "vt_tracks_step: tracks [%d, %d) exceed max_tracks %d", first, first + n, h->cfg.max_tracks);
     cudaStream_t st = (cudaStream_t)stream;
     VT_CUDA(h, cudaSetDevice(h->cfg.device));
+    // crop + stem run per chunk (their intermediates are large); blocks + head run once over all n tracks
     for (int c0 = 0; c0 < n; c0 += h->chunk) {
         const int m = (n - c0 < h->chunk) ? n - c0 : h->chunk;
         const int t0 = first + c0;
-        VT_LAUNCH(h, VT_STAGE_CROP, m, st, "vt_tracks_step/crop", launch_crop_normalize(frames, frame_offsets + c0, frame_hw + 2 * c0, h->d_state + (size_t)t0 * 4,
-                                                                 h->cfg.search_factor, kSx, m, h->mw.lut, h->d_crop, nullptr, nullptr,
-                                                                 nullptr, h->d_status + t0, st));
-        VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_tracks_step/stem", launch_stem(h->d_crop, kSx, m, h->mw, h->d_scratch, h->d_tokx, kNx, 0, st));
-        VT_LAUNCH(h, VT_STAGE_BLOCKS, m, st, "vt_tracks_step/blocks", run_blocks(h, h->d_tmpl + (size_t)t0 * kNz * kC, kNz, h->d_tokx, kNx, h->d_tok, m, nullptr, 0, st));
+        VT_LAUNCH(h, VT_STAGE_CROP, m, st, "vt_tracks_step/crop",
+                  launch_crop_normalize(frames, frame_offsets + c0, frame_hw + 2 * c0, h->d_state + (size_t)t0 * 4, h->cfg.search_factor,
+                                        kSx, m, h->mw.lut, h->d_crop, nullptr, nullptr, nullptr, h->d_status + t0, st));
+        VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_tracks_step/stem",
+                  launch_stem(h->d_crop, kSx, m, h->mw, h->d_scratch, h->d_tokx + (size_t)c0 * kNx * kC, kNx, 0, st));
+    }
+    {
+        const int m = n;
+        VT_LAUNCH(h, VT_STAGE_BLOCKS, m, st, "vt_tracks_step/blocks",
+                  run_blocks(h, h->d_tmpl + (size_t)first * kNz * kC, kNz, h->d_tokx, kNx, h->d_tok, m, nullptr, 0, st));
         HeadArgs a{};
         a.tokens = h->d_tok; a.n = m;
         // maps of the last step are kept planar per array: score [max][256] | size [max][512] | offset [max][512]
-        a.score_map = h->d_maps + (size_t)t0 * 256;
-        a.size_map = h->d_maps + (size_t)h->cfg.max_tracks * 256 + (size_t)t0 * 512;
-        a.offset_map = h->d_maps + (size_t)h->cfg.max_tracks * 768 + (size_t)t0 * 512;
-        a.state = h->d_state + (size_t)t0 * 4;
-        a.frame_hw = frame_hw + 2 * c0;
-        a.status = h->d_status + t0;
-        a.out_boxes = out_boxes + (size_t)c0 * 5;
-        a.out_detail = out_detail ? out_detail + (size_t)c0 * 8 : nullptr;
+        a.score_map = h->d_maps + (size_t)first * 256;
+        a.size_map = h->d_maps + (size_t)h->cfg.max_tracks * 256 + (size_t)first * 512;
+        a.offset_map = h->d_maps + (size_t)h->cfg.max_tracks * 768 + (size_t)first * 512;
+        a.state = h->d_state + (size_t)first * 4;
+        a.frame_hw = frame_hw;
+        a.status = h->d_status + first;
+        a.out_boxes = out_boxes;
+        a.out_detail = out_detail;
         a.update_state = update_state;
         a.search_factor = h->cfg.search_factor;
         VT_LAUNCH(h, VT_STAGE_HEAD, m, st, "vt_tracks_step/head", launch_head(a, h->mw, st));

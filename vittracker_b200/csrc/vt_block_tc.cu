@@ -1,0 +1,483 @@
+// K3 (tensor-core variant): the three ViT blocks on tcgen05 tensor cores with TMEM accumulators.
+//   x = x + proj(softmax((q*48^-0.5) k^T) v),  [q;k;v] = qkv(LN(x));   x = x + fc2(GELU_erf(fc1(LN(x))))
+// (lib/models/vit_dist/vit_dist.py:84,88-89; timm Block restated at tracking/onnxexport.py:126-225)
+//
+// One persistent CTA per SM walks over tracks.  A track's 320 tokens form three M=128 row tiles
+// (the third is half padding).  Every contraction is a chain of tcgen05.mma (kind::f16, M=128,
+// fp32 accumulate in TMEM) whose A operand is read FROM TMEM and whose B operand (weights, K, V) is
+// read from shared memory through no-swizzle UMMA descriptors:
+//   - the epilogue threads read an accumulator row with tcgen05.ld (TMEM lane = token row), apply
+//     bias / LayerNorm / softmax / GELU in fp32, split the result into fp16 hi + lo and write it back
+//     to TMEM with tcgen05.st as the A operand of the next contraction (P overwrites S in place);
+//   - every product is evaluated as hi*hi + lo*hi + hi*lo (three MMAs per K step into one
+//     accumulator), which keeps ~22 mantissa bits on the operands: single-pass fp16/bf16/TF32
+//     inputs flip the Hann-weighted arg-max the tracker depends on;
+//   - softmax row statistics are thread-local (one row per TMEM lane); the 48 / 192 / 320 columns of
+//     a row are shared by three warps (column thirds) that exchange partial sums through smem.
+// Warp roles: warps 0-11 = epilogue (lane quarter = warp % 4, column third = warp / 4),
+// warp 12 = control (bulk weight loads + single-thread MMA issue).  Control and epilogue ping-pong
+// through two mbarriers (`go`: operands ready, 12 warp arrivals; `done`: tcgen05.commit).
+//
+// Algorithmic work per track: 112.07 MFLOP; issued MMA work is 3x that (split) x 1.2
+// (padding of the third tile).
+#include "vt_internal.h"
+#include "vt_tc.cuh"
+
+namespace vt {
+
+using namespace tc;
+
+namespace {
+
+constexpr int kTcThreads = 13 * 32;
+constexpr int kEpiThreads = 12 * 32;
+
+// ---- TMEM columns --------------------------------------------------------------------------------
+constexpr uint32_t kColBig = 0;        // [0,320): QKV out (2 buffers of 144 at 0 / 160), S -> P, fc1 out -> GELU operand
+constexpr uint32_t kColOut = 320;      // [320,368): O, proj out, fc2 out
+constexpr uint32_t kColOpa = 368;      // [368,512): three 48-column A-operand slots (hi 24 | lo 24), one per row tile
+
+// ---- shared memory (bytes) -------------------------------------------------------------------------
+constexpr int kSmWa = 0;                                  // Wqkv hi|lo, Wproj hi|lo (bulk copied per block)
+constexpr int kSmX = kSmWa + kTcWaBytes;                  // attention: K hi|lo, V hi|lo ; MLP: W1 hi|lo, W2 hi|lo
+constexpr int kKBytes = kN * kC * 2;                      // 30720 per precision
+constexpr int kSmKhi = kSmX, kSmKlo = kSmX + kKBytes, kSmVhi = kSmX + 2 * kKBytes, kSmVlo = kSmX + 3 * kKBytes;
+constexpr int kSmW1hi = kSmX, kSmW1lo = kSmX + 18432, kSmW2hi = kSmX + 36864, kSmW2lo = kSmX + 55296;
+constexpr int kSmPar = kSmX + 4 * kKBytes;                // fp32 parameters of all blocks
+constexpr int kSmRed = kSmPar + kDepth * kTcParFloats * 4;   // 4 arrays x 3 thirds x 128 rows fp32
+constexpr int kSmBar = kSmRed + 4 * 3 * 128 * 4;          // mbarriers
+constexpr int kSmTmem = kSmBar + 4 * 8;
+constexpr int kTcSmemBytes = kSmTmem + 16;
+static_assert(kTcWbBytes <= 4 * kKBytes, "MLP weights overlay the K/V region");
+static_assert(kSmBar % 8 == 0 && kSmX % 128 == 0, "alignment");
+
+// parameter offsets inside one block's fp32 parameter vector
+constexpr int kPLn1g = 0, kPLn1b = 48, kPBqkv = 96, kPBproj = 240, kPLn2g = 288, kPLn2b = 336, kPBfc1 = 384, kPBfc2 = 576;
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+
+struct Epi {
+    uint32_t tbase;        // TMEM base address
+    uint32_t lane_addr;    // (32 * quarter) << 16
+    int q, s, lane, row;   // lane quarter, column third, lane, row inside the tile (32q + lane)
+    float* red;            // [4][3][128]
+    uint64_t *mb_go, *mb_done;
+    uint32_t done_ph;
+
+    __device__ __forceinline__ bool active(int t) const { return !(t == 2 && q >= 2); }    // rows 320..383 are padding
+    __device__ __forceinline__ uint32_t taddr(uint32_t col) const { return tbase + lane_addr + col; }
+
+    // operands written (TMEM and/or smem): publish to the control thread
+    __device__ __forceinline__ void signal_go(bool wrote_smem) {
+        tc_wait_st();
+        if (wrote_smem) fence_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(mb_go);
+    }
+    __device__ __forceinline__ void wait_done() {
+        mbar_wait(mb_done, done_ph);
+        done_ph ^= 1;
+        tc_fence_after();
+    }
+
+    // sum over the 48 columns of a row (three thirds) of a per-thread partial; `arr` selects the scratch array
+    __device__ __forceinline__ float row_sum(float partial, int arr) {
+        float* r = red + arr * 384;
+        r[s * 128 + row] = partial;
+        epi_bar();
+        return r[row] + r[128 + row] + r[256 + row];
+    }
+
+    // LayerNorm statistics of a 48-wide row held as 3 x 16 values
+    __device__ __forceinline__ void ln16(const float (&v)[16], const float* g, const float* b, float (&y)[16]) {
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sum += v[i];
+        const float mean = row_sum(sum, 0) * (1.f / 48.f);
+        float var = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { const float d = v[i] - mean; var = fmaf(d, d, var); }
+        const float rstd = rsqrtf(row_sum(var, 1) * (1.f / 48.f) + kLnEps);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) y[i] = (v[i] - mean) * rstd * g[16 * s + i] + b[16 * s + i];
+    }
+
+    // write this thread's 16 K-elements [16s, 16s+16) of row `row` into A-operand slot t (hi cols 8s.., lo cols 24+8s..)
+    __device__ __forceinline__ void store_opa16(int t, const float (&y)[16]) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) split_pack2(y[2 * j], y[2 * j + 1], hi[j], lo[j]);
+        tmem_st8(taddr(kColOpa + 48 * t + 8 * s), hi);
+        tmem_st8(taddr(kColOpa + 48 * t + 24 + 8 * s), lo);
+    }
+};
+
+__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752f)); }
+
+}  // namespace
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float* __restrict__ tok_x, int x_stride_rows,
+                 float* __restrict__ out, int n, ModelW w, float* __restrict__ taps, size_t tap_stride) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float* s_par = reinterpret_cast<float*>(smem + kSmPar);
+    float* s_red = reinterpret_cast<float*>(smem + kSmRed);
+    uint64_t* mb_go = reinterpret_cast<uint64_t*>(smem + kSmBar);
+    uint64_t* mb_done = mb_go + 1;
+    uint64_t* mb_wa = mb_go + 2;
+    uint64_t* mb_wb = mb_go + 3;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kSmTmem);
+
+    if (warp == 12) tmem_alloc(s_tmem, 512);
+    if (tid == 0) {
+        mbar_init(mb_go, 12);
+        mbar_init(mb_done, 1);
+        mbar_init(mb_wa, 1);
+        mbar_init(mb_wb, 1);
+        mbar_fence_init();
+    }
+    for (int i = tid; i < kDepth * kTcParFloats; i += kTcThreads) s_par[i] = __ldg(w.tc[i / kTcParFloats].par + i % kTcParFloats);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *s_tmem;
+    const uint32_t sbase = smem_u32(smem);
+
+    if (warp == 12) {
+        // =========================== control: weight loads + MMA issue (one thread) ===========================
+        if (lane == 0) {
+            uint32_t go_ph = 0, wa_ph = 0, wb_ph = 0;
+            const uint32_t id48 = instr_desc_f16(128, 48, false), id48mn = instr_desc_f16(128, 48, true);
+            const uint32_t id144 = instr_desc_f16(128, 144, false), id160 = instr_desc_f16(128, 160, false);
+            const uint32_t id192 = instr_desc_f16(128, 192, false);
+            auto wait_go = [&]() { mbar_wait(mb_go, go_ph); go_ph ^= 1; tc_fence_after(); };
+            auto load_wa = [&](int blk) { mbar_arrive_expect_tx(mb_wa, kTcWaBytes); bulk_g2s(smem + kSmWa, w.tc[blk].wa, kTcWaBytes, mb_wa); };
+            auto load_wb = [&](int blk) { mbar_arrive_expect_tx(mb_wb, kTcWbBytes); bulk_g2s(smem + kSmX, w.tc[blk].wb, kTcWbBytes, mb_wb); };
+            // D[d_col] = A(opa slot t, K = 48) x B^T, B K-major [k/8][N][8] at byte offsets b_hi / b_lo
+            auto gemm_k48 = [&](int t, uint32_t d_col, uint32_t b_hi, uint32_t b_lo, int N, uint32_t idesc) {
+                const uint32_t a = tbase + kColOpa + 48 * t;
+#pragma unroll
+                for (int ks = 0; ks < 3; ++ks) {
+                    const uint64_t bh = smem_desc(sbase + b_hi + ks * 2 * N * 16, N * 16, 128);
+                    const uint64_t bl = smem_desc(sbase + b_lo + ks * 2 * N * 16, N * 16, 128);
+                    mma_ts(tbase + d_col, a + 8 * ks, bh, idesc, ks > 0);           // hi * hi
+                    mma_ts(tbase + d_col, a + 24 + 8 * ks, bh, idesc, true);        // lo * hi
+                    mma_ts(tbase + d_col, a + 8 * ks, bl, idesc, true);             // hi * lo
+                }
+            };
+            auto qkv = [&](int t, uint32_t d_col) { gemm_k48(t, d_col, kSmWa, kSmWa + 13824, 144, id144); };
+            auto proj = [&](int t) { gemm_k48(t, kColOut, kSmWa + 27648, kSmWa + 27648 + 4608, 48, id48); };
+            auto fc1 = [&](int t) { gemm_k48(t, kColBig, kSmW1hi, kSmW1lo, 192, id192); };
+            // S = q k^T over 320 keys as two N = 160 halves; K operand K-major [k/8][320][8]
+            auto scores = [&](int t) {
+                const uint32_t a = tbase + kColOpa + 48 * t;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const uint32_t d = tbase + kColBig + 160 * half;
+#pragma unroll
+                    for (int ks = 0; ks < 3; ++ks) {
+                        const uint32_t off = ks * 2 * (kN * 16) + half * 160 * 16;
+                        const uint64_t bh = smem_desc(sbase + kSmKhi + off, kN * 16, 128);
+                        const uint64_t bl = smem_desc(sbase + kSmKlo + off, kN * 16, 128);
+                        mma_ts(d, a + 8 * ks, bh, id160, ks > 0);
+                        mma_ts(d, a + 24 + 8 * ks, bh, id160, true);
+                        mma_ts(d, a + 8 * ks, bl, id160, true);
+                    }
+                }
+            };
+            // O = P V: P in TMEM (16-key group g: hi cols 16g.., lo cols 16g+8..), V MN-major [f/8][key/8][key%8][f%8]
+            auto pv = [&]() {
+#pragma unroll 4
+                for (int g = 0; g < kN / 16; ++g) {
+                    const uint32_t a = tbase + kColBig + 16 * g;
+                    const uint64_t bh = smem_desc(sbase + kSmVhi + g * 256, 128, (kN / 8) * 128);
+                    const uint64_t bl = smem_desc(sbase + kSmVlo + g * 256, 128, (kN / 8) * 128);
+                    mma_ts(tbase + kColOut, a, bh, id48mn, g > 0);
+                    mma_ts(tbase + kColOut, a + 8, bh, id48mn, true);
+                    mma_ts(tbase + kColOut, a, bl, id48mn, true);
+                }
+            };
+            // y = gelu(h) W2^T: operand in TMEM (16-wide group g: hi 16g.., lo 16g+8..), W2 K-major [k/8][48][8], K = 192
+            auto fc2 = [&]() {
+#pragma unroll 4
+                for (int g = 0; g < kHid / 16; ++g) {
+                    const uint32_t a = tbase + kColBig + 16 * g;
+                    const uint64_t bh = smem_desc(sbase + kSmW2hi + g * 2 * 48 * 16, 48 * 16, 128);
+                    const uint64_t bl = smem_desc(sbase + kSmW2lo + g * 2 * 48 * 16, 48 * 16, 128);
+                    mma_ts(tbase + kColOut, a, bh, id48, g > 0);
+                    mma_ts(tbase + kColOut, a + 8, bh, id48, true);
+                    mma_ts(tbase + kColOut, a, bl, id48, true);
+                }
+            };
+            bool first = true;
+            for (int trk = blockIdx.x; trk < n; trk += gridDim.x) {
+                const bool last_track = trk + (int)gridDim.x >= n;
+                for (int blk = 0; blk < kDepth; ++blk) {
+                    if (first) { load_wa(0); first = false; }
+                    wait_go();                                                   // 1: LN1 operands of all tiles
+                    mbar_wait(mb_wa, wa_ph); wa_ph ^= 1;
+                    qkv(0, kColBig); qkv(1, kColBig + 160); mma_commit(mb_done);
+                    wait_go(); qkv(2, kColBig); mma_commit(mb_done);             // 2
+                    wait_go(); scores(0); mma_commit(mb_done);                   // 3: K, V complete
+                    wait_go(); pv(); mma_commit(mb_done);                        // 4
+                    wait_go(); proj(0); scores(1); mma_commit(mb_done);          // 5
+                    wait_go(); pv(); mma_commit(mb_done);                        // 6
+                    wait_go(); proj(1); scores(2); mma_commit(mb_done);          // 7
+                    wait_go(); pv(); mma_commit(mb_done);                        // 8
+                    wait_go(); load_wb(blk); proj(2); mma_commit(mb_done);       // 9: K/V dead -> MLP weights stream in
+                    wait_go();                                                   // 10: Wqkv/Wproj dead -> prefetch the next block's
+                    if (!(last_track && blk == kDepth - 1)) load_wa((blk + 1) % kDepth);
+                    mbar_wait(mb_wb, wb_ph); wb_ph ^= 1;
+                    fc1(0); mma_commit(mb_done);
+                    wait_go(); fc2(); mma_commit(mb_done);                       // 11
+                    wait_go(); fc1(1); mma_commit(mb_done);                      // 12
+                    wait_go(); fc2(); mma_commit(mb_done);                       // 13
+                    wait_go(); fc1(2); mma_commit(mb_done);                      // 14
+                    wait_go(); fc2(); mma_commit(mb_done);                       // 15
+                }
+            }
+        }
+        __syncwarp();        // reconverge the control warp before the CTA-wide barrier below
+    } else {
+        // ======================================= epilogue warps ===========================================
+        Epi e;
+        e.tbase = tbase; e.q = warp & 3; e.s = warp >> 2; e.lane = lane; e.row = 32 * e.q + lane;
+        e.lane_addr = (uint32_t)(32 * e.q) << 16;
+        e.red = s_red; e.mb_go = mb_go; e.mb_done = mb_done; e.done_ph = 0;
+        const int s = e.s, row = e.row;
+        const float scale = 0.14433756729740643f;                 // 48 ** -0.5
+        const float kLog2e = 1.4426950408889634f;
+
+        for (int trk = blockIdx.x; trk < n; trk += gridDim.x) {
+            // residual slice x[t][16]: tile t, row 128 t + row, columns [16 s, 16 s + 16)
+            float x[3][16];
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const int r = 128 * t + row;
+                const float* src = nullptr;
+                if (r < kNz) src = tok_z + ((size_t)trk * z_stride_rows + r) * kC + 16 * s;
+                else if (r < kN) src = tok_x + ((size_t)trk * x_stride_rows + (r - kNz)) * kC + 16 * s;
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (src) v = __ldg(reinterpret_cast<const float4*>(src + i));
+                    x[t][i] = v.x; x[t][i + 1] = v.y; x[t][i + 2] = v.z; x[t][i + 3] = v.w;
+                }
+                if (taps && r < kN) {
+                    float* tp = taps + ((size_t)trk * kN + r) * kC + 16 * s;
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(tp + i) = make_float4(x[t][i], x[t][i + 1], x[t][i + 2], x[t][i + 3]);
+                }
+            }
+
+#pragma unroll 1
+            for (int blk = 0; blk < kDepth; ++blk) {
+                const float* par = s_par + blk * kTcParFloats;
+
+                if (blk == 0) {                 // later blocks: LN1 was fused into the previous block's last epilogue
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        float y[16];
+                        e.ln16(x[t], par + kPLn1g, par + kPLn1b, y);
+                        if (e.active(t)) e.store_opa16(t, y);
+                    }
+                }
+                e.signal_go(false);             // -> 1
+
+                // ---- QKV epilogue: third 0 -> q (scaled) into the tile's A slot, third 1 -> K rows, third 2 -> V rows
+                auto epi_qkv = [&](int t, uint32_t col) {
+                    if (!e.active(t)) return;
+                    float v[48];
+#pragma unroll
+                    for (int c = 0; c < 48; c += 16) {
+                        uint32_t r[16];
+                        tmem_ld16(e.taddr(col + 48 * s + c), r);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[c + j] = __uint_as_float(r[j]) + par[kPBqkv + 48 * s + c + j];
+                    }
+                    const int key = 128 * t + row;
+                    if (s == 0) {
+#pragma unroll
+                        for (int c = 0; c < 24; c += 8) {
+                            uint32_t hi[8], lo[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) split_pack2(v[2 * (c + j)] * scale, v[2 * (c + j) + 1] * scale, hi[j], lo[j]);
+                            tmem_st8(e.taddr(kColOpa + 48 * t + c), hi);
+                            tmem_st8(e.taddr(kColOpa + 48 * t + 24 + c), lo);
+                        }
+                    } else {
+                        // K: K-major [k/8][key][8]   V: MN-major [f/8][key/8][key%8][f%8]  (both: chunk * 320*16 + key*16)
+                        uint8_t* hi_base = smem + (s == 1 ? kSmKhi : kSmVhi) + key * 16;
+                        uint8_t* lo_base = smem + (s == 1 ? kSmKlo : kSmVlo) + key * 16;
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) {
+                            uint32_t hi[4], lo[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) split_pack2(v[8 * c + 2 * j], v[8 * c + 2 * j + 1], hi[j], lo[j]);
+                            *reinterpret_cast<uint4*>(hi_base + c * (kN * 16)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                            *reinterpret_cast<uint4*>(lo_base + c * (kN * 16)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        }
+                    }
+                };
+                e.wait_done();
+                epi_qkv(0, kColBig);
+                epi_qkv(1, kColBig + 160);
+                e.signal_go(true);              // -> 2
+                e.wait_done();
+                epi_qkv(2, kColBig);
+                e.signal_go(true);              // -> 3
+
+                // ---- attention per tile -------------------------------------------------------------------
+                float inv_l[3];
+                auto softmax = [&](int t) {
+                    // thirds own 112 / 112 / 96 score columns (7, 7, 6 groups of 16 keys)
+                    const int c_begin = 112 * s, groups = (s == 2) ? 6 : 7;
+                    float m = -INFINITY;
+                    if (e.active(t)) {
+                        for (int g = 0; g < groups; ++g) {
+                            uint32_t r[16];
+                            tmem_ld16(e.taddr(kColBig + c_begin + 16 * g), r);
+                            tc_wait_ld();
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(r[j]));
+                        }
+                    }
+                    float* rm = e.red + 2 * 384;
+                    rm[s * 128 + row] = m;
+                    epi_bar();
+                    m = fmaxf(fmaxf(rm[row], rm[128 + row]), rm[256 + row]);
+                    float l = 0.f;
+                    if (e.active(t)) {
+                        const float mb = m * kLog2e;
+                        for (int g = 0; g < groups; ++g) {
+                            uint32_t r[16];
+                            const uint32_t a = e.taddr(kColBig + c_begin + 16 * g);
+                            tmem_ld16(a, r);
+                            tc_wait_ld();
+                            uint32_t hi[8], lo[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float p0 = exp2f(fmaf(__uint_as_float(r[2 * j]), kLog2e, -mb));
+                                const float p1 = exp2f(fmaf(__uint_as_float(r[2 * j + 1]), kLog2e, -mb));
+                                l += p0 + p1;
+                                split_pack2(p0, p1, hi[j], lo[j]);
+                            }
+                            tmem_st8(a, hi);            // P overwrites S in place: [hi x8 | lo x8] per 16 keys
+                            tmem_st8(a + 8, lo);
+                        }
+                    }
+                    e.red[3 * 384 + s * 128 + row] = l;     // summed after the next barrier (in epi_o)
+                };
+                auto epi_o = [&](int t) {
+                    epi_bar();                               // partial row sums of softmax(t) are visible
+                    const float* rl = e.red + 3 * 384;
+                    const float inv = 1.f / (rl[row] + rl[128 + row] + rl[256 + row]);
+                    inv_l[t] = inv;
+                    if (!e.active(t)) return;
+                    uint32_t r[16];
+                    tmem_ld16(e.taddr(kColOut + 16 * s), r);
+                    tc_wait_ld();
+                    float y[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(r[j]) * inv;
+                    e.store_opa16(t, y);
+                };
+                auto epi_proj = [&](int t) {
+                    if (e.active(t)) {
+                        uint32_t r[16];
+                        tmem_ld16(e.taddr(kColOut + 16 * s), r);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) x[t][j] += __uint_as_float(r[j]) + par[kPBproj + 16 * s + j];
+                    }
+                    float y[16];
+                    e.ln16(x[t], par + kPLn2g, par + kPLn2b, y);
+                    if (e.active(t)) e.store_opa16(t, y);
+                };
+                e.wait_done(); softmax(0); e.signal_go(false);                    // -> 4
+                e.wait_done(); epi_o(0); e.signal_go(false);                      // -> 5
+                e.wait_done(); epi_proj(0); softmax(1); e.signal_go(false);       // -> 6
+                e.wait_done(); epi_o(1); e.signal_go(false);                      // -> 7
+                e.wait_done(); epi_proj(1); softmax(2); e.signal_go(false);       // -> 8
+                e.wait_done(); epi_o(2); e.signal_go(false);                      // -> 9
+                e.wait_done(); epi_proj(2); e.signal_go(false);                   // -> 10
+
+                // ---- MLP per tile -------------------------------------------------------------------------
+                auto gelu = [&](int t) {
+                    if (!e.active(t)) return;
+#pragma unroll 1
+                    for (int g = 0; g < 4; ++g) {                                 // third s owns hidden columns [64 s, 64 s + 64)
+                        const uint32_t a = e.taddr(kColBig + 64 * s + 16 * g);
+                        uint32_t r[16];
+                        tmem_ld16(a, r);
+                        tc_wait_ld();
+                        uint32_t hi[8], lo[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float h0 = gelu_erf(__uint_as_float(r[2 * j]) + par[kPBfc1 + 64 * s + 16 * g + 2 * j]);
+                            const float h1 = gelu_erf(__uint_as_float(r[2 * j + 1]) + par[kPBfc1 + 64 * s + 16 * g + 2 * j + 1]);
+                            split_pack2(h0, h1, hi[j], lo[j]);
+                        }
+                        tmem_st8(a, hi);
+                        tmem_st8(a + 8, lo);
+                    }
+                };
+                auto epi_fc2 = [&](int t) {
+                    if (e.active(t)) {
+                        uint32_t r[16];
+                        tmem_ld16(e.taddr(kColOut + 16 * s), r);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) x[t][j] += __uint_as_float(r[j]) + par[kPBfc2 + 16 * s + j];
+                        const int rr = 128 * t + row;
+                        if (taps && rr < kN) {
+                            float* tp = taps + (size_t)(blk + 1) * tap_stride + ((size_t)trk * kN + rr) * kC + 16 * s;
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(tp + i) = make_float4(x[t][i], x[t][i + 1], x[t][i + 2], x[t][i + 3]);
+                        }
+                        if (blk == kDepth - 1 && rr < kN) {
+                            float* dst = out + ((size_t)trk * kN + rr) * kC + 16 * s;
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(x[t][i], x[t][i + 1], x[t][i + 2], x[t][i + 3]);
+                        }
+                    }
+                    if (blk < kDepth - 1) {      // LayerNorm 1 of the next block -> the tile's A slot
+                        const float* np = par + kTcParFloats;
+                        float y[16];
+                        e.ln16(x[t], np + kPLn1g, np + kPLn1b, y);
+                        if (e.active(t)) e.store_opa16(t, y);
+                    }
+                };
+                e.wait_done(); gelu(0); e.signal_go(false);                       // -> 11
+                e.wait_done(); epi_fc2(0); e.signal_go(false);                    // -> 12
+                e.wait_done(); gelu(1); e.signal_go(false);                       // -> 13
+                e.wait_done(); epi_fc2(1); e.signal_go(false);                    // -> 14
+                e.wait_done(); gelu(2); e.signal_go(false);                       // -> 15
+                e.wait_done(); epi_fc2(2);
+                (void)inv_l;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) tmem_dealloc(tbase, 512);
+}
+
+int launch_blocks_tc(const float* tok_z, int z_stride_rows, const float* tok_x, int x_stride_rows, float* out, int n,
+                     const ModelW& w, float* taps, size_t tap_stride, int num_sms, cudaStream_t st) {
+    if (n <= 0) return 0;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(blocks_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) != cudaSuccess) return -1;
+        configured = true;
+    }
+    const int grid = n < num_sms ? n : num_sms;
+    blocks_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(tok_z, z_stride_rows, tok_x, x_stride_rows, out, n, w, taps, tap_stride);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+}  // namespace vt

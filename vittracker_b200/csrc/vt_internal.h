@@ -41,9 +41,21 @@ struct HeadW {               // CENTER head, BN folded, towers ordered ctr, offs
     const float *w5, *b5;    // [3][4][2] (ctr uses column 0), [3][2]
 };
 
+// Tensor-core block kernel operands (vt_block_tc.cu): fp16 hi/lo split weights in the UMMA
+// no-swizzle K-major layout [k/8][n][8], one bulk-copyable blob per phase, plus fp32 parameters.
+constexpr int kTcWaBytes = 2 * (144 * 48 * 2) + 2 * (48 * 48 * 2);      // Wqkv hi|lo, Wproj hi|lo = 36864
+constexpr int kTcWbBytes = 2 * (192 * 48 * 2) + 2 * (48 * 192 * 2);     // W1 hi|lo, W2 hi|lo     = 73728
+constexpr int kTcParFloats = 624;   // ln1_g 48 | ln1_b 48 | bqkv 144 | bproj 48 | ln2_g 48 | ln2_b 48 | bfc1 192 | bfc2 48
+struct BlockTcW {
+    const uint8_t* wa;     // kTcWaBytes
+    const uint8_t* wb;     // kTcWbBytes
+    const float* par;      // kTcParFloats
+};
+
 struct ModelW {
     StemLayerW stem[4];
     BlockW blk[kDepth];
+    BlockTcW tc[kDepth];
     const float *norm_g, *norm_b;
     const float *pos_z, *pos_x;    // [64][48], [256][48]
     HeadW head;
@@ -67,6 +79,10 @@ int launch_stem(const float* img, int S, int n, const ModelW& w, float* scratch,
 // result written to out [n][320][48]; taps (or null) receives [depth][n][320][48].
 int launch_blocks_simt(const float* tok_z, int z_stride_rows, const float* tok_x, int x_stride_rows,
                        float* out, int n, const ModelW& w, float* taps, size_t tap_stride, cudaStream_t st);
+
+// ViT blocks on the tcgen05 tensor cores (fp16 hi/lo split operands, fp32 accumulation in TMEM).
+int launch_blocks_tc(const float* tok_z, int z_stride_rows, const float* tok_x, int x_stride_rows,
+                     float* out, int n, const ModelW& w, float* taps, size_t tap_stride, int num_sms, cudaStream_t st);
 
 struct HeadArgs {
     const float* tokens;      // [n][320][48] block output (pre final-norm)
