@@ -37,10 +37,13 @@ def stress_sd(golden_model):
     return state_dict_from_npz(golden_model)
 
 
-@pytest.fixture(scope="module")
-def engine(cfg, stress_sd):
+BLOCKS = ["simt", "tcgen05"]            # fp32 CUDA-core kernel and tcgen05 tensor-core kernel: same parity bar
+
+
+@pytest.fixture(scope="module", params=BLOCKS)
+def engine(request, cfg, stress_sd):
     from vittracker_b200.engine import Engine
-    e = Engine(cfg, max_tracks=1024, chunk_tracks=128)
+    e = Engine(cfg, max_tracks=1024, chunk_tracks=128, blocks_impl=request.param)
     e.load_state_dict(stress_sd)
     return e
 
@@ -127,11 +130,12 @@ def test_forward_against_reference_golden(engine, golden_model):
     assert close(boxes, g["pred_boxes_windowed"], atol=1e-4)
 
 
+@pytest.mark.parametrize("blocks", BLOCKS)
 @pytest.mark.parametrize("stress", [False, True])
-def test_forward_random_batch_against_oracle(cfg, stress):
+def test_forward_random_batch_against_oracle(cfg, stress, blocks):
     from vittracker_b200.engine import Engine
     sd = O.make_state_dict(seed=5 if stress else 0, stress=stress)
-    e = Engine(cfg, max_tracks=4, chunk_tracks=3)            # chunk < batch: exercises chunking
+    e = Engine(cfg, max_tracks=4, chunk_tracks=3, blocks_impl=blocks)   # chunk < batch: exercises chunking
     e.load_state_dict(sd)
     frame = O.synth_frames(1, 360, 480, seed=41, smooth=True)[0]
     boxes = O.synth_boxes(7, 360, 480, seed=42)
@@ -146,9 +150,10 @@ def test_forward_random_batch_against_oracle(cfg, stress):
     assert torch.equal(got["score_map"].flatten(1).argmax(1).cpu(), want["score_map"].flatten(1).argmax(1))
 
 
-def test_model_dropin_surface(cfg, stress_sd):
+@pytest.mark.parametrize("blocks", BLOCKS)
+def test_model_dropin_surface(cfg, stress_sd, blocks):
     from vittracker_b200 import build_ostrack_dist
-    net = build_ostrack_dist(cfg)
+    net = build_ostrack_dist(cfg, blocks_impl=blocks)
     net.load_state_dict(stress_sd, strict=True)
     net = net.cuda().eval()
     z, x = torch.randn(1, 3, 128, 128), torch.randn(1, 3, 256, 256)
@@ -166,13 +171,15 @@ def test_model_dropin_surface(cfg, stress_sd):
 # ------------------------------------------------------------------------------------------------
 # tracker state machine
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("blocks", BLOCKS)
 @pytest.mark.parametrize("tag", ["stress", "stable"])
-def test_tracker_closed_loop_against_reference_golden(golden_track, golden_model, tag):
+def test_tracker_closed_loop_against_reference_golden(golden_track, golden_model, tag, blocks):
     from vittracker_b200 import get_tracker_class, parameters
     g = golden_track
     sd = state_dict_from_npz(golden_model) if tag == "stress" else state_dict_from_npz(g, "w_stable::")
     params = parameters("vit_48_h32_noKD")
     params.state_dict = sd
+    params.blocks_impl = blocks
     trk = get_tracker_class()(params, "synthetic")
     frames = g["frames"]
     init = [float(v) for v in g[f"{tag}_init"]]
@@ -236,16 +243,17 @@ def _oracle_open_loop(sd, frames, fidx_init, fidx_step, init_boxes, step_boxes):
     return res
 
 
-def test_batched_open_loop_argmax_and_boxes_against_oracle(cfg):
+@pytest.mark.parametrize("blocks,n", [("simt", 96), ("tcgen05", 96), ("tcgen05", 1200)])
+def test_batched_open_loop_argmax_and_boxes_against_oracle(cfg, blocks, n):
     from vittracker_b200 import BatchedTracker, FramePool
     sd = O.make_state_dict(seed=9, stress=True)
-    n, F = 96, 3
+    F = 3
     frames = O.synth_frames(F, 360, 640, seed=51, smooth=True)
     init_boxes = O.synth_boxes(n, 360, 640, seed=52)
     step_boxes = O.synth_boxes(n, 360, 640, seed=53)
     fi = np.arange(n) % F
     fs = (np.arange(n) + 1) % F
-    bt = BatchedTracker(cfg, sd, max_tracks=n, chunk_tracks=40)
+    bt = BatchedTracker(cfg, sd, max_tracks=n, chunk_tracks=40 if n < 200 else 256, blocks_impl=blocks)
     pool = FramePool(frames, bt.device)
     st = bt.initialize(pool, torch.from_numpy(fi), init_boxes)
     assert int(st.abs().sum()) == 0
@@ -265,20 +273,21 @@ def test_batched_open_loop_argmax_and_boxes_against_oracle(cfg):
         assert close(out[i, :4], w["state"]), (i, out[i], w["state"])
         assert abs(out[i, 4] - w["conf"]) < 1e-4
         assert np.array_equal(new_state[i], out[i, :4])
-    print(f"open loop: {n} tracks, {ties} ties excluded, {flips} arg-max flips")
+    print(f"open loop [{blocks}]: {n} tracks, {ties} ties excluded, {flips} arg-max flips")
     assert flips == 0
     maps = bt.engine.tracks_last_maps(0, n)
     assert close(maps["score_map"][5].flatten().cpu().numpy(), want[5]["score"], atol=1e-4)
 
 
-def test_batched_full_size_properties(cfg, stress_sd):
+@pytest.mark.parametrize("blocks", BLOCKS)
+def test_batched_full_size_properties(cfg, stress_sd, blocks):
     """BASELINE config 3 size (1024 concurrent tracks): size-independent properties."""
     from vittracker_b200 import BatchedTracker, FramePool
     n, F = 1024, 4
     frames = O.synth_frames(F, 720, 1280, seed=61)
     boxes = O.synth_boxes(n, 720, 1280, seed=62)
     fidx = torch.arange(n) % F
-    bt = BatchedTracker(cfg, stress_sd, max_tracks=n, chunk_tracks=256)
+    bt = BatchedTracker(cfg, stress_sd, max_tracks=n, chunk_tracks=256, blocks_impl=blocks)
     pool = FramePool(frames, bt.device)
     assert int(bt.initialize(pool, fidx, boxes).abs().sum()) == 0
     a = bt.track(pool, (fidx + 1) % F, update_state=False).clone()
@@ -292,7 +301,7 @@ def test_batched_full_size_properties(cfg, stress_sd):
     assert ((a[:, 4] >= 1e-4) & (a[:, 4] <= 0.9999 + 1e-7)).all()
     # permutation equivariance: tracks are independent, so reversing the batch reverses the result
     perm = torch.arange(n - 1, -1, -1)
-    bt2 = BatchedTracker(cfg, stress_sd, max_tracks=n, chunk_tracks=96)
+    bt2 = BatchedTracker(cfg, stress_sd, max_tracks=n, chunk_tracks=96, blocks_impl=blocks)
     bt2.initialize(pool, fidx[perm], boxes[perm.numpy()])
     c = bt2.track(pool, ((fidx + 1) % F)[perm], update_state=False)
     assert torch.equal(c, a[perm.to(a.device)]), "result depends on batch position / chunking"
@@ -303,17 +312,19 @@ def test_batched_full_size_properties(cfg, stress_sd):
             assert close(a[i, :4].cpu().numpy(), wnt["state"]), (i, a[i], wnt["state"])
 
 
-def test_batched_closed_loop_matches_single_tracker(cfg, golden_track):
+@pytest.mark.parametrize("blocks", BLOCKS)
+def test_batched_closed_loop_matches_single_tracker(cfg, golden_track, blocks):
     from vittracker_b200 import BatchedTracker, FramePool, get_tracker_class, parameters
     g = golden_track
     sd = state_dict_from_npz(g, "w_stable::")
     frames = g["frames"]
-    bt = BatchedTracker(cfg, sd, max_tracks=2)
+    bt = BatchedTracker(cfg, sd, max_tracks=2, blocks_impl=blocks)
     pool = FramePool(frames, bt.device)
     init = np.array([g["stable_init"], g["stable_init"] + [3, -2, 4, 1]])
     bt.initialize(pool, torch.zeros(2, dtype=torch.int64), init)
     params = parameters("vit_48_h32_noKD")
     params.state_dict = sd
+    params.blocks_impl = blocks
     singles = []
     for k in range(2):
         t = get_tracker_class()(params, "synthetic")

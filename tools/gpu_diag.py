@@ -15,7 +15,7 @@ from oracle import vt_oracle as O  # noqa: E402
 from vittracker_b200 import BatchedTracker, FramePool, load_cfg  # noqa: E402
 from vittracker_b200.engine import Engine  # noqa: E402
 
-blocks = sys.argv[1] if len(sys.argv) > 1 else "simt"
+blocks = sys.argv[1] if len(sys.argv) > 1 else "tcgen05"
 cfg = load_cfg()
 print("device", torch.cuda.get_device_name(0), "blocks_impl", blocks)
 

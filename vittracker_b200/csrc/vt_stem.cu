@@ -12,6 +12,17 @@
 
 namespace vt {
 
+// cp.async of BYTES (4 or 16) bytes; when !valid nothing is read and the destination is zero-filled
+template <int BYTES>
+__device__ __forceinline__ void cp_async(float* dst_smem, const float* src_gmem, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    const int sz = valid ? BYTES : 0;
+    if (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(src_gmem), "r"(sz) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(src_gmem), "r"(sz) : "memory");
+}
+
 template <int CIN, int COUT, int QG, int P, int TW, int TH>
 struct ConvCfg {
     static constexpr int kPixGroups = TW * TH / P;
@@ -23,7 +34,7 @@ struct ConvCfg {
     // TW == 16: two output rows share a warp -> row pitch must be == 8 (mod 16) to stay conflict free
     static constexpr int kPitch = (TW == 32) ? kPitchRaw : ((kPitchRaw - 8 + 15) / 16 * 16 + 8);
     static constexpr int kTileFloats = (CIN * kInRows * kPitch + 3) / 4 * 4;   // keeps the weights 16-byte aligned
-    static constexpr int kWFloats = CIN * 9 * COUT;
+    static constexpr int kWFloats = (CIN * 9 * COUT + 3) / 4 * 4;      // copied in 16-byte pieces (packed slots are padded alike)
     static constexpr size_t kSmemBytes = (size_t)(kTileFloats + kWFloats + COUT) * sizeof(float);
     static_assert(kPixGroups % 32 == 0, "channel group must be warp uniform");
     static_assert(32 % TW == 0 && (TW == 16 || TW == 32), "tile width");
@@ -48,10 +59,12 @@ conv3x3s2_kernel(const float* __restrict__ in, int Hin, int Win, const float* __
     const int b = blockIdx.y;
     const int tid = threadIdx.x;
 
-    for (int i = tid; i < K::kWFloats; i += K::kThreads) ws[i] = wg[i];
-    for (int i = tid; i < COUT; i += K::kThreads) bs[i] = bg[i];
+    // weights / bias / input tile are staged with cp.async: every load is in flight at once (the tile
+    // fill was latency-bound as a loop of dependent ld.global + st.shared); padding is zero-filled
+    for (int i = tid * 4; i < K::kWFloats; i += K::kThreads * 4) cp_async<16>(ws + i, wg + i, true);
+    if (tid < COUT) cp_async<4>(bs + tid, bg + tid, true);
 
-    // stage the input tile: tile column c <-> input column 2*tx0 - 1 + c, row r <-> 2*ty0 - 1 + r
+    // tile column c <-> input column 2*tx0 - 1 + c, row r <-> 2*ty0 - 1 + r
     const float* inb = in + (size_t)b * CIN * Hin * Win;
     const int ix0 = 2 * tx0 - 1, iy0 = 2 * ty0 - 1;
     for (int i = tid; i < CIN * K::kInRows * K::kPitchRaw; i += K::kThreads) {
@@ -59,11 +72,12 @@ conv3x3s2_kernel(const float* __restrict__ in, int Hin, int Win, const float* __
         const int r = (i / K::kPitchRaw) % K::kInRows;
         const int ci = i / (K::kPitchRaw * K::kInRows);
         const int gx = ix0 + c, gy = iy0 + r;
-        float v = 0.f;
-        if (gx >= 0 && gx < Win && gy >= 0 && gy < Hin) v = __ldg(inb + ((size_t)ci * Hin + gy) * Win + gx);
+        const bool ok = gx >= 0 && gx < Win && gy >= 0 && gy < Hin;
         const int slot = (c & 1) ? (K::kEven + (c >> 1)) : (c >> 1);
-        tile[(ci * K::kInRows + r) * K::kPitch + slot] = v;
+        cp_async<4>(tile + (ci * K::kInRows + r) * K::kPitch + slot, ok ? inb + ((size_t)ci * Hin + gy) * Win + gx : inb, ok);
     }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncthreads();
 
     const int cg = tid / K::kPixGroups;                 // warp-uniform channel group

@@ -27,7 +27,7 @@ def hann2d_window(sz: int = 16) -> torch.Tensor:
 
 class Engine:
     def __init__(self, cfg, max_tracks: int = 1, chunk_tracks: int = 0, device: Optional[int] = None,
-                 blocks_impl: str = "simt", depth: int = 3):
+                 blocks_impl: str = "tcgen05", depth: int = 3):
         if not torch.cuda.is_available():
             raise RuntimeError("vittracker_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()

@@ -31,7 +31,7 @@ class CenterHeadHandle:
 
 
 class OstrackDistB200:
-    def __init__(self, cfg, depth: int = 3, mode: str = "eval", blocks_impl: str = "simt", max_tracks: int = 1,
+    def __init__(self, cfg, depth: int = 3, mode: str = "eval", blocks_impl: str = "tcgen05", max_tracks: int = 1,
                  chunk_tracks: int = 0):
         if mode != "eval":
             raise NotImplementedError("only mode='eval' (inference) is implemented; the distillation/training "
