@@ -29,16 +29,23 @@ struct ConvCfg {
     static constexpr int kChGroups = COUT / QG;
     static constexpr int kThreads = kPixGroups * kChGroups;
     static constexpr int kInRows = 2 * TH + 1;
-    static constexpr int kEven = TW + 1;                   // even input columns 0,2,..,2*TW
-    static constexpr int kPitchRaw = 2 * TW + 1;
+    // One tile row holds input columns 2*tx0-1 .. 2*tx0+2*TW-1 de-interleaved by parity:
+    //   [0] pad | [1 .. TW+1] even-slot columns E[0..TW] | [TW+2 .. 2TW+1] odd-slot columns O[0..TW-1]
+    // (tile column c = input column - (2*tx0-1); even c -> E[c/2], odd c -> O[c/2]).  The pad keeps the
+    // 8-byte stores of the staging loop aligned; output pixel x reads E[x], O[x], E[x+1]: stride-1 per lane.
+    static constexpr int kEOff = 1;
+    static constexpr int kOOff = TW + 2;
+    static constexpr int kPitchRaw = 2 * TW + 2;
     // TW == 16: two output rows share a warp -> row pitch must be == 8 (mod 16) to stay conflict free
     static constexpr int kPitch = (TW == 32) ? kPitchRaw : ((kPitchRaw - 8 + 15) / 16 * 16 + 8);
+    static constexpr int kChunks = TW / 2 + 1;               // aligned float4 chunks per tile row
     static constexpr int kTileFloats = (CIN * kInRows * kPitch + 3) / 4 * 4;   // keeps the weights 16-byte aligned
     static constexpr int kWFloats = (CIN * 9 * COUT + 3) / 4 * 4;      // copied in 16-byte pieces (packed slots are padded alike)
     static constexpr size_t kSmemBytes = (size_t)(kTileFloats + kWFloats + COUT) * sizeof(float);
     static_assert(kPixGroups % 32 == 0, "channel group must be warp uniform");
     static_assert(32 % TW == 0 && (TW == 16 || TW == 32), "tile width");
     static_assert(COUT % QG == 0 && QG % 2 == 0, "channel grouping");
+    static_assert(kPitch % 2 == 0 && kOOff % 2 == 0, "8-byte aligned odd-slot stores");
 };
 
 template <int CIN, int COUT, int QG, int P, int TW, int TH, bool HSWISH, bool TOKENS>
@@ -64,17 +71,46 @@ conv3x3s2_kernel(const float* __restrict__ in, int Hin, int Win, const float* __
     for (int i = tid * 4; i < K::kWFloats; i += K::kThreads * 4) cp_async<16>(ws + i, wg + i, true);
     if (tid < COUT) cp_async<4>(bs + tid, bg + tid, true);
 
-    // tile column c <-> input column 2*tx0 - 1 + c, row r <-> 2*ty0 - 1 + r
-    const float* inb = in + (size_t)b * CIN * Hin * Win;
-    const int ix0 = 2 * tx0 - 1, iy0 = 2 * ty0 - 1;
-    for (int i = tid; i < CIN * K::kInRows * K::kPitchRaw; i += K::kThreads) {
-        const int c = i % K::kPitchRaw;
-        const int r = (i / K::kPitchRaw) % K::kInRows;
-        const int ci = i / (K::kPitchRaw * K::kInRows);
-        const int gx = ix0 + c, gy = iy0 + r;
-        const bool ok = gx >= 0 && gx < Win && gy >= 0 && gy < Hin;
-        const int slot = (c & 1) ? (K::kEven + (c >> 1)) : (c >> 1);
-        cp_async<4>(tile + (ci * K::kInRows + r) * K::kPitch + slot, ok ? inb + ((size_t)ci * Hin + gy) * Win + gx : inb, ok);
+    // Input tile: aligned float4 loads (chunk j of a row covers input columns 2*tx0-4+4j .. +3), several
+    // in flight per thread, de-interleaved in registers.  Win is a multiple of 4, so a chunk is entirely
+    // inside or outside the image; outside (and rows outside) is the convolution's zero padding.
+    {
+        const float* inb = in + (size_t)b * CIN * Hin * Win;
+        const int gx0 = 2 * tx0 - 4, iy0 = 2 * ty0 - 1;
+        constexpr int kItems = CIN * K::kInRows * K::kChunks;
+        constexpr int kBatch = 4;
+#pragma unroll 1
+        for (int i0 = tid; i0 < kItems; i0 += kBatch * K::kThreads) {
+            float4 v[kBatch];
+            int dst[kBatch], jj[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const int i = i0 + u * K::kThreads;
+                const int j = i % K::kChunks;
+                const int rr = i / K::kChunks;                // ci * kInRows + r
+                const int r = rr % K::kInRows;
+                const int ci = rr / K::kInRows;
+                const int gx = gx0 + 4 * j, gy = iy0 + r;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                jj[u] = j;
+                dst[u] = (i < kItems) ? rr * K::kPitch : -1;
+                if (i < kItems && gx >= 0 && gx < Win && gy >= 0 && gy < Hin)
+                    v[u] = __ldg(reinterpret_cast<const float4*>(inb + ((size_t)ci * Hin + gy) * Win + gx));
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                if (dst[u] < 0) continue;
+                float* row = tile + dst[u];
+                const int j = jj[u];
+                if (j == 0) {
+                    row[K::kEOff] = v[u].w;                                              // c = 0 -> E[0]
+                } else {
+                    // c = 4j-3 (odd) 4j-2 (even) 4j-1 (odd) 4j (even) -> O[2j-2], E[2j-1], O[2j-1], E[2j]
+                    *reinterpret_cast<float2*>(row + K::kOOff + 2 * j - 2) = make_float2(v[u].x, v[u].z);
+                    *reinterpret_cast<float2*>(row + K::kEOff + 2 * j - 1) = make_float2(v[u].y, v[u].w);
+                }
+            }
+        }
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
@@ -103,9 +139,9 @@ conv3x3s2_kernel(const float* __restrict__ in, int Hin, int Win, const float* __
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 const float* row = tile + (ci * K::kInRows + 2 * ly[p] + ky) * K::kPitch;
-                xin[p][0] = row[lx];                     // input col 2x   (even slot x)
-                xin[p][1] = row[K::kEven + lx];          // input col 2x+1 (odd slot x)
-                xin[p][2] = row[lx + 1];                 // input col 2x+2 (even slot x+1)
+                xin[p][0] = row[K::kEOff + lx];          // tile col 2x   (even slot x)
+                xin[p][1] = row[K::kOOff + lx];          // tile col 2x+1 (odd slot x)
+                xin[p][2] = row[K::kEOff + lx + 1];      // tile col 2x+2 (even slot x+1)
             }
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
