@@ -41,7 +41,6 @@ struct VtContext {
     int chunk = 0;
     int num_sms = 148;
     // chunk workspace
-    float* d_crop = nullptr;          // [chunk][3][256][256]
     float* d_scratch = nullptr;       // stem intermediates
     float* d_tokz = nullptr;          // [chunk][64][48]   (vt_forward only)
     float* d_tokx = nullptr;          // [max_tracks][256][48]
@@ -148,7 +147,7 @@ struct Packer {
 void free_all(VtHandle h) {
     for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : h->evpool) cudaEventDestroy(e);
-    cudaFree(h->d_weights); cudaFree(h->d_crop); cudaFree(h->d_scratch); cudaFree(h->d_tokz);
+    cudaFree(h->d_weights); cudaFree(h->d_scratch); cudaFree(h->d_tokz);
     cudaFree(h->d_tokx); cudaFree(h->d_tok); cudaFree(h->d_state); cudaFree(h->d_tmpl);
     cudaFree(h->d_status); cudaFree(h->d_maps);
 }
@@ -229,7 +228,6 @@ int vt_create(const VtConfig* cfg, VtHandle* out) {
     const size_t ch = h->chunk, mt = cfg->max_tracks;
     cudaError_t e = cudaSuccess;
     auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
-    A((void**)&h->d_crop, ch * 3 * kSx * kSx * sizeof(float));
     A((void**)&h->d_scratch, ch * stem_scratch_floats(kSx) * sizeof(float));
     A((void**)&h->d_tokz, ch * kNz * kC * sizeof(float));
     A((void**)&h->d_tokx, mt * kNx * kC * sizeof(float));     // whole-step buffers: blocks + head run once per step
@@ -522,11 +520,9 @@ int vt_tracks_init(VtHandle h, const uint8_t* frames, const int64_t* frame_offse
     VT_CUDA(h, cudaSetDevice(h->cfg.device));
     for (int c0 = 0; c0 < n; c0 += h->chunk) {
         const int m = (n - c0 < h->chunk) ? n - c0 : h->chunk;
-        VT_LAUNCH(h, VT_STAGE_CROP, m, st, "vt_tracks_init/crop", launch_crop_normalize(frames, frame_offsets + c0, frame_hw + 2 * c0, boxes_xywh + 4 * c0,
-                                                                 h->cfg.template_factor, kTz, m, h->mw.lut, h->d_crop, nullptr, nullptr,
-                                                                 nullptr, h->d_status + first + c0, st));
-        VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_tracks_init/stem", launch_stem(h->d_crop, kTz, m, h->mw, h->d_scratch,
-                                                       h->d_tmpl + (size_t)(first + c0) * kNz * kC, kNz, 0, st));
+        VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_tracks_init/crop+stem",
+                  launch_crop_stem(frames, frame_offsets + c0, frame_hw + 2 * c0, boxes_xywh + 4 * c0, h->cfg.template_factor, kTz, m,
+                                   h->mw, h->d_scratch, h->d_tmpl + (size_t)(first + c0) * kNz * kC, kNz, 0, h->d_status + first + c0, st));
     }
     VT_CUDA(h, cudaMemcpyAsync(h->d_state + (size_t)first * 4, boxes_xywh, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if (out_status) VT_CUDA(h, cudaMemcpyAsync(out_status, h->d_status + first, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
@@ -546,11 +542,9 @@ int vt_tracks_step(VtHandle h, const uint8_t* frames, const int64_t* frame_offse
     for (int c0 = 0; c0 < n; c0 += h->chunk) {
         const int m = (n - c0 < h->chunk) ? n - c0 : h->chunk;
         const int t0 = first + c0;
-        VT_LAUNCH(h, VT_STAGE_CROP, m, st, "vt_tracks_step/crop",
-                  launch_crop_normalize(frames, frame_offsets + c0, frame_hw + 2 * c0, h->d_state + (size_t)t0 * 4, h->cfg.search_factor,
-                                        kSx, m, h->mw.lut, h->d_crop, nullptr, nullptr, nullptr, h->d_status + t0, st));
-        VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_tracks_step/stem",
-                  launch_stem(h->d_crop, kSx, m, h->mw, h->d_scratch, h->d_tokx + (size_t)c0 * kNx * kC, kNx, 0, st));
+        VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_tracks_step/crop+stem",
+                  launch_crop_stem(frames, frame_offsets + c0, frame_hw + 2 * c0, h->d_state + (size_t)t0 * 4, h->cfg.search_factor, kSx, m,
+                                   h->mw, h->d_scratch, h->d_tokx + (size_t)c0 * kNx * kC, kNx, 0, h->d_status + t0, st));
     }
     {
         const int m = n;

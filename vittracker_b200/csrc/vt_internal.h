@@ -75,6 +75,11 @@ size_t stem_scratch_floats(int S);
 int launch_stem(const float* img, int S, int n, const ModelW& w, float* scratch, float* tokens,
                 int tok_stride_rows, int tok_off, cudaStream_t st);
 
+// Crop + stem straight from raw uint8 frames (the first conv layer gathers its tile from the frame).
+int launch_crop_stem(const uint8_t* frames, const int64_t* frame_offsets, const int32_t* frame_hw, const double* boxes,
+                     double factor, int S, int n, const ModelW& w, float* scratch, float* tokens, int tok_stride_rows,
+                     int tok_off, int32_t* out_status, cudaStream_t st);
+
 // ViT blocks (fp32 SIMT): tokens_z [n][64][48] (stride z_stride rows per track), tokens_x likewise; in place
 // result written to out [n][320][48]; taps (or null) receives [depth][n][320][48].
 int launch_blocks_simt(const float* tok_z, int z_stride_rows, const float* tok_x, int x_stride_rows,

@@ -8,6 +8,7 @@
 // in shared memory as [cin][ky][kx][cout]; a thread owns P output pixels x QG output channels and
 // reads its weights with broadcast vector loads.  The last layer writes tokens (row = y*16+x,
 // token-major [token][48]) with the positional embedding added (vit_dist.py:53,81-82).
+#include "vt_geom.cuh"
 #include "vt_internal.h"
 
 namespace vt {
@@ -48,74 +49,13 @@ struct ConvCfg {
     static_assert(kPitch % 2 == 0 && kOOff % 2 == 0, "8-byte aligned odd-slot stores");
 };
 
+// Accumulate and store: the tile / weights / bias are in shared memory (see ConvCfg for the tile layout).
 template <int CIN, int COUT, int QG, int P, int TW, int TH, bool HSWISH, bool TOKENS>
-__global__ void __launch_bounds__(ConvCfg<CIN, COUT, QG, P, TW, TH>::kThreads)
-conv3x3s2_kernel(const float* __restrict__ in, int Hin, int Win, const float* __restrict__ wg,
-                 const float* __restrict__ bg, float* __restrict__ out, const float* __restrict__ pos,
-                 int tok_stride_rows, int tok_off) {
+__device__ __forceinline__ void conv_compute(const float* tile, const float* ws, const float* bs, int tx0, int ty0, int Hout,
+                                             int Wout, int b, float* __restrict__ out, const float* __restrict__ pos,
+                                             int tok_stride_rows, int tok_off) {
     using K = ConvCfg<CIN, COUT, QG, P, TW, TH>;
-    extern __shared__ __align__(16) float smem[];
-    float* tile = smem;
-    float* ws = smem + K::kTileFloats;
-    float* bs = ws + K::kWFloats;
-
-    const int Hout = Hin >> 1, Wout = Win >> 1;
-    const int tiles_x = (Wout + TW - 1) / TW;
-    const int tx0 = (blockIdx.x % tiles_x) * TW;
-    const int ty0 = (blockIdx.x / tiles_x) * TH;
-    const int b = blockIdx.y;
     const int tid = threadIdx.x;
-
-    // weights / bias / input tile are staged with cp.async: every load is in flight at once (the tile
-    // fill was latency-bound as a loop of dependent ld.global + st.shared); padding is zero-filled
-    for (int i = tid * 4; i < K::kWFloats; i += K::kThreads * 4) cp_async<16>(ws + i, wg + i, true);
-    if (tid < COUT) cp_async<4>(bs + tid, bg + tid, true);
-
-    // Input tile: aligned float4 loads (chunk j of a row covers input columns 2*tx0-4+4j .. +3), several
-    // in flight per thread, de-interleaved in registers.  Win is a multiple of 4, so a chunk is entirely
-    // inside or outside the image; outside (and rows outside) is the convolution's zero padding.
-    {
-        const float* inb = in + (size_t)b * CIN * Hin * Win;
-        const int gx0 = 2 * tx0 - 4, iy0 = 2 * ty0 - 1;
-        constexpr int kItems = CIN * K::kInRows * K::kChunks;
-        constexpr int kBatch = 4;
-#pragma unroll 1
-        for (int i0 = tid; i0 < kItems; i0 += kBatch * K::kThreads) {
-            float4 v[kBatch];
-            int dst[kBatch], jj[kBatch];
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                const int i = i0 + u * K::kThreads;
-                const int j = i % K::kChunks;
-                const int rr = i / K::kChunks;                // ci * kInRows + r
-                const int r = rr % K::kInRows;
-                const int ci = rr / K::kInRows;
-                const int gx = gx0 + 4 * j, gy = iy0 + r;
-                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                jj[u] = j;
-                dst[u] = (i < kItems) ? rr * K::kPitch : -1;
-                if (i < kItems && gx >= 0 && gx < Win && gy >= 0 && gy < Hin)
-                    v[u] = __ldg(reinterpret_cast<const float4*>(inb + ((size_t)ci * Hin + gy) * Win + gx));
-            }
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                if (dst[u] < 0) continue;
-                float* row = tile + dst[u];
-                const int j = jj[u];
-                if (j == 0) {
-                    row[K::kEOff] = v[u].w;                                              // c = 0 -> E[0]
-                } else {
-                    // c = 4j-3 (odd) 4j-2 (even) 4j-1 (odd) 4j (even) -> O[2j-2], E[2j-1], O[2j-1], E[2j]
-                    *reinterpret_cast<float2*>(row + K::kOOff + 2 * j - 2) = make_float2(v[u].x, v[u].z);
-                    *reinterpret_cast<float2*>(row + K::kEOff + 2 * j - 1) = make_float2(v[u].y, v[u].w);
-                }
-            }
-        }
-    }
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    __syncthreads();
-
     const int cg = tid / K::kPixGroups;                 // warp-uniform channel group
     const int pg = tid % K::kPixGroups;
     const int lane = pg & 31, wq = pg >> 5;
@@ -198,6 +138,187 @@ conv3x3s2_kernel(const float* __restrict__ in, int Hin, int Win, const float* __
 }
 
 template <int CIN, int COUT, int QG, int P, int TW, int TH, bool HSWISH, bool TOKENS>
+__global__ void __launch_bounds__(ConvCfg<CIN, COUT, QG, P, TW, TH>::kThreads)
+conv3x3s2_kernel(const float* __restrict__ in, int Hin, int Win, const float* __restrict__ wg,
+                 const float* __restrict__ bg, float* __restrict__ out, const float* __restrict__ pos,
+                 int tok_stride_rows, int tok_off) {
+    using K = ConvCfg<CIN, COUT, QG, P, TW, TH>;
+    extern __shared__ __align__(16) float smem[];
+    float* tile = smem;
+    float* ws = smem + K::kTileFloats;
+    float* bs = ws + K::kWFloats;
+
+    const int Hout = Hin >> 1, Wout = Win >> 1;
+    const int tiles_x = (Wout + TW - 1) / TW;
+    const int tx0 = (blockIdx.x % tiles_x) * TW;
+    const int ty0 = (blockIdx.x / tiles_x) * TH;
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x;
+
+    // weights / bias / input tile are staged with cp.async: every load is in flight at once (the tile
+    // fill was latency-bound as a loop of dependent ld.global + st.shared); padding is zero-filled
+    for (int i = tid * 4; i < K::kWFloats; i += K::kThreads * 4) cp_async<16>(ws + i, wg + i, true);
+    if (tid < COUT) cp_async<4>(bs + tid, bg + tid, true);
+
+    // Input tile: aligned float4 loads (chunk j of a row covers input columns 2*tx0-4+4j .. +3), several
+    // in flight per thread, de-interleaved in registers.  Win is a multiple of 4, so a chunk is entirely
+    // inside or outside the image; outside (and rows outside) is the convolution's zero padding.
+    {
+        const float* inb = in + (size_t)b * CIN * Hin * Win;
+        const int gx0 = 2 * tx0 - 4, iy0 = 2 * ty0 - 1;
+        constexpr int kItems = CIN * K::kInRows * K::kChunks;
+        constexpr int kBatch = 4;
+#pragma unroll 1
+        for (int i0 = tid; i0 < kItems; i0 += kBatch * K::kThreads) {
+            float4 v[kBatch];
+            int dst[kBatch], jj[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const int i = i0 + u * K::kThreads;
+                const int j = i % K::kChunks;
+                const int rr = i / K::kChunks;                // ci * kInRows + r
+                const int r = rr % K::kInRows;
+                const int ci = rr / K::kInRows;
+                const int gx = gx0 + 4 * j, gy = iy0 + r;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                jj[u] = j;
+                dst[u] = (i < kItems) ? rr * K::kPitch : -1;
+                if (i < kItems && gx >= 0 && gx < Win && gy >= 0 && gy < Hin)
+                    v[u] = __ldg(reinterpret_cast<const float4*>(inb + ((size_t)ci * Hin + gy) * Win + gx));
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                if (dst[u] < 0) continue;
+                float* row = tile + dst[u];
+                const int j = jj[u];
+                if (j == 0) {
+                    row[K::kEOff] = v[u].w;                                              // c = 0 -> E[0]
+                } else {
+                    // c = 4j-3 (odd) 4j-2 (even) 4j-1 (odd) 4j (even) -> O[2j-2], E[2j-1], O[2j-1], E[2j]
+                    *reinterpret_cast<float2*>(row + K::kOOff + 2 * j - 2) = make_float2(v[u].x, v[u].z);
+                    *reinterpret_cast<float2*>(row + K::kEOff + 2 * j - 1) = make_float2(v[u].y, v[u].w);
+                }
+            }
+        }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncthreads();
+
+    conv_compute<CIN, COUT, QG, P, TW, TH, HSWISH, TOKENS>(tile, ws, bs, tx0, ty0, Hout, Wout, b, out, pos, tok_stride_rows, tok_off);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Fused K1 + first stem layer: the 65 x 65 x 3 input tile of conv1 is gathered straight from the raw
+// uint8 frame (crop + zero pad + OpenCV-exact fixed-point bilinear + normalisation LUT, exactly the
+// arithmetic of crop_normalize_kernel in vt_crop.cu), so the normalised 3 x S x S crop is never
+// written to or re-read from HBM.  Column / row taps are computed once per CTA (float64 geometry).
+// ---------------------------------------------------------------------------------------------------
+using Conv1Cfg = ConvCfg<3, 6, 6, 4, 32, 32>;
+constexpr int kCc1Threads = Conv1Cfg::kThreads;                         // 256
+constexpr int kCc1TileSide = 2 * 32 + 1;                                // 65 resized-crop pixels per side
+constexpr size_t kCc1SmemBytes = Conv1Cfg::kSmemBytes + 64 + 2 * 80 * sizeof(int4) + 768 * sizeof(float);
+
+template <int S>
+__global__ void __launch_bounds__(kCc1Threads)
+crop_conv1_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict__ frame_offsets,
+                  const int32_t* __restrict__ frame_hw, const double* __restrict__ boxes, double factor,
+                  const float* __restrict__ lut, const float* __restrict__ wg, const float* __restrict__ bg,
+                  float* __restrict__ out, int32_t* __restrict__ out_status) {
+    using K = Conv1Cfg;
+    extern __shared__ __align__(16) float smem[];
+    float* tile = smem;
+    float* ws = smem + K::kTileFloats;
+    float* bs = ws + K::kWFloats;
+    int4* s_col = reinterpret_cast<int4*>(smem + ((K::kTileFloats + K::kWFloats + 6 + 3) / 4 * 4));
+    int4* s_row = s_col + 80;
+    float* s_lut = reinterpret_cast<float*>(s_row + 80);
+
+    constexpr int Hout = S / 2;
+    constexpr int tiles_x = Hout / 32;
+    const int tx0 = (blockIdx.x % tiles_x) * 32;
+    const int ty0 = (blockIdx.x / tiles_x) * 32;
+    const int item = blockIdx.y;
+    const int tid = threadIdx.x;
+
+    for (int i = tid * 4; i < K::kWFloats; i += kCc1Threads * 4) cp_async<16>(ws + i, wg + i, true);
+    if (tid < 6) cp_async<4>(bs + tid, bg + tid, true);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    for (int i = tid; i < 768; i += kCc1Threads) s_lut[i] = __ldg(lut + i);
+
+    const int H = frame_hw[2 * item], W = frame_hw[2 * item + 1];
+    const double* bx = boxes + 4 * item;
+    const CropGeom g = crop_geometry(bx[0], bx[1], bx[2], bx[3], factor, S, H, W);
+    if (blockIdx.x == 0 && tid == 0 && out_status) out_status[item] = g.status;
+    const double scale = resize_scale(S, g.crop_sz);
+
+    // tap tables: .x/.y = byte offsets of the two taps (0 when the tap is padding), .z = weights (lo | hi << 16,
+    // 0 for a padding tap), .w = flags (bit 0: outside the resized crop = convolution zero padding; rows: bit 1/2 tap valid)
+    if (tid < kCc1TileSide) {
+        const int d = 2 * tx0 - 1 + tid;
+        int4 t = make_int4(0, 0, 0, 1);
+        if (d >= 0 && d < S && g.status == 0) {
+            int s0, s1, a0, a1; bool w0, w1;
+            tap_x(d, scale, g.crop_sz, s0, s1, a0, a1, w0, w1);
+            const int ix0 = g.x1 + s0, ix1 = g.x1 + s1;
+            const bool v0 = ix0 >= 0 && ix0 <= W - 2, v1 = ix1 >= 0 && ix1 <= W - 2;
+            t = make_int4(v0 ? ix0 * 3 : 0, v1 ? ix1 * 3 : 0, (v0 ? a0 : 0) | ((v1 ? a1 : 0) << 16), 0);
+        }
+        s_col[tid] = t;
+    } else if (tid >= 128 && tid < 128 + kCc1TileSide) {
+        const int d = 2 * ty0 - 1 + (tid - 128);
+        int4 t = make_int4(0, 0, 0, 1);
+        if (d >= 0 && d < S && g.status == 0) {
+            int r0, r1, b0, b1; bool w0, w1;
+            tap_y(d, scale, g.crop_sz, r0, r1, b0, b1, w0, w1);
+            const int iy0 = g.y1 + r0, iy1 = g.y1 + r1;
+            const bool v0 = iy0 >= 0 && iy0 <= H - 2, v1 = iy1 >= 0 && iy1 <= H - 2;
+            t = make_int4(v0 ? iy0 * W * 3 : 0, v1 ? iy1 * W * 3 : 0, b0 | (b1 << 16), (v0 ? 2 : 0) | (v1 ? 4 : 0));
+        }
+        s_row[tid - 128] = t;
+    }
+    __syncthreads();
+
+    const uint8_t* __restrict__ im = frames + frame_offsets[item];
+    constexpr int kPix = kCc1TileSide * kCc1TileSide;
+#pragma unroll 2
+    for (int i = tid; i < kPix; i += kCc1Threads) {
+        const int r = i / kCc1TileSide, c = i - r * kCc1TileSide;
+        const int4 ct = s_col[c], rt = s_row[r];
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+        if (!((ct.w | rt.w) & 1)) {
+            const uint8_t* q00 = im + rt.x + ct.x;
+            const uint8_t* q01 = im + rt.x + ct.y;
+            const uint8_t* q10 = im + rt.y + ct.x;
+            const uint8_t* q11 = im + rt.y + ct.y;
+            int p00[3], p01[3], p10[3], p11[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) { p00[ch] = __ldg(q00 + ch); p01[ch] = __ldg(q01 + ch); p10[ch] = __ldg(q10 + ch); p11[ch] = __ldg(q11 + ch); }
+            const int a0 = ct.z & 0xffff, a1 = ct.z >> 16, b0 = rt.z & 0xffff, b1 = rt.z >> 16;
+            const bool vy0 = rt.w & 2, vy1 = rt.w & 4;
+            float vv[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const int h0 = vy0 ? p00[ch] * a0 + p01[ch] * a1 : 0;
+                const int h1 = vy1 ? p10[ch] * a0 + p11[ch] * a1 : 0;
+                int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+                v = min(max(v, 0), 255);
+                vv[ch] = s_lut[ch * 256 + v];
+            }
+            v0 = vv[0]; v1 = vv[1]; v2 = vv[2];
+        }
+        const int slot = (c & 1) ? (K::kOOff + (c >> 1)) : (K::kEOff + (c >> 1));
+        float* dst = tile + r * K::kPitch + slot;
+        dst[0] = v0;
+        dst[K::kInRows * K::kPitch] = v1;
+        dst[2 * K::kInRows * K::kPitch] = v2;
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncthreads();
+    conv_compute<3, 6, 6, 4, 32, 32, true, false>(tile, ws, bs, tx0, ty0, Hout, Hout, item, out, nullptr, 0, 0);
+}
+
+template <int CIN, int COUT, int QG, int P, int TW, int TH, bool HSWISH, bool TOKENS>
 static int run_conv(const float* in, int Hin, int n, const StemLayerW& w, float* out, const float* pos,
                     int tok_stride_rows, int tok_off, cudaStream_t st) {
     using K = ConvCfg<CIN, COUT, QG, P, TW, TH>;
@@ -224,6 +345,51 @@ static int run_conv(const float* in, int Hin, int n, const StemLayerW& w, float*
 size_t stem_scratch_floats(int S) {
     // conv1 out 6 x S/2 x S/2, conv2 out 12 x S/4 x S/4, conv3 out 24 x S/8 x S/8
     return (size_t)6 * (S / 2) * (S / 2) + (size_t)12 * (S / 4) * (S / 4) + (size_t)24 * (S / 8) * (S / 8);
+}
+
+template <int S>
+static int run_crop_conv1(const uint8_t* frames, const int64_t* frame_offsets, const int32_t* frame_hw, const double* boxes,
+                          double factor, int n, const ModelW& w, float* out, int32_t* out_status, cudaStream_t st) {
+    auto kern = crop_conv1_kernel<S>;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCc1SmemBytes) != cudaSuccess) return -1;
+        configured = true;
+    }
+    constexpr int tiles = (S / 64) * (S / 64);
+    int launched = 0;
+    for (int first = 0; first < n; first += 32768) {
+        const int m = min(32768, n - first);
+        kern<<<dim3(tiles, m), kCc1Threads, kCc1SmemBytes, st>>>(frames, frame_offsets + first, frame_hw + 2 * first, boxes + 4 * first, factor,
+                                                                 w.lut, w.stem[0].w, w.stem[0].b, out + (size_t)first * 6 * (S / 2) * (S / 2),
+                                                                 out_status ? out_status + first : nullptr);
+        ++launched;
+    }
+    return cudaGetLastError() == cudaSuccess ? launched : -1;
+}
+
+// Crop + stem straight from raw frames (fused first layer); same outputs as launch_crop_normalize + launch_stem.
+int launch_crop_stem(const uint8_t* frames, const int64_t* frame_offsets, const int32_t* frame_hw, const double* boxes,
+                     double factor, int S, int n, const ModelW& w, float* scratch, float* tokens, int tok_stride_rows,
+                     int tok_off, int32_t* out_status, cudaStream_t st) {
+    if (n <= 0) return 0;
+    float* a1 = scratch;
+    float* a2 = a1 + (size_t)n * 6 * (S / 2) * (S / 2);
+    float* a3 = a2 + (size_t)n * 12 * (S / 4) * (S / 4);
+    const float* pos = (S == kSx) ? w.pos_x : w.pos_z;
+    int total = 0, r;
+    if (S == 256) r = run_crop_conv1<256>(frames, frame_offsets, frame_hw, boxes, factor, n, w, a1, out_status, st);
+    else if (S == 128) r = run_crop_conv1<128>(frames, frame_offsets, frame_hw, boxes, factor, n, w, a1, out_status, st);
+    else return -1;
+    if (r < 0) return r;
+    total += r;
+    if ((r = run_conv<6, 12, 12, 2, 32, 16, true, false>(a1, S / 2, n, w.stem[1], a2, nullptr, 0, 0, st)) < 0) return r;
+    total += r;
+    if ((r = run_conv<12, 24, 12, 2, 32, 8, true, false>(a2, S / 4, n, w.stem[2], a3, nullptr, 0, 0, st)) < 0) return r;
+    total += r;
+    if ((r = run_conv<24, 48, 12, 4, 16, 16, false, true>(a3, S / 8, n, w.stem[3], tokens, pos, tok_stride_rows, tok_off, st)) < 0) return r;
+    total += r;
+    return total;
 }
 
 int launch_stem(const float* img, int S, int n, const ModelW& w, float* scratch, float* tokens,
