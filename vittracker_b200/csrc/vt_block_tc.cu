@@ -27,6 +27,18 @@ namespace vt {
 
 using namespace tc;
 
+// Optional per-step cycle trace of CTA 0 (development aid): -DVT_TC_TRACE, read back with vt_tc_trace_read().
+#ifdef VT_TC_TRACE
+__device__ long long g_tc_trace[2][4096];
+__device__ int g_tc_trace_n[2];
+#define TC_TRACE(side)                                                                      \
+    do {                                                                                    \
+        if (blockIdx.x == 0) { int k__ = g_tc_trace_n[side]; if (k__ < 4096) { g_tc_trace[side][k__] = clock64(); g_tc_trace_n[side] = k__ + 1; } } \
+    } while (0)
+#else
+#define TC_TRACE(side) do {} while (0)
+#endif
+
 namespace {
 
 constexpr int kTcThreads = 13 * 32;
@@ -76,9 +88,11 @@ struct Epi {
         if (lane == 0) mbar_arrive(mb_go);
     }
     __device__ __forceinline__ void wait_done() {
+        if (threadIdx.x == 0) TC_TRACE(1);
         mbar_wait(mb_done, done_ph);
         done_ph ^= 1;
         tc_fence_after();
+        if (threadIdx.x == 0) TC_TRACE(1);
     }
 
     // sum over the 48 columns of a row (three thirds) of a per-thread partial; `arr` selects the scratch array
@@ -113,7 +127,30 @@ struct Epi {
     }
 };
 
-__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752f)); }
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// GELU(v) = 0.5 v (1 + erf(v / sqrt 2)) with erf from Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7, about one
+// fp32 ulp of the 1 + erf term): one reciprocal, one exponential and a degree-5 Horner instead of erff's
+// two branch-selected polynomials (erff was ~30 % of this kernel's CUDA-core instructions).
+__device__ __forceinline__ float gelu_erf(float v) {
+    const float z = fabsf(v) * 0.70710678118654752f;
+    const float t = rcp_approx(fmaf(0.3275911f, z, 1.f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = ex2_approx(-1.4426950408889634f * z * z);
+    const float erf_abs = fmaf(-p * t, e, 1.f);                 // erf(|v| / sqrt 2)
+    return 0.5f * v * (1.f + copysignf(erf_abs, v));
+}
 
 }  // namespace
 
@@ -142,19 +179,19 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tbase = *s_tmem;
+    const uint32_t tbase = __shfl_sync(0xffffffffu, *s_tmem, 0);       // provably warp-uniform
     const uint32_t sbase = smem_u32(smem);
 
     if (warp == 12) {
         // =========================== control: weight loads + MMA issue (one thread) ===========================
-        if (lane == 0) {
+        {   // the whole warp runs this program convergently; MMA / commit / bulk copy are done by one elected lane
             uint32_t go_ph = 0, wa_ph = 0, wb_ph = 0;
             const uint32_t id48 = instr_desc_f16(128, 48, false), id48mn = instr_desc_f16(128, 48, true);
             const uint32_t id144 = instr_desc_f16(128, 144, false), id160 = instr_desc_f16(128, 160, false);
             const uint32_t id192 = instr_desc_f16(128, 192, false);
-            auto wait_go = [&]() { mbar_wait(mb_go, go_ph); go_ph ^= 1; tc_fence_after(); };
-            auto load_wa = [&](int blk) { mbar_arrive_expect_tx(mb_wa, kTcWaBytes); bulk_g2s(smem + kSmWa, w.tc[blk].wa, kTcWaBytes, mb_wa); };
-            auto load_wb = [&](int blk) { mbar_arrive_expect_tx(mb_wb, kTcWbBytes); bulk_g2s(smem + kSmX, w.tc[blk].wb, kTcWbBytes, mb_wb); };
+            auto wait_go = [&]() { TC_TRACE(0); mbar_wait(mb_go, go_ph); go_ph ^= 1; tc_fence_after(); TC_TRACE(0); };
+            auto load_wa = [&](int blk) { bulk_g2s_elect(smem + kSmWa, w.tc[blk].wa, kTcWaBytes, mb_wa); };
+            auto load_wb = [&](int blk) { bulk_g2s_elect(smem + kSmX, w.tc[blk].wb, kTcWbBytes, mb_wb); };
             // D[d_col] = A(opa slot t, K = 48) x B^T, B K-major [k/8][N][8] at byte offsets b_hi / b_lo
             auto gemm_k48 = [&](int t, uint32_t d_col, uint32_t b_hi, uint32_t b_lo, int N, uint32_t idesc) {
                 const uint32_t a = tbase + kColOpa + 48 * t;
@@ -162,9 +199,9 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                 for (int ks = 0; ks < 3; ++ks) {
                     const uint64_t bh = smem_desc(sbase + b_hi + ks * 2 * N * 16, N * 16, 128);
                     const uint64_t bl = smem_desc(sbase + b_lo + ks * 2 * N * 16, N * 16, 128);
-                    mma_ts(tbase + d_col, a + 8 * ks, bh, idesc, ks > 0);           // hi * hi
-                    mma_ts(tbase + d_col, a + 24 + 8 * ks, bh, idesc, true);        // lo * hi
-                    mma_ts(tbase + d_col, a + 8 * ks, bl, idesc, true);             // hi * lo
+                    mma_ts_elect(tbase + d_col, a + 8 * ks, bh, idesc, ks > 0);           // hi * hi
+                    mma_ts_elect(tbase + d_col, a + 24 + 8 * ks, bh, idesc, true);        // lo * hi
+                    mma_ts_elect(tbase + d_col, a + 8 * ks, bl, idesc, true);             // hi * lo
                 }
             };
             auto qkv = [&](int t, uint32_t d_col) { gemm_k48(t, d_col, kSmWa, kSmWa + 13824, 144, id144); };
@@ -181,9 +218,9 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                         const uint32_t off = ks * 2 * (kN * 16) + half * 160 * 16;
                         const uint64_t bh = smem_desc(sbase + kSmKhi + off, kN * 16, 128);
                         const uint64_t bl = smem_desc(sbase + kSmKlo + off, kN * 16, 128);
-                        mma_ts(d, a + 8 * ks, bh, id160, ks > 0);
-                        mma_ts(d, a + 24 + 8 * ks, bh, id160, true);
-                        mma_ts(d, a + 8 * ks, bl, id160, true);
+                        mma_ts_elect(d, a + 8 * ks, bh, id160, ks > 0);
+                        mma_ts_elect(d, a + 24 + 8 * ks, bh, id160, true);
+                        mma_ts_elect(d, a + 8 * ks, bl, id160, true);
                     }
                 }
             };
@@ -194,9 +231,9 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                     const uint32_t a = tbase + kColBig + 16 * g;
                     const uint64_t bh = smem_desc(sbase + kSmVhi + g * 256, 128, (kN / 8) * 128);
                     const uint64_t bl = smem_desc(sbase + kSmVlo + g * 256, 128, (kN / 8) * 128);
-                    mma_ts(tbase + kColOut, a, bh, id48mn, g > 0);
-                    mma_ts(tbase + kColOut, a + 8, bh, id48mn, true);
-                    mma_ts(tbase + kColOut, a, bl, id48mn, true);
+                    mma_ts_elect(tbase + kColOut, a, bh, id48mn, g > 0);
+                    mma_ts_elect(tbase + kColOut, a + 8, bh, id48mn, true);
+                    mma_ts_elect(tbase + kColOut, a, bl, id48mn, true);
                 }
             };
             // y = gelu(h) W2^T: operand in TMEM (16-wide group g: hi 16g.., lo 16g+8..), W2 K-major [k/8][48][8], K = 192
@@ -206,9 +243,9 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                     const uint32_t a = tbase + kColBig + 16 * g;
                     const uint64_t bh = smem_desc(sbase + kSmW2hi + g * 2 * 48 * 16, 48 * 16, 128);
                     const uint64_t bl = smem_desc(sbase + kSmW2lo + g * 2 * 48 * 16, 48 * 16, 128);
-                    mma_ts(tbase + kColOut, a, bh, id48, g > 0);
-                    mma_ts(tbase + kColOut, a + 8, bh, id48, true);
-                    mma_ts(tbase + kColOut, a, bl, id48, true);
+                    mma_ts_elect(tbase + kColOut, a, bh, id48, g > 0);
+                    mma_ts_elect(tbase + kColOut, a + 8, bh, id48, true);
+                    mma_ts_elect(tbase + kColOut, a, bl, id48, true);
                 }
             };
             bool first = true;
@@ -218,24 +255,24 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                     if (first) { load_wa(0); first = false; }
                     wait_go();                                                   // 1: LN1 operands of all tiles
                     mbar_wait(mb_wa, wa_ph); wa_ph ^= 1;
-                    qkv(0, kColBig); qkv(1, kColBig + 160); mma_commit(mb_done);
-                    wait_go(); qkv(2, kColBig); mma_commit(mb_done);             // 2
-                    wait_go(); scores(0); mma_commit(mb_done);                   // 3: K, V complete
-                    wait_go(); pv(); mma_commit(mb_done);                        // 4
-                    wait_go(); proj(0); scores(1); mma_commit(mb_done);          // 5
-                    wait_go(); pv(); mma_commit(mb_done);                        // 6
-                    wait_go(); proj(1); scores(2); mma_commit(mb_done);          // 7
-                    wait_go(); pv(); mma_commit(mb_done);                        // 8
-                    wait_go(); load_wb(blk); proj(2); mma_commit(mb_done);       // 9: K/V dead -> MLP weights stream in
+                    qkv(0, kColBig); qkv(1, kColBig + 160); mma_commit_elect(mb_done);
+                    wait_go(); qkv(2, kColBig); mma_commit_elect(mb_done);             // 2
+                    wait_go(); scores(0); mma_commit_elect(mb_done);                   // 3: K, V complete
+                    wait_go(); pv(); mma_commit_elect(mb_done);                        // 4
+                    wait_go(); proj(0); scores(1); mma_commit_elect(mb_done);          // 5
+                    wait_go(); pv(); mma_commit_elect(mb_done);                        // 6
+                    wait_go(); proj(1); scores(2); mma_commit_elect(mb_done);          // 7
+                    wait_go(); pv(); mma_commit_elect(mb_done);                        // 8
+                    wait_go(); load_wb(blk); proj(2); mma_commit_elect(mb_done);       // 9: K/V dead -> MLP weights stream in
                     wait_go();                                                   // 10: Wqkv/Wproj dead -> prefetch the next block's
                     if (!(last_track && blk == kDepth - 1)) load_wa((blk + 1) % kDepth);
                     mbar_wait(mb_wb, wb_ph); wb_ph ^= 1;
-                    fc1(0); mma_commit(mb_done);
-                    wait_go(); fc2(); mma_commit(mb_done);                       // 11
-                    wait_go(); fc1(1); mma_commit(mb_done);                      // 12
-                    wait_go(); fc2(); mma_commit(mb_done);                       // 13
-                    wait_go(); fc1(2); mma_commit(mb_done);                      // 14
-                    wait_go(); fc2(); mma_commit(mb_done);                       // 15
+                    fc1(0); mma_commit_elect(mb_done);
+                    wait_go(); fc2(); mma_commit_elect(mb_done);                       // 11
+                    wait_go(); fc1(1); mma_commit_elect(mb_done);                      // 12
+                    wait_go(); fc2(); mma_commit_elect(mb_done);                       // 13
+                    wait_go(); fc1(2); mma_commit_elect(mb_done);                      // 14
+                    wait_go(); fc2(); mma_commit_elect(mb_done);                       // 15
                 }
             }
         }
@@ -333,16 +370,22 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                 // ---- attention per tile -------------------------------------------------------------------
                 float inv_l[3];
                 auto softmax = [&](int t) {
-                    // thirds own 112 / 112 / 96 score columns (7, 7, 6 groups of 16 keys)
+                    // thirds own 112 / 112 / 96 score columns (7, 7, 6 groups of 16 keys); TMEM loads are
+                    // software pipelined (group g+1 is in flight while group g is processed)
                     const int c_begin = 112 * s, groups = (s == 2) ? 6 : 7;
+                    const uint32_t a0 = e.taddr(kColBig + c_begin);
                     float m = -INFINITY;
                     if (e.active(t)) {
-                        for (int g = 0; g < groups; ++g) {
-                            uint32_t r[16];
-                            tmem_ld16(e.taddr(kColBig + c_begin + 16 * g), r);
-                            tc_wait_ld();
+                        uint32_t r[2][16];
+                        tmem_ld16(a0, r[0]);
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(r[j]));
+                        for (int g = 0; g < 7; ++g) {
+                            if (g < groups) {
+                                tc_wait_ld();
+                                if (g + 1 < groups) tmem_ld16(a0 + 16 * (g + 1), r[(g + 1) & 1]);
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(r[g & 1][j]));
+                            }
                         }
                     }
                     float* rm = e.red + 2 * 384;
@@ -352,21 +395,24 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                     float l = 0.f;
                     if (e.active(t)) {
                         const float mb = m * kLog2e;
-                        for (int g = 0; g < groups; ++g) {
-                            uint32_t r[16];
-                            const uint32_t a = e.taddr(kColBig + c_begin + 16 * g);
-                            tmem_ld16(a, r);
-                            tc_wait_ld();
-                            uint32_t hi[8], lo[8];
+                        uint32_t r[2][16];
+                        tmem_ld16(a0, r[0]);
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float p0 = exp2f(fmaf(__uint_as_float(r[2 * j]), kLog2e, -mb));
-                                const float p1 = exp2f(fmaf(__uint_as_float(r[2 * j + 1]), kLog2e, -mb));
-                                l += p0 + p1;
-                                split_pack2(p0, p1, hi[j], lo[j]);
+                        for (int g = 0; g < 7; ++g) {
+                            if (g < groups) {
+                                tc_wait_ld();
+                                if (g + 1 < groups) tmem_ld16(a0 + 16 * (g + 1), r[(g + 1) & 1]);
+                                uint32_t hi[8], lo[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const float p0 = ex2_approx(fmaf(__uint_as_float(r[g & 1][2 * j]), kLog2e, -mb));
+                                    const float p1 = ex2_approx(fmaf(__uint_as_float(r[g & 1][2 * j + 1]), kLog2e, -mb));
+                                    l += p0 + p1;
+                                    split_pack2(p0, p1, hi[j], lo[j]);
+                                }
+                                tmem_st8(a0 + 16 * g, hi);       // P overwrites S in place: [hi x8 | lo x8] per 16 keys
+                                tmem_st8(a0 + 16 * g + 8, lo);
                             }
-                            tmem_st8(a, hi);            // P overwrites S in place: [hi x8 | lo x8] per 16 keys
-                            tmem_st8(a + 8, lo);
                         }
                     }
                     e.red[3 * 384 + s * 128 + row] = l;     // summed after the next barrier (in epi_o)
@@ -408,21 +454,22 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                 // ---- MLP per tile -------------------------------------------------------------------------
                 auto gelu = [&](int t) {
                     if (!e.active(t)) return;
-#pragma unroll 1
-                    for (int g = 0; g < 4; ++g) {                                 // third s owns hidden columns [64 s, 64 s + 64)
-                        const uint32_t a = e.taddr(kColBig + 64 * s + 16 * g);
-                        uint32_t r[16];
-                        tmem_ld16(a, r);
+                    const uint32_t a0 = e.taddr(kColBig + 64 * s);                // third s owns hidden columns [64 s, 64 s + 64)
+                    uint32_t r[2][16];
+                    tmem_ld16(a0, r[0]);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
                         tc_wait_ld();
+                        if (g + 1 < 4) tmem_ld16(a0 + 16 * (g + 1), r[(g + 1) & 1]);
                         uint32_t hi[8], lo[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float h0 = gelu_erf(__uint_as_float(r[2 * j]) + par[kPBfc1 + 64 * s + 16 * g + 2 * j]);
-                            const float h1 = gelu_erf(__uint_as_float(r[2 * j + 1]) + par[kPBfc1 + 64 * s + 16 * g + 2 * j + 1]);
+                            const float h0 = gelu_erf(__uint_as_float(r[g & 1][2 * j]) + par[kPBfc1 + 64 * s + 16 * g + 2 * j]);
+                            const float h1 = gelu_erf(__uint_as_float(r[g & 1][2 * j + 1]) + par[kPBfc1 + 64 * s + 16 * g + 2 * j + 1]);
                             split_pack2(h0, h1, hi[j], lo[j]);
                         }
-                        tmem_st8(a, hi);
-                        tmem_st8(a + 8, lo);
+                        tmem_st8(a0 + 16 * g, hi);
+                        tmem_st8(a0 + 16 * g + 8, lo);
                     }
                 };
                 auto epi_fc2 = [&](int t) {
@@ -466,6 +513,17 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
     __syncthreads();
     if (warp == 12) tmem_dealloc(tbase, 512);
 }
+
+#ifdef VT_TC_TRACE
+extern "C" int vt_tc_trace_read(long long* host, int* n) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(n, g_tc_trace_n, 2 * sizeof(int));
+    cudaMemcpyFromSymbol(host, g_tc_trace, sizeof(long long) * 2 * 4096);
+    int zero[2] = {0, 0};
+    cudaMemcpyToSymbol(g_tc_trace_n, zero, sizeof zero);
+    return 0;
+}
+#endif
 
 int launch_blocks_tc(const float* tok_z, int z_stride_rows, const float* tok_x, int x_stride_rows, float* out, int n,
                      const ModelW& w, float* taps, size_t tap_stride, int num_sms, cudaStream_t st) {

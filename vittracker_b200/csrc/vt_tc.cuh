@@ -133,6 +133,31 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- warp-convergent variants: every lane executes the statement, one elected lane performs it -----------
+// (issuing from inside `if (lane == 0)` makes the compiler wrap each UTCHMMA in a per-lane waterfall loop)
+__device__ __forceinline__ void mma_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+        : "memory");
+}
+// arm `bar` with `bytes` and start the bulk copy, both by the elected lane
+__device__ __forceinline__ void bulk_g2s_elect(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t.reg .b64 st;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q mbarrier.arrive.expect_tx.shared::cta.b64 st, [%3], %2;\n\t"
+        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
 // ---- fp32 -> fp16 hi/lo split ------------------------------------------------------------------------
 // v ~= hi + lo with hi = fp16(v), lo = fp16(v - hi): ~22 significant bits for |v| well inside fp16 range.
 __device__ __forceinline__ void split_pack2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
