@@ -336,3 +336,56 @@ def test_batched_closed_loop_matches_single_tracker(cfg, golden_track, blocks):
             s = singles[k].track(frames[t % 4], {})
             assert close(out[k, :4], s["target_bbox"], atol=1e-9, rtol=0), (t, k, out[k], s["target_bbox"])
     assert close(out[0, :4], g["stable_states"][7])
+
+
+# ------------------------------------------------------------------------------------------------
+# multi-GPU: tracks sharded over ranks, one NCCL all-gather of the boxes (needs >= 2 GPUs)
+# ------------------------------------------------------------------------------------------------
+_NCCL_WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["VT_ROOT"])
+from oracle import vt_oracle as O
+from vittracker_b200 import BatchedTracker, FramePool, ShardedTracker, load_cfg, shard_range
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%s" % os.environ["VT_PORT"], rank=rank, world_size=world,
+                        device_id=torch.device("cuda", rank))
+total, F = 37, 3                                   # ragged split on purpose
+cfg = load_cfg()
+sd = O.make_state_dict(seed=4, stress=True)
+frames = O.synth_frames(F, 240, 320, seed=5, smooth=True)
+boxes = O.synth_boxes(total, 240, 320, seed=6)
+lo, hi = shard_range(total, rank, world)
+bt = BatchedTracker(cfg, sd, max_tracks=hi - lo)
+pool = FramePool(frames, bt.device)
+fidx = torch.arange(total) % F
+bt.initialize(pool, fidx[lo:hi], boxes[lo:hi])
+sh = ShardedTracker(total, bt)
+local = bt.track(pool, ((fidx + 1) % F)[lo:hi])
+full = sh.gather(local).cpu()
+assert full.shape == (total, 5)
+if rank == 0:                                      # single-GPU run of all tracks must give the same boxes
+    ref = BatchedTracker(cfg, sd, max_tracks=total)
+    ref.initialize(pool, fidx, boxes)
+    want = ref.track(pool, (fidx + 1) % F).cpu()
+    assert torch.equal(full, want), (full - want).abs().max()
+dist.barrier()
+dist.destroy_process_group()
+print("OK", rank)
+'''
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_tracks_nccl_gather_matches_single_gpu(tmp_path):
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "worker.py"
+    script.write_text(_NCCL_WORKER)
+    port = str(29600 + os.getpid() % 2000)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", VT_ROOT=root, VT_PORT=port, MASTER_ADDR="127.0.0.1")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=600)
+        assert p.returncode == 0 and "OK" in out, out[-3000:]
