@@ -45,6 +45,18 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def ncu_traffic(blocks, items_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the block kernel, from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json, bytes per track), scaled to this launch size."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(p) as f:
+            per_track = json.load(f)[blocks]["dram_bytes_per_track"]
+        return per_track * items_per_launch
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -202,7 +214,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tracks", type=int, default=1024, help="concurrent tracks per GPU")
     ap.add_argument("--frames", type=int, default=64, help="distinct frames resident per GPU")
-    ap.add_argument("--chunk", type=int, default=256)
+    ap.add_argument("--chunk", type=int, default=1024)
     ap.add_argument("--blocks", default="tcgen05", choices=["simt", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
@@ -285,28 +297,35 @@ def main():
     ms = float(tms.item())
     value = n * world * K / (ms / 1e3)
 
-    # ---- end to end through the public API with HOST buffers: frames H2D + boxes H2D + step + boxes D2H
+    # ---- end to end through the public API with HOST buffers: every step uploads its 64 frames (pinned host
+    # memory -> HBM on a copy stream, double-buffered so that the upload of step t+1 overlaps the compute of
+    # step t), uploads the boxes, runs the step and reads the boxes back
+    from vittracker_b200 import PipelinedFrameFeeder
     host_pools = [torch.from_numpy(O.synth_frames(F, FRAME_H, FRAME_W, seed=5000 + rank + k)).pin_memory() for k in range(2)]
     host_boxes = step_boxes.cpu().pin_memory()
     host_out = torch.empty((n * world if world > 1 else n, 5), dtype=torch.float64).pin_memory()
     dev_boxes = torch.empty((n, 4), dtype=torch.float64, device=dev)
+    feeder = PipelinedFrameFeeder(F, FRAME_H, FRAME_W, dev)
 
-    def e2e_step(t):
-        pool.data.copy_(host_pools[t % 2], non_blocking=True)
-        dev_boxes.copy_(host_boxes[t % nsets], non_blocking=True)
-        bt.engine.tracks_set_state(dev_boxes, first=0)
-        out = bt.track_offsets(pool.data, step_offsets[t % F], update_state=True)
-        if sharded is not None:
-            out = sharded.gather(out)
-        host_out.copy_(out, non_blocking=True)
+    def e2e_run(steps):
+        feeder.upload(host_pools[0])
+        for t in range(steps):
+            fp = feeder.acquire()
+            if t + 1 < steps:
+                feeder.upload(host_pools[(t + 1) % 2])
+            dev_boxes.copy_(host_boxes[t % nsets], non_blocking=True)
+            bt.engine.tracks_set_state(dev_boxes, first=0)
+            out = bt.track_offsets(fp.data, step_offsets[t % F], update_state=True)
+            if sharded is not None:
+                out = sharded.gather(out)
+            host_out.copy_(out, non_blocking=True)
+            feeder.release(fp)
 
-    for t in range(2):
-        e2e_step(t)
+    e2e_run(3)
     barrier()
     Ke = max(3, min(K, 10))
     e0.record()
-    for t in range(Ke):
-        e2e_step(t)
+    e2e_run(Ke)
     e1.record()
     barrier()
     tms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -335,7 +354,7 @@ def main():
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
         "roofline": {"kernel": "blocks_simt_kernel" if args.blocks == "simt" else "blocks_tc_kernel", "bound": "tensor",
                      "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+                     "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": ncu_traffic(args.blocks, blk_items),
                      "peak_source": peaks["source"] + ", bf16 dense sustained",
                      "algorithmic_flop_per_launch": FLOP_BLOCKS * blk_items, "avg_launch_ms": blk_ms,
                      "share_of_step": blk["ms"] / total_stage_ms},
@@ -343,7 +362,8 @@ def main():
                    for k, v in stages.items()},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "note": "per step: H2D of all %d frames + boxes from pinned host memory, step, D2H of the boxes" % F},
+                "note": "per step: H2D of all %d frames + boxes from pinned host memory (upload of step t+1 overlaps compute "
+                        "of step t on a copy stream), step, D2H of the boxes" % F},
         "gpu_launches": int(launches),
     }
     if crop["ms"] > 0:

@@ -79,6 +79,45 @@ class BatchedTracker:
         return r
 
 
+class PipelinedFrameFeeder:
+    """Host -> HBM frame ingest overlapped with tracking: two device frame pools and a copy stream.
+
+    ``upload(host_frames)`` starts the asynchronous copy of the next step's frames (pinned uint8
+    [F, H, W, 3]) into the idle pool; ``acquire()`` makes the compute stream wait for the oldest
+    pending upload and returns that pool; ``release(pool)`` marks the pool reusable once the work
+    queued so far on the compute stream (the step that read it) has finished."""
+
+    def __init__(self, F: int, H: int, W: int, device: torch.device):
+        self.device = device
+        self.pools = [FramePool(torch.zeros((F, H, W, 3), dtype=torch.uint8), device) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self._ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self._free = [None, None]
+        self._pending = []
+        self._next = 0
+
+    def upload(self, host_frames: torch.Tensor) -> None:
+        i = self._next
+        self._next ^= 1
+        with torch.cuda.stream(self.copy_stream):
+            if self._free[i] is not None:
+                self.copy_stream.wait_event(self._free[i])
+            self.pools[i].data.copy_(host_frames, non_blocking=True)
+            self._ready[i].record(self.copy_stream)
+        self._pending.append(i)
+
+    def acquire(self) -> FramePool:
+        i = self._pending.pop(0)
+        torch.cuda.current_stream(self.device).wait_event(self._ready[i])
+        return self.pools[i]
+
+    def release(self, pool: FramePool) -> None:
+        i = 0 if pool is self.pools[0] else 1
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._free[i] = ev
+
+
 def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous slice [lo, hi) of ``total`` tracks owned by ``rank`` (sizes differ by at most one)."""
     base, rem = divmod(total, world)

@@ -222,7 +222,7 @@ int vt_create(const VtConfig* cfg, VtHandle* out) {
     VtHandle h = new VtContext();
     h->cfg = *cfg;
     h->num_sms = prop.multiProcessorCount;
-    h->chunk = cfg->chunk_tracks > 0 ? cfg->chunk_tracks : 256;
+    h->chunk = cfg->chunk_tracks > 0 ? cfg->chunk_tracks : 1024;
     if (h->chunk > cfg->max_tracks) h->chunk = cfg->max_tracks;
     if (cudaSetDevice(cfg->device) != cudaSuccess) { delete h; return fail(nullptr, VT_ERR_CUDA, "cudaSetDevice failed"); }
     const size_t ch = h->chunk, mt = cfg->max_tracks;

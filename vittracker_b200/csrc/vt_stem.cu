@@ -253,7 +253,8 @@ crop_conv1_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict_
     const double scale = resize_scale(S, g.crop_sz);
 
     // tap tables: .x/.y = byte offsets of the two taps (0 when the tap is padding), .z = weights (lo | hi << 16,
-    // 0 for a padding tap), .w = flags (bit 0: outside the resized crop = convolution zero padding; rows: bit 1/2 tap valid)
+    // 0 for a padding tap: a zero pixel and a zero weight give the same products), .w = 1 when the position is
+    // outside the resized crop (= the convolution's zero padding, which is 0.0f and not the normalised pixel 0)
     if (tid < kCc1TileSide) {
         const int d = 2 * tx0 - 1 + tid;
         int4 t = make_int4(0, 0, 0, 1);
@@ -273,45 +274,50 @@ crop_conv1_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict_
             tap_y(d, scale, g.crop_sz, r0, r1, b0, b1, w0, w1);
             const int iy0 = g.y1 + r0, iy1 = g.y1 + r1;
             const bool v0 = iy0 >= 0 && iy0 <= H - 2, v1 = iy1 >= 0 && iy1 <= H - 2;
-            t = make_int4(v0 ? iy0 * W * 3 : 0, v1 ? iy1 * W * 3 : 0, b0 | (b1 << 16), (v0 ? 2 : 0) | (v1 ? 4 : 0));
+            t = make_int4(v0 ? iy0 * W * 3 : 0, v1 ? iy1 * W * 3 : 0, (v0 ? b0 : 0) | ((v1 ? b1 : 0) << 16), 0);
         }
         s_row[tid - 128] = t;
     }
     __syncthreads();
 
     const uint8_t* __restrict__ im = frames + frame_offsets[item];
-    constexpr int kPix = kCc1TileSide * kCc1TileSide;
-#pragma unroll 2
-    for (int i = tid; i < kPix; i += kCc1Threads) {
-        const int r = i / kCc1TileSide, c = i - r * kCc1TileSide;
-        const int4 ct = s_col[c], rt = s_row[r];
+    // One resized-crop pixel (3 channels) of tile position (r, c): 2x2 source taps, 11-bit fixed point exactly as
+    // cv::resize (HResize then VResizeLinear 8U), then the normalisation table.  Padding taps carry weight 0 and a
+    // safe offset, so the twelve byte loads are unconditional and can all be in flight.
+    auto gather_px = [&](int r, const int4 ct, int slot) {
+        const int4 rt = s_row[r];
         float v0 = 0.f, v1 = 0.f, v2 = 0.f;
         if (!((ct.w | rt.w) & 1)) {
-            const uint8_t* q00 = im + rt.x + ct.x;
-            const uint8_t* q01 = im + rt.x + ct.y;
-            const uint8_t* q10 = im + rt.y + ct.x;
-            const uint8_t* q11 = im + rt.y + ct.y;
+            const uint8_t* q00 = im + (rt.x + ct.x);
+            const uint8_t* q01 = im + (rt.x + ct.y);
+            const uint8_t* q10 = im + (rt.y + ct.x);
+            const uint8_t* q11 = im + (rt.y + ct.y);
             int p00[3], p01[3], p10[3], p11[3];
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) { p00[ch] = __ldg(q00 + ch); p01[ch] = __ldg(q01 + ch); p10[ch] = __ldg(q10 + ch); p11[ch] = __ldg(q11 + ch); }
-            const int a0 = ct.z & 0xffff, a1 = ct.z >> 16, b0 = rt.z & 0xffff, b1 = rt.z >> 16;
-            const bool vy0 = rt.w & 2, vy1 = rt.w & 4;
-            float vv[3];
+            const int a0 = ct.z & 0xffff, a1 = (unsigned)ct.z >> 16, b0 = rt.z & 0xffff, b1 = (unsigned)rt.z >> 16;
+            int v[3];
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-                const int h0 = vy0 ? p00[ch] * a0 + p01[ch] * a1 : 0;
-                const int h1 = vy1 ? p10[ch] * a0 + p11[ch] * a1 : 0;
-                int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-                v = min(max(v, 0), 255);
-                vv[ch] = s_lut[ch * 256 + v];
+                const int h0 = p00[ch] * a0 + p01[ch] * a1;
+                const int h1 = p10[ch] * a0 + p11[ch] * a1;
+                v[ch] = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;     // always in [0, 255]
             }
-            v0 = vv[0]; v1 = vv[1]; v2 = vv[2];
+            v0 = s_lut[v[0]]; v1 = s_lut[256 + v[1]]; v2 = s_lut[512 + v[2]];
         }
-        const int slot = (c & 1) ? (K::kOOff + (c >> 1)) : (K::kEOff + (c >> 1));
         float* dst = tile + r * K::kPitch + slot;
         dst[0] = v0;
         dst[K::kInRows * K::kPitch] = v1;
         dst[2 * K::kInRows * K::kPitch] = v2;
+    };
+    {
+        // threads own a fixed column (taps in registers) and walk down rows: columns 0..63 x 4 row phases, then column 64
+        const int c = tid & 63;
+        const int4 ct = s_col[c];
+        const int slot = (c & 1) ? (K::kOOff + (c >> 1)) : (K::kEOff + (c >> 1));
+#pragma unroll 2
+        for (int r = tid >> 6; r < kCc1TileSide; r += 4) gather_px(r, ct, slot);
+        if (tid < kCc1TileSide) gather_px(tid, s_col[64], K::kEOff + 32);
     }
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncthreads();
