@@ -217,7 +217,7 @@ conv3x3s2_kernel(const float* __restrict__ in, int Hin, int Win, const float* __
 using Conv1Cfg = ConvCfg<3, 6, 6, 4, 32, 32>;
 constexpr int kCc1Threads = Conv1Cfg::kThreads;                         // 256
 constexpr int kCc1TileSide = 2 * 32 + 1;                                // 65 resized-crop pixels per side
-constexpr size_t kCc1SmemBytes = Conv1Cfg::kSmemBytes + 64 + 2 * 80 * sizeof(int4) + 768 * sizeof(float);
+constexpr size_t kCc1SmemBytes = Conv1Cfg::kSmemBytes + 64 + 2 * 80 * sizeof(int4);     // 4 CTAs / SM
 
 template <int S>
 __global__ void __launch_bounds__(kCc1Threads)
@@ -232,7 +232,6 @@ crop_conv1_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict_
     float* bs = ws + K::kWFloats;
     int4* s_col = reinterpret_cast<int4*>(smem + ((K::kTileFloats + K::kWFloats + 6 + 3) / 4 * 4));
     int4* s_row = s_col + 80;
-    float* s_lut = reinterpret_cast<float*>(s_row + 80);
 
     constexpr int Hout = S / 2;
     constexpr int tiles_x = Hout / 32;
@@ -244,7 +243,6 @@ crop_conv1_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict_
     for (int i = tid * 4; i < K::kWFloats; i += kCc1Threads * 4) cp_async<16>(ws + i, wg + i, true);
     if (tid < 6) cp_async<4>(bs + tid, bg + tid, true);
     asm volatile("cp.async.commit_group;\n" ::: "memory");
-    for (int i = tid; i < 768; i += kCc1Threads) s_lut[i] = __ldg(lut + i);
 
     const int H = frame_hw[2 * item], W = frame_hw[2 * item + 1];
     const double* bx = boxes + 4 * item;
@@ -303,7 +301,7 @@ crop_conv1_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict_
                 const int h1 = p10[ch] * a0 + p11[ch] * a1;
                 v[ch] = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;     // always in [0, 255]
             }
-            v0 = s_lut[v[0]]; v1 = s_lut[256 + v[1]]; v2 = s_lut[512 + v[2]];
+            v0 = __ldg(lut + v[0]); v1 = __ldg(lut + 256 + v[1]); v2 = __ldg(lut + 512 + v[2]);     // 3 KB table, L1 resident
         }
         float* dst = tile + r * K::kPitch + slot;
         dst[0] = v0;
@@ -315,7 +313,7 @@ crop_conv1_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict_
         const int c = tid & 63;
         const int4 ct = s_col[c];
         const int slot = (c & 1) ? (K::kOOff + (c >> 1)) : (K::kEOff + (c >> 1));
-#pragma unroll 2
+#pragma unroll 4
         for (int r = tid >> 6; r < kCc1TileSide; r += 4) gather_px(r, ct, slot);
         if (tid < kCc1TileSide) gather_px(tid, s_col[64], K::kEOff + 32);
     }
