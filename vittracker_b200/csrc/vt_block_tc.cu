@@ -48,6 +48,11 @@ constexpr int kEpiThreads = 12 * 32;
 constexpr uint32_t kColBig = 0;        // [0,320): QKV out (2 buffers of 144 at 0 / 160), S -> P, fc1 out -> GELU operand
 constexpr uint32_t kColOut = 320;      // [320,368): O, proj out, fc2 out
 constexpr uint32_t kColOpa = 368;      // [368,512): three 48-column A-operand slots (hi 24 | lo 24), one per row tile
+// MLP phase (the attention regions are dead by then): two fc1-output / GELU-operand buffers and two fc2 outputs, so
+// that the GELU of one row tile overlaps the MMAs of the others.  H_B / Y_A / Y_B alias the A-operand slots; the
+// control program orders every aliasing write after the MMA that last read the slot.
+constexpr uint32_t kColHA = 0, kColHB = 192;       // 192 columns each
+constexpr uint32_t kColYA = 384, kColYB = 432;     // 48 columns each
 
 // ---- shared memory (bytes) -------------------------------------------------------------------------
 constexpr int kSmWa = 0;                                  // Wqkv hi|lo, Wproj hi|lo (bulk copied per block)
@@ -58,7 +63,7 @@ constexpr int kSmW1hi = kSmX, kSmW1lo = kSmX + 18432, kSmW2hi = kSmX + 36864, kS
 constexpr int kSmPar = kSmX + 4 * kKBytes;                // fp32 parameters of all blocks
 constexpr int kSmRed = kSmPar + kDepth * kTcParFloats * 4;   // 4 arrays x 3 thirds x 128 rows fp32
 constexpr int kSmBar = kSmRed + 4 * 3 * 128 * 4;          // mbarriers
-constexpr int kSmTmem = kSmBar + 4 * 8;
+constexpr int kSmTmem = kSmBar + 12 * 8;
 constexpr int kTcSmemBytes = kSmTmem + 16;
 static_assert(kTcWbBytes <= 4 * kKBytes, "MLP weights overlay the K/V region");
 static_assert(kSmBar % 8 == 0 && kSmX % 128 == 0, "alignment");
@@ -80,12 +85,20 @@ struct Epi {
     __device__ __forceinline__ uint32_t taddr(uint32_t col) const { return tbase + lane_addr + col; }
 
     // operands written (TMEM and/or smem): publish to the control thread
-    __device__ __forceinline__ void signal_go(bool wrote_smem) {
+    __device__ __forceinline__ void signal(uint64_t* bar, bool wrote_smem) {
         tc_wait_st();
         if (wrote_smem) fence_async_smem();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(mb_go);
+        if (lane == 0) mbar_arrive(bar);
+    }
+    __device__ __forceinline__ void signal_go(bool wrote_smem) { signal(mb_go, wrote_smem); }
+    __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t& ph) {
+        if (threadIdx.x == 0) TC_TRACE(1);
+        mbar_wait(bar, ph);
+        ph ^= 1;
+        tc_fence_after();
+        if (threadIdx.x == 0) TC_TRACE(1);
     }
     __device__ __forceinline__ void wait_done() {
         if (threadIdx.x == 0) TC_TRACE(1);
@@ -165,6 +178,10 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
     uint64_t* mb_done = mb_go + 1;
     uint64_t* mb_wa = mb_go + 2;
     uint64_t* mb_wb = mb_go + 3;
+    uint64_t* mb_h = mb_go + 4;        // [2] fc1 output ready in H_A / H_B          (tcgen05.commit)
+    uint64_t* mb_y = mb_go + 6;        // [2] fc2 output ready in Y_A / Y_B          (tcgen05.commit)
+    uint64_t* mb_g = mb_go + 8;        // [2] GELU operand written in H_A / H_B      (12 warp arrivals)
+    uint64_t* mb_yfree = mb_go + 10;   // Y_A has been read, may be overwritten      (12 warp arrivals)
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kSmTmem);
 
     if (warp == 12) tmem_alloc(s_tmem, 512);
@@ -173,6 +190,10 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
         mbar_init(mb_done, 1);
         mbar_init(mb_wa, 1);
         mbar_init(mb_wb, 1);
+        mbar_init(mb_h, 1); mbar_init(mb_h + 1, 1);
+        mbar_init(mb_y, 1); mbar_init(mb_y + 1, 1);
+        mbar_init(mb_g, 12); mbar_init(mb_g + 1, 12);
+        mbar_init(mb_yfree, 12);
         mbar_fence_init();
     }
     for (int i = tid; i < kDepth * kTcParFloats; i += kTcThreads) s_par[i] = __ldg(w.tc[i / kTcParFloats].par + i % kTcParFloats);
@@ -206,7 +227,7 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
             };
             auto qkv = [&](int t, uint32_t d_col) { gemm_k48(t, d_col, kSmWa, kSmWa + 13824, 144, id144); };
             auto proj = [&](int t) { gemm_k48(t, kColOut, kSmWa + 27648, kSmWa + 27648 + 4608, 48, id48); };
-            auto fc1 = [&](int t) { gemm_k48(t, kColBig, kSmW1hi, kSmW1lo, 192, id192); };
+            auto fc1 = [&](int t, uint32_t h_col) { gemm_k48(t, h_col, kSmW1hi, kSmW1lo, 192, id192); };
             // S = q k^T over 320 keys as two N = 160 halves; K operand K-major [k/8][320][8]
             auto scores = [&](int t) {
                 const uint32_t a = tbase + kColOpa + 48 * t;
@@ -237,17 +258,19 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                 }
             };
             // y = gelu(h) W2^T: operand in TMEM (16-wide group g: hi 16g.., lo 16g+8..), W2 K-major [k/8][48][8], K = 192
-            auto fc2 = [&]() {
+            auto fc2 = [&](uint32_t h_col, uint32_t y_col) {
 #pragma unroll 4
                 for (int g = 0; g < kHid / 16; ++g) {
-                    const uint32_t a = tbase + kColBig + 16 * g;
+                    const uint32_t a = tbase + h_col + 16 * g;
                     const uint64_t bh = smem_desc(sbase + kSmW2hi + g * 2 * 48 * 16, 48 * 16, 128);
                     const uint64_t bl = smem_desc(sbase + kSmW2lo + g * 2 * 48 * 16, 48 * 16, 128);
-                    mma_ts_elect(tbase + kColOut, a, bh, id48, g > 0);
-                    mma_ts_elect(tbase + kColOut, a + 8, bh, id48, true);
-                    mma_ts_elect(tbase + kColOut, a, bl, id48, true);
+                    mma_ts_elect(tbase + y_col, a, bh, id48, g > 0);
+                    mma_ts_elect(tbase + y_col, a + 8, bh, id48, true);
+                    mma_ts_elect(tbase + y_col, a, bl, id48, true);
                 }
             };
+            uint32_t h_ph[2] = {0, 0}, y_ph[2] = {0, 0}, g_ph[2] = {0, 0}, yfree_ph = 0;
+            auto wait_on = [&](uint64_t* bar, uint32_t& ph) { TC_TRACE(0); mbar_wait(bar, ph); ph ^= 1; tc_fence_after(); TC_TRACE(0); };
             bool first = true;
             for (int trk = blockIdx.x; trk < n; trk += gridDim.x) {
                 const bool last_track = trk + (int)gridDim.x >= n;
@@ -267,12 +290,23 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                     wait_go();                                                   // 10: Wqkv/Wproj dead -> prefetch the next block's
                     if (!(last_track && blk == kDepth - 1)) load_wa((blk + 1) % kDepth);
                     mbar_wait(mb_wb, wb_ph); wb_ph ^= 1;
-                    fc1(0); mma_commit_elect(mb_done);
-                    wait_go(); fc2(); mma_commit_elect(mb_done);                       // 11
-                    wait_go(); fc1(1); mma_commit_elect(mb_done);                      // 12
-                    wait_go(); fc2(); mma_commit_elect(mb_done);                       // 13
-                    wait_go(); fc1(2); mma_commit_elect(mb_done);                      // 14
-                    wait_go(); fc2(); mma_commit_elect(mb_done);                       // 15
+                    // ---- MLP, pipelined over row tiles (tile 0 -> H_A/Y_A, tile 1 -> H_B/Y_B, tile 2 -> H_A/Y_A) ----
+                    fc1(0, kColHA); mma_commit_elect(mb_h);
+                    wait_on(mb_h, h_ph[0]);                                      // H_B aliases operand slot 0: fc1(0) must be done
+                    fc1(1, kColHB); mma_commit_elect(mb_h + 1);
+                    wait_on(mb_g, g_ph[0]);                                      // GELU(0) operand in H_A
+                    wait_on(mb_h + 1, h_ph[1]);                                  // Y_A aliases operand slots 0/1: fc1(1) must be done
+                    fc2(kColHA, kColYA); mma_commit_elect(mb_y);
+                    wait_on(mb_y, y_ph[0]);                                      // fc2(0) has read H_A
+                    fc1(2, kColHA); mma_commit_elect(mb_h);
+                    wait_on(mb_g + 1, g_ph[1]);                                  // GELU(1) operand in H_B
+                    wait_on(mb_h, h_ph[0]);                                      // Y_B aliases operand slot 2: fc1(2) must be done
+                    fc2(kColHB, kColYB); mma_commit_elect(mb_y + 1);
+                    wait_on(mb_g, g_ph[0]);                                      // GELU(2) operand in H_A
+                    wait_on(mb_yfree, yfree_ph);                                 // Y_A (tile 0) has been consumed
+                    fc2(kColHA, kColYA); mma_commit_elect(mb_y);
+                    wait_on(mb_y + 1, y_ph[1]);                                  // keep this side's phase bits in step
+                    wait_on(mb_y, y_ph[0]);
                 }
             }
         }
@@ -286,6 +320,7 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
         const int s = e.s, row = e.row;
         const float scale = 0.14433756729740643f;                 // 48 ** -0.5
         const float kLog2e = 1.4426950408889634f;
+        uint32_t h_ph[2] = {0, 0}, y_ph[2] = {0, 0};
 
         for (int trk = blockIdx.x; trk < n; trk += gridDim.x) {
             // residual slice x[t][16]: tile t, row 128 t + row, columns [16 s, 16 s + 16)
@@ -313,13 +348,11 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
             for (int blk = 0; blk < kDepth; ++blk) {
                 const float* par = s_par + blk * kTcParFloats;
 
-                if (blk == 0) {                 // later blocks: LN1 was fused into the previous block's last epilogue
 #pragma unroll
-                    for (int t = 0; t < 3; ++t) {
-                        float y[16];
-                        e.ln16(x[t], par + kPLn1g, par + kPLn1b, y);
-                        if (e.active(t)) e.store_opa16(t, y);
-                    }
+                for (int t = 0; t < 3; ++t) {      // LayerNorm 1 -> the tiles' A-operand slots
+                    float y[16];
+                    e.ln16(x[t], par + kPLn1g, par + kPLn1b, y);
+                    if (e.active(t)) e.store_opa16(t, y);
                 }
                 e.signal_go(false);             // -> 1
 
@@ -452,9 +485,9 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                 e.wait_done(); epi_proj(2); e.signal_go(false);                   // -> 10
 
                 // ---- MLP per tile -------------------------------------------------------------------------
-                auto gelu = [&](int t) {
+                auto gelu = [&](int t, uint32_t h_col) {
                     if (!e.active(t)) return;
-                    const uint32_t a0 = e.taddr(kColBig + 64 * s);                // third s owns hidden columns [64 s, 64 s + 64)
+                    const uint32_t a0 = e.taddr(h_col + 64 * s);                  // third s owns hidden columns [64 s, 64 s + 64)
                     uint32_t r[2][16];
                     tmem_ld16(a0, r[0]);
 #pragma unroll
@@ -472,38 +505,32 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                         tmem_st8(a0 + 16 * g + 8, lo);
                     }
                 };
-                auto epi_fc2 = [&](int t) {
-                    if (e.active(t)) {
-                        uint32_t r[16];
-                        tmem_ld16(e.taddr(kColOut + 16 * s), r);
-                        tc_wait_ld();
+                auto epi_fc2 = [&](int t, uint32_t y_col) {
+                    if (!e.active(t)) return;
+                    uint32_t r[16];
+                    tmem_ld16(e.taddr(y_col + 16 * s), r);
+                    tc_wait_ld();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) x[t][j] += __uint_as_float(r[j]) + par[kPBfc2 + 16 * s + j];
-                        const int rr = 128 * t + row;
-                        if (taps && rr < kN) {
-                            float* tp = taps + (size_t)(blk + 1) * tap_stride + ((size_t)trk * kN + rr) * kC + 16 * s;
+                    for (int j = 0; j < 16; ++j) x[t][j] += __uint_as_float(r[j]) + par[kPBfc2 + 16 * s + j];
+                    const int rr = 128 * t + row;
+                    if (taps && rr < kN) {
+                        float* tp = taps + (size_t)(blk + 1) * tap_stride + ((size_t)trk * kN + rr) * kC + 16 * s;
 #pragma unroll
-                            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(tp + i) = make_float4(x[t][i], x[t][i + 1], x[t][i + 2], x[t][i + 3]);
-                        }
-                        if (blk == kDepth - 1 && rr < kN) {
-                            float* dst = out + ((size_t)trk * kN + rr) * kC + 16 * s;
-#pragma unroll
-                            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(x[t][i], x[t][i + 1], x[t][i + 2], x[t][i + 3]);
-                        }
+                        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(tp + i) = make_float4(x[t][i], x[t][i + 1], x[t][i + 2], x[t][i + 3]);
                     }
-                    if (blk < kDepth - 1) {      // LayerNorm 1 of the next block -> the tile's A slot
-                        const float* np = par + kTcParFloats;
-                        float y[16];
-                        e.ln16(x[t], np + kPLn1g, np + kPLn1b, y);
-                        if (e.active(t)) e.store_opa16(t, y);
+                    if (blk == kDepth - 1 && rr < kN) {
+                        float* dst = out + ((size_t)trk * kN + rr) * kC + 16 * s;
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(x[t][i], x[t][i + 1], x[t][i + 2], x[t][i + 3]);
                     }
                 };
-                e.wait_done(); gelu(0); e.signal_go(false);                       // -> 11
-                e.wait_done(); epi_fc2(0); e.signal_go(false);                    // -> 12
-                e.wait_done(); gelu(1); e.signal_go(false);                       // -> 13
-                e.wait_done(); epi_fc2(1); e.signal_go(false);                    // -> 14
-                e.wait_done(); gelu(2); e.signal_go(false);                       // -> 15
-                e.wait_done(); epi_fc2(2);
+                // MLP, pipelined over row tiles: the tensor pipe runs fc1 / fc2 of the other tiles during each GELU
+                e.wait_bar(mb_h, h_ph[0]);      gelu(0, kColHA);     e.signal(mb_g, false);
+                e.wait_bar(mb_h + 1, h_ph[1]);  gelu(1, kColHB);     e.signal(mb_g + 1, false);
+                e.wait_bar(mb_y, y_ph[0]);      epi_fc2(0, kColYA);  e.signal(mb_yfree, false);
+                e.wait_bar(mb_h, h_ph[0]);      gelu(2, kColHA);     e.signal(mb_g, false);
+                e.wait_bar(mb_y + 1, y_ph[1]);  epi_fc2(1, kColYB);
+                e.wait_bar(mb_y, y_ph[0]);      epi_fc2(2, kColYA);
                 (void)inv_l;
             }
         }
