@@ -390,6 +390,28 @@ int vt_finalize_weights(VtHandle h, void* stream) {
             }
         }
     }
+    // head conv1 for the tensor cores: piece (h, kx) holds B[n = co - 48 h][k = ky * 48 + ci] as fp16 hi | lo
+    const size_t o_htc = slot(6 * kHeadTcPieceBytes / 4);
+    {
+        uint8_t* base8 = reinterpret_cast<uint8_t*>(&pk.buf[o_htc]);
+        const float* w1 = &pk.buf[hw[0]];                       // folded, [ci][ky*3+kx][96]
+        for (int h2 = 0; h2 < 2; ++h2)
+            for (int kx = 0; kx < 3; ++kx) {
+                uint8_t* hi8 = base8 + (size_t)(h2 * 3 + kx) * kHeadTcPieceBytes;
+                uint8_t* lo8 = hi8 + kHeadTcPieceBytes / 2;
+                for (int n = 0; n < 48; ++n)
+                    for (int ky = 0; ky < 3; ++ky)
+                        for (int ci = 0; ci < 48; ++ci) {
+                            const int k = ky * 48 + ci;
+                            const float v = w1[((size_t)ci * 9 + ky * 3 + kx) * 96 + h2 * 48 + n];
+                            const __half hi = __float2half_rn(v);
+                            const __half lo = __float2half_rn(v - __half2float(hi));
+                            const size_t off = ((size_t)(k / 8) * 48 + n) * 16 + (k % 8) * 2;
+                            memcpy(hi8 + off, &hi, 2);
+                            memcpy(lo8 + off, &lo, 2);
+                        }
+            }
+    }
     hw[4] = slot(3 * 4 * 2); hb[4] = slot(3 * 2);
     for (int t = 0; t < 3; ++t) {
         const std::string p = std::string("box_head.conv5_") + kTowers[t] + ".";
@@ -451,6 +473,7 @@ int vt_finalize_weights(VtHandle h, void* stream) {
     m.head.w1 = base + hw[0]; m.head.b1 = base + hb[0]; m.head.w2 = base + hw[1]; m.head.b2 = base + hb[1];
     m.head.w3 = base + hw[2]; m.head.b3 = base + hb[2]; m.head.w4 = base + hw[3]; m.head.b4 = base + hb[3];
     m.head.w5 = base + hw[4]; m.head.b5 = base + hb[4];
+    m.head_tc_w1 = reinterpret_cast<const uint8_t*>(base + o_htc);
     m.hann = base + o_hann; m.lut = base + o_lut;
     h->finalized = true;
     return VT_OK;
@@ -494,6 +517,7 @@ int vt_forward(VtHandle h, const float* z, const float* x, int32_t n, float* pre
         a.size_map = size_map ? size_map + (size_t)first * 512 : nullptr;
         a.offset_map = offset_map ? offset_map + (size_t)first * 512 : nullptr;
         a.tokens_norm = taps ? taps + (size_t)(kDepth + 1) * tap_stride + (size_t)first * kN * kC : nullptr;
+        a.use_tc = h->cfg.blocks_impl == VT_BLOCKS_TCGEN05;
         VT_LAUNCH(h, VT_STAGE_HEAD, m, st, "vt_forward/head", launch_head(a, h->mw, st));
     }
     return VT_OK;
@@ -563,6 +587,7 @@ int vt_tracks_step(VtHandle h, const uint8_t* frames, const int64_t* frame_offse
         a.out_detail = out_detail;
         a.update_state = update_state;
         a.search_factor = h->cfg.search_factor;
+        a.use_tc = h->cfg.blocks_impl == VT_BLOCKS_TCGEN05;
         VT_LAUNCH(h, VT_STAGE_HEAD, m, st, "vt_tracks_step/head", launch_head(a, h->mw, st));
     }
     h->last_first = first; h->last_n = n;

@@ -7,8 +7,17 @@
 //   track() epilogue    lib/test/tracker/vit_dist.py:103-111,147-156 + lib/utils/box_ops.py:97-106
 // The three towers' first convolutions share their input and are merged into one 48->96 layer whose
 // 166 KB of weights are streamed through a double-buffered cp.async ring; later layers reuse the ring.
+//
+// head_kernel<true> runs that first 48 -> 96 convolution (69 % of the head's FLOPs) on the tcgen05 tensor
+// cores instead: the LayerNorm output is written to shared memory as fp16 hi/lo in 8-channel chunks
+// [chunk][row 0..17][x 0..15][8] (a zero row above and below), which a no-swizzle K-major UMMA descriptor can
+// address for any vertical tap by moving its start row.  Horizontal taps are not gathered at all: for each kx
+// one accumulator T_kx[y][x'] = sum_{ky,ci} in[y+ky-1][x'][ci] W[ci][ky][kx][co] is built in TMEM over the
+// UNSHIFTED columns, and the epilogue adds T_0[y][x-1] + T_1[y][x] + T_2[y][x+1] with warp shuffles (a
+// warp's 32 TMEM lanes are two complete image rows).  Products are hi*hi + lo*hi + hi*lo as in the blocks.
 #include "vt_geom.cuh"
 #include "vt_internal.h"
+#include "vt_tc.cuh"
 
 namespace vt {
 
@@ -24,6 +33,18 @@ constexpr int kOffRed = kOffMaps + 6 * 256;          // reduction scratch (32 fl
 constexpr int kHeadFloats = kOffRed + 32;
 constexpr size_t kHeadSmemBytes = (size_t)kHeadFloats * sizeof(float);
 static_assert(kHeadSmemBytes <= 227 * 1024, "head smem");
+
+// ---- tensor-core conv1 (head_kernel<true>) -------------------------------------------------------------
+constexpr int kTcAChunk = 18 * 16 * 16;                 // bytes per 8-channel chunk: 18 rows x 16 px x 16 B
+constexpr int kTcAHi = 0, kTcALo = 6 * kTcAChunk;       // inside the (otherwise unused) feat region
+static_assert(2 * 6 * kTcAChunk <= 48 * kPlane * 4, "A operand fits the feat region");
+constexpr int kTcWBuf0 = kOffW * 4;                     // weight piece ring: buffer 0 = the cp.async ring area,
+constexpr int kTcWBuf1 = (kOffOut1 + 48 * kPlane) * 4;  // buffer 1 = conv1-output planes 48..95 (written only at the very end)
+static_assert(2 * kWChunk * 4 >= kHeadTcPieceBytes, "weight piece fits ring buffer 0");
+constexpr int kOffTcBar = kOffRed + 32;                 // 5 mbarriers + TMEM base (floats)
+constexpr int kHeadTcFloats = kOffTcBar + 16;
+constexpr size_t kHeadTcSmemBytes = (size_t)kHeadTcFloats * sizeof(float);
+static_assert(kHeadTcSmemBytes <= 227 * 1024 && (kOffTcBar * 4) % 8 == 0, "head smem (tc)");
 
 __device__ __forceinline__ void cp_async16(float* dst_smem, const float* src_gmem) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
@@ -131,8 +152,9 @@ __device__ __forceinline__ float sigmoid_clamp(float v) {
     return fminf(fmaxf(s, 1e-4f), 0.9999f);               // torch.clamp(x.sigmoid_(), 1e-4, 1 - 1e-4)
 }
 
+template <bool TC>
 __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(HeadArgs a, ModelW w) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     float* feat = smem + kOffFeat;
     float* out1 = smem + kOffOut1;
     float* wbuf = smem + kOffW;
@@ -150,7 +172,20 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(HeadArgs a, Model
     if (tid < 12) sb[168 + tid] = w.head.b4[tid];
     if (tid < 24) sb[180 + tid] = w.head.w5[tid];
     if (tid < 6) sb[204 + tid] = w.head.b5[tid];
+    uint64_t* tc_bar = reinterpret_cast<uint64_t*>(smem + kOffTcBar);      // [0,1] piece loaded, [2,3] piece consumed, [4] accumulators ready
+    uint32_t* tc_tmem = reinterpret_cast<uint32_t*>(tc_bar + 5);
+    if (TC) {
+        if (tid < 32) tc::tmem_alloc(tc_tmem, 512);
+        if (tid == 32) {
+            tc::mbar_init(tc_bar + 0, 1); tc::mbar_init(tc_bar + 1, 1);
+            tc::mbar_init(tc_bar + 2, 1); tc::mbar_init(tc_bar + 3, 1);
+            tc::mbar_init(tc_bar + 4, 1);
+            tc::mbar_fence_init();
+        }
+        tc::tc_fence_before();
+    }
     __syncthreads();
+    if (TC) tc::tc_fence_after();
 
     // ---- final LayerNorm (vit_dist.py:94) on search token `tid`; tokens -> (C,16,16) (vit_dist.py:126-129)
     {
@@ -181,14 +216,114 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(HeadArgs a, Model
         float y[kC];
         norm_row(kNz + tid, y);
         const int py = tid >> 4, px = tid & 15;
+        if (!TC) {
 #pragma unroll
-        for (int k = 0; k < kC; ++k) feat[k * kPlane + (py + 1) * 18 + px + 1] = y[k];
+            for (int k = 0; k < kC; ++k) feat[k * kPlane + (py + 1) * 18 + px + 1] = y[k];
+        } else {
+            uint8_t* ab = reinterpret_cast<uint8_t*>(smem) + ((py + 1) * 16 + px) * 16;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) tc::split_pack2(y[8 * c + 2 * j], y[8 * c + 2 * j + 1], hi[j], lo[j]);
+                *reinterpret_cast<uint4*>(ab + kTcAHi + c * kTcAChunk) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(ab + kTcALo + c * kTcAChunk) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            tc::fence_async_smem();
+        }
         if (a.tokens_norm && tid < kNz) { float yz[kC]; norm_row(tid, yz); }
     }
     __syncthreads();
 
     // ---- conv towers ---------------------------------------------------------------------------
-    head_conv<48, 24, 4, false, 4>(feat, out1, w.head.w1, sb, wbuf);               // 48 -> 3x32 (merged)
+    if (!TC) {
+        head_conv<48, 24, 4, false, 4>(feat, out1, w.head.w1, sb, wbuf);           // 48 -> 3x32 (merged)
+    } else {
+        const uint32_t tbase = __shfl_sync(0xffffffffu, *tc_tmem, 0);
+        const uint32_t sbase = tc::smem_u32(smem);
+        const int warp = tid >> 5, lane = tid & 31;
+        const uint32_t id48 = tc::instr_desc_f16(128, 48, false);
+        // piece p = 3 h + kx lives in ring buffer p & 1; D region of (tile, kx) = columns (tile * 3 + kx) * 48
+        auto load_piece = [&](int p) {
+            tc::bulk_g2s_elect(reinterpret_cast<uint8_t*>(smem) + ((p & 1) ? kTcWBuf1 : kTcWBuf0),
+                               w.head_tc_w1 + (size_t)p * kHeadTcPieceBytes, kHeadTcPieceBytes, tc_bar + (p & 1));
+        };
+        if (warp == 0) load_piece(0);
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            if (warp == 0) {                     // convergent: every lane runs the program, one elected lane issues
+#pragma unroll 1
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int p = 3 * h + kx;
+                    if (p + 1 < 6) {
+                        if (p >= 1) tc::mbar_wait(tc_bar + 2 + ((p + 1) & 1), ((p - 1) >> 1) & 1);   // piece p-1 consumed
+                        load_piece(p + 1);
+                    }
+                    tc::mbar_wait(tc_bar + (p & 1), (p >> 1) & 1);                                   // piece p landed
+                    tc::tc_fence_after();
+                    const uint32_t wb = sbase + ((p & 1) ? kTcWBuf1 : kTcWBuf0);
+#pragma unroll
+                    for (int tile = 0; tile < 2; ++tile) {
+                        const uint32_t d = tbase + (tile * 3 + kx) * 48;
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                            for (int ks = 0; ks < 3; ++ks) {
+                                const uint32_t aoff = (2 * ks) * kTcAChunk + (8 * tile + ky) * 256;
+                                const uint64_t ah = tc::smem_desc(sbase + kTcAHi + aoff, kTcAChunk, 128);
+                                const uint64_t al = tc::smem_desc(sbase + kTcALo + aoff, kTcAChunk, 128);
+                                const uint32_t boff = (ky * 6 + 2 * ks) * 768;
+                                const uint64_t bh = tc::smem_desc(wb + boff, 768, 128);
+                                const uint64_t bl = tc::smem_desc(wb + kHeadTcPieceBytes / 2 + boff, 768, 128);
+                                tc::mma_ss_elect(d, ah, bh, id48, (ky | ks) != 0);
+                                tc::mma_ss_elect(d, al, bh, id48, 1);
+                                tc::mma_ss_elect(d, ah, bl, id48, 1);
+                            }
+                    }
+                    tc::mma_commit_elect(tc_bar + 2 + (p & 1));
+                }
+                tc::mma_commit_elect(tc_bar + 4);
+            }
+            tc::mbar_wait(tc_bar + 4, h);
+            tc::tc_fence_after();
+            if (h == 1) {
+                // every MMA has completed: the fp16 operand (feat region, soon the conv2 output planes) and ring buffer 1
+                // (output planes 48..) are dead - restore the all-zero planes whose borders the CUDA-core layers rely on
+                for (int i = tid * 4; i < 48 * kPlane; i += kHeadThreads * 4)
+                    *reinterpret_cast<float4*>(feat + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = tid * 4; i < kHeadTcPieceBytes / 4; i += kHeadThreads * 4)
+                    *reinterpret_cast<float4*>(out1 + 48 * kPlane + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+                __syncthreads();
+            }
+            // epilogue: pixel = tid (tile = warp / 4, TMEM lane quarter = warp % 4); combine the three horizontal taps
+            {
+                const int tile = warp >> 2;
+                const uint32_t ta = tbase + ((uint32_t)(32 * (warp & 3)) << 16) + tile * 144;
+                const int py = tid >> 4, px = tid & 15;
+                float* op = out1 + (h * 48) * kPlane + (py + 1) * 18 + px + 1;
+#pragma unroll 1
+                for (int c0 = 0; c0 < 48; c0 += 16) {
+                    uint32_t r0[16], r1[16], r2[16];
+                    tc::tmem_ld16(ta + c0, r0);
+                    tc::tmem_ld16(ta + 48 + c0, r1);
+                    tc::tmem_ld16(ta + 96 + c0, r2);
+                    tc::tc_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float t0 = __shfl_up_sync(0xffffffffu, __uint_as_float(r0[j]), 1);     // T_0[y][x-1]
+                        float t2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[j]), 1);   // T_2[y][x+1]
+                        if (px == 0) t0 = 0.f;
+                        if (px == 15) t2 = 0.f;
+                        const float v = (t0 + __uint_as_float(r1[j])) + t2 + sb[h * 48 + c0 + j];
+                        op[(c0 + j) * kPlane] = fmaxf(v, 0.f);                                   // ReLU
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            __syncthreads();
+            tc::tc_fence_after();
+        }
+    }
     float* out2 = feat;                                                            // [3][16] planes
     head_conv<32, 16, 3, true, 8>(out1, out2, w.head.w2, sb + 96, wbuf);           // 32 -> 16 per tower
     float* out3 = out1;                                                            // [3][8] planes
@@ -229,6 +364,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(HeadArgs a, Model
     block_argmax256(m_score[tid], tid, red, raw_max, raw_idx);
     float win_max; int win_idx;
     block_argmax256(m_resp[tid], tid, red, win_max, win_idx);
+    if (TC && tid < 32) tc::tmem_dealloc(__shfl_sync(0xffffffffu, *tc_tmem, 0), 512);     // all TMEM reads ended before the barriers above
     if (tid != 0) return;
 
     if (a.pred_boxes) {
@@ -288,10 +424,12 @@ int launch_head(const HeadArgs& a, const ModelW& w, cudaStream_t st) {
     if (a.n <= 0) return 0;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmemBytes) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(head_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmemBytes) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(head_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadTcSmemBytes) != cudaSuccess) return -1;
         configured = true;
     }
-    head_kernel<<<a.n, kHeadThreads, kHeadSmemBytes, st>>>(a, w);
+    if (a.use_tc) head_kernel<true><<<a.n, kHeadThreads, kHeadTcSmemBytes, st>>>(a, w);
+    else head_kernel<false><<<a.n, kHeadThreads, kHeadSmemBytes, st>>>(a, w);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -45,6 +45,7 @@ struct HeadW {               // CENTER head, BN folded, towers ordered ctr, offs
 // no-swizzle K-major layout [k/8][n][8], one bulk-copyable blob per phase, plus fp32 parameters.
 constexpr int kTcWaBytes = 2 * (144 * 48 * 2) + 2 * (48 * 48 * 2);      // Wqkv hi|lo, Wproj hi|lo = 36864
 constexpr int kTcWbBytes = 2 * (192 * 48 * 2) + 2 * (48 * 192 * 2);     // W1 hi|lo, W2 hi|lo     = 73728
+constexpr int kHeadTcPieceBytes = 2 * (144 * 48 * 2);      // one (half, kx) piece of head conv1: hi | lo, N = 48, K = 144 -> 27648
 constexpr int kTcParFloats = 624;   // ln1_g 48 | ln1_b 48 | bqkv 144 | bproj 48 | ln2_g 48 | ln2_b 48 | bfc1 192 | bfc2 48
 struct BlockTcW {
     const uint8_t* wa;     // kTcWaBytes
@@ -59,6 +60,7 @@ struct ModelW {
     const float *norm_g, *norm_b;
     const float *pos_z, *pos_x;    // [64][48], [256][48]
     HeadW head;
+    const uint8_t* head_tc_w1;     // head conv1 for tcgen05: 6 pieces (half h, kx) x [hi | lo] x K-major [k/8][48][8], k = ky*48 + ci
     const float* hann;             // [256] fp32 window (lib/test/utils/hann.py)
     const float* lut;              // [3][256] normalisation table ((v/255 - mean)/std)
 };
@@ -103,6 +105,7 @@ struct HeadArgs {
     double* out_detail;       // [n][8] (nullable)
     int update_state;
     double search_factor;
+    int use_tc;               // first (48 -> 96) convolution on the tcgen05 tensor cores
 };
 int launch_head(const HeadArgs& a, const ModelW& w, cudaStream_t st);
 
