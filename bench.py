@@ -256,7 +256,8 @@ def main():
     step_boxes = torch.stack([torch.tensor(O.synth_boxes(n, FRAME_H, FRAME_W, seed=3000 + 97 * rank + s)) for s in range(nsets)]).to(dev)
 
     # per-step frame offsets prepared up front: the timed loop launches only this library's kernels
-    step_offsets = [pool.offsets((fidx0 + t) % F) for t in range(F)]
+    fidx_host = np.arange(n, dtype=np.int64) % F
+    step_offsets = [torch.from_numpy(((fidx_host + t) % F) * pool.frame_bytes).to(dev) for t in range(F)]
 
     def step(t):
         bt.engine.tracks_set_state(step_boxes[t % nsets], first=0)
