@@ -312,6 +312,38 @@ int vt_finalize_weights(VtHandle h, void* stream) {
                     pk.buf[stem_w[l] + ((size_t)ci * 9 + k) * co_n + co] = (float)((double)w[((size_t)co * ci_n + ci) * 9 + k] * s);
         }
     }
+    // ---- stem conv3 / conv4 for the tensor cores: fp16 hi | lo, K-major chunks [k/8][NPAD][8];
+    //      accumulator A holds taps (ky, kx in {1, 2}), accumulator B taps (ky, kx = 0); channels / outputs zero padded
+    size_t stc_w[2], stc_b[2];
+    {
+        const int lcin[2] = {12, 24}, lcch[2] = {2, 4}, lcout[2] = {24, 48}, lnpad[2] = {32, 48};
+        for (int i = 0; i < 2; ++i) {
+            const int l = 2 + i, CIN = lcin[i], CCH = lcch[i], COUT = lcout[i], NPAD = lnpad[i];
+            const size_t prec = (size_t)9 * CCH * 8 * NPAD * 2;
+            stc_w[i] = slot(2 * prec / 4);
+            stc_b[i] = slot(NPAD);
+            if (prec * 2 != stem_tc_weight_bytes(i)) return fail(h, VT_ERR_WEIGHTS, "internal: stem tc weight size mismatch");
+            uint8_t* hi8 = reinterpret_cast<uint8_t*>(&pk.buf[stc_w[i]]);
+            uint8_t* lo8 = hi8 + prec;
+            const float* wf = &pk.buf[stem_w[l]];             // folded [ci][ky][kx][co]
+            for (int co = 0; co < COUT; ++co) pk.buf[stc_b[i] + co] = pk.buf[stem_b[l] + co];
+            for (int q = 0; q < 9 * CCH; ++q) {
+                const bool accB = q >= 6 * CCH;
+                const int tap = (accB ? q - 6 * CCH : q) / CCH, cc = q % CCH;
+                const int ky = accB ? tap : tap / 2, kx = accB ? 0 : 1 + (tap & 1);
+                for (int n = 0; n < NPAD; ++n)
+                    for (int e = 0; e < 8; ++e) {
+                        const int ci = cc * 8 + e;
+                        const float v = (ci < CIN && n < COUT) ? wf[(((size_t)ci * 3 + ky) * 3 + kx) * COUT + n] : 0.f;
+                        const __half hi = __float2half_rn(v);
+                        const __half lo = __float2half_rn(v - __half2float(hi));
+                        const size_t off = ((size_t)q * NPAD + n) * 16 + e * 2;
+                        memcpy(hi8 + off, &hi, 2);
+                        memcpy(lo8 + off, &lo, 2);
+                    }
+            }
+        }
+    }
     // ---- blocks: Linear weights [out][in] -> K-major [in][out]
     struct BOff { size_t ln1g, ln1b, wqkv, bqkv, wproj, bproj, ln2g, ln2b, wfc1, bfc1, wfc2, bfc2; } bo[kDepth];
     auto copyv = [&](size_t o, const float* src, size_t n) { if (src) memcpy(&pk.buf[o], src, n * sizeof(float)); };
@@ -474,6 +506,7 @@ int vt_finalize_weights(VtHandle h, void* stream) {
     m.head.w3 = base + hw[2]; m.head.b3 = base + hb[2]; m.head.w4 = base + hw[3]; m.head.b4 = base + hb[3];
     m.head.w5 = base + hw[4]; m.head.b5 = base + hb[4];
     m.head_tc_w1 = reinterpret_cast<const uint8_t*>(base + o_htc);
+    for (int i = 0; i < 2; ++i) { m.stem_tc_w[i] = reinterpret_cast<const uint8_t*>(base + stc_w[i]); m.stem_tc_b[i] = base + stc_b[i]; }
     m.hann = base + o_hann; m.lut = base + o_lut;
     h->finalized = true;
     return VT_OK;
@@ -506,8 +539,8 @@ int vt_forward(VtHandle h, const float* z, const float* x, int32_t n, float* pre
     const size_t tap_stride = (size_t)n * kN * kC;
     for (int first = 0; first < n; first += h->chunk) {
         const int m = (n - first < h->chunk) ? n - first : h->chunk;
-        VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_forward/stem(z)", launch_stem(z + (size_t)first * 3 * kTz * kTz, kTz, m, h->mw, h->d_scratch, h->d_tokz, kNz, 0, st));
-        VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_forward/stem(x)", launch_stem(x + (size_t)first * 3 * kSx * kSx, kSx, m, h->mw, h->d_scratch, h->d_tokx, kNx, 0, st));
+        VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_forward/stem(z)", launch_stem(z + (size_t)first * 3 * kTz * kTz, kTz, m, h->mw, h->d_scratch, h->d_tokz, kNz, 0, h->cfg.blocks_impl == VT_BLOCKS_TCGEN05, st));
+        VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_forward/stem(x)", launch_stem(x + (size_t)first * 3 * kSx * kSx, kSx, m, h->mw, h->d_scratch, h->d_tokx, kNx, 0, h->cfg.blocks_impl == VT_BLOCKS_TCGEN05, st));
         VT_LAUNCH(h, VT_STAGE_BLOCKS, m, st, "vt_forward/blocks", run_blocks(h, h->d_tokz, kNz, h->d_tokx, kNx, h->d_tok, m,
                                                       taps ? taps + (size_t)first * kN * kC : nullptr, tap_stride, st));
         HeadArgs a{};
@@ -546,7 +579,8 @@ int vt_tracks_init(VtHandle h, const uint8_t* frames, const int64_t* frame_offse
         const int m = (n - c0 < h->chunk) ? n - c0 : h->chunk;
         VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_tracks_init/crop+stem",
                   launch_crop_stem(frames, frame_offsets + c0, frame_hw + 2 * c0, boxes_xywh + 4 * c0, h->cfg.template_factor, kTz, m,
-                                   h->mw, h->d_scratch, h->d_tmpl + (size_t)(first + c0) * kNz * kC, kNz, 0, h->d_status + first + c0, st));
+                                   h->mw, h->d_scratch, h->d_tmpl + (size_t)(first + c0) * kNz * kC, kNz, 0, h->d_status + first + c0,
+                                   h->cfg.blocks_impl == VT_BLOCKS_TCGEN05, st));
     }
     VT_CUDA(h, cudaMemcpyAsync(h->d_state + (size_t)first * 4, boxes_xywh, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if (out_status) VT_CUDA(h, cudaMemcpyAsync(out_status, h->d_status + first, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
@@ -568,7 +602,8 @@ int vt_tracks_step(VtHandle h, const uint8_t* frames, const int64_t* frame_offse
         const int t0 = first + c0;
         VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_tracks_step/crop+stem",
                   launch_crop_stem(frames, frame_offsets + c0, frame_hw + 2 * c0, h->d_state + (size_t)t0 * 4, h->cfg.search_factor, kSx, m,
-                                   h->mw, h->d_scratch, h->d_tokx + (size_t)c0 * kNx * kC, kNx, 0, h->d_status + t0, st));
+                                   h->mw, h->d_scratch, h->d_tokx + (size_t)c0 * kNx * kC, kNx, 0, h->d_status + t0,
+                                   h->cfg.blocks_impl == VT_BLOCKS_TCGEN05, st));
     }
     {
         const int m = n;

@@ -60,6 +60,8 @@ struct ModelW {
     const float *norm_g, *norm_b;
     const float *pos_z, *pos_x;    // [64][48], [256][48]
     HeadW head;
+    const uint8_t* stem_tc_w[2];   // stem conv3 / conv4 for tcgen05 (vt_stem_tc.cu): fp16 hi | lo, K-major chunks, T_A taps then T_B taps
+    const float* stem_tc_b[2];     // biases padded to the MMA N
     const uint8_t* head_tc_w1;     // head conv1 for tcgen05: 6 pieces (half h, kx) x [hi | lo] x K-major [k/8][48][8], k = ky*48 + ci
     const float* hann;             // [256] fp32 window (lib/test/utils/hann.py)
     const float* lut;              // [3][256] normalisation table ((v/255 - mean)/std)
@@ -75,12 +77,16 @@ int launch_crop_normalize(const uint8_t* frames, const int64_t* frame_offsets, c
 // scratch must hold n * stem_scratch_floats(S) floats.
 size_t stem_scratch_floats(int S);
 int launch_stem(const float* img, int S, int n, const ModelW& w, float* scratch, float* tokens,
-                int tok_stride_rows, int tok_off, cudaStream_t st);
+                int tok_stride_rows, int tok_off, bool use_tc, cudaStream_t st);
+// Search-branch conv3 + conv4 on the tensor cores (a2: conv2 output [n][12][64][64]; a3: scratch for conv3 output)
+int launch_stem34_tc(const float* a2, int n, const ModelW& w, float* a3, float* tokens, int tok_stride_rows, int tok_off,
+                     cudaStream_t st);
+size_t stem_tc_weight_bytes(int layer);
 
 // Crop + stem straight from raw uint8 frames (the first conv layer gathers its tile from the frame).
 int launch_crop_stem(const uint8_t* frames, const int64_t* frame_offsets, const int32_t* frame_hw, const double* boxes,
                      double factor, int S, int n, const ModelW& w, float* scratch, float* tokens, int tok_stride_rows,
-                     int tok_off, int32_t* out_status, cudaStream_t st);
+                     int tok_off, int32_t* out_status, bool use_tc, cudaStream_t st);
 
 // ViT blocks (fp32 SIMT): tokens_z [n][64][48] (stride z_stride rows per track), tokens_x likewise; in place
 // result written to out [n][320][48]; taps (or null) receives [depth][n][320][48].

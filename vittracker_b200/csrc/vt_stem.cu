@@ -375,7 +375,7 @@ static int run_crop_conv1(const uint8_t* frames, const int64_t* frame_offsets, c
 // Crop + stem straight from raw frames (fused first layer); same outputs as launch_crop_normalize + launch_stem.
 int launch_crop_stem(const uint8_t* frames, const int64_t* frame_offsets, const int32_t* frame_hw, const double* boxes,
                      double factor, int S, int n, const ModelW& w, float* scratch, float* tokens, int tok_stride_rows,
-                     int tok_off, int32_t* out_status, cudaStream_t st) {
+                     int tok_off, int32_t* out_status, bool use_tc, cudaStream_t st) {
     if (n <= 0) return 0;
     float* a1 = scratch;
     float* a2 = a1 + (size_t)n * 6 * (S / 2) * (S / 2);
@@ -389,6 +389,10 @@ int launch_crop_stem(const uint8_t* frames, const int64_t* frame_offsets, const 
     total += r;
     if ((r = run_conv<6, 12, 12, 2, 32, 16, true, false>(a1, S / 2, n, w.stem[1], a2, nullptr, 0, 0, st)) < 0) return r;
     total += r;
+    if (use_tc && S == kSx) {        // search branch: layers 3 and 4 on the tensor cores
+        if ((r = launch_stem34_tc(a2, n, w, a3, tokens, tok_stride_rows, tok_off, st)) < 0) return r;
+        return total + r;
+    }
     if ((r = run_conv<12, 24, 12, 2, 32, 8, true, false>(a2, S / 4, n, w.stem[2], a3, nullptr, 0, 0, st)) < 0) return r;
     total += r;
     if ((r = run_conv<24, 48, 12, 4, 16, 16, false, true>(a3, S / 8, n, w.stem[3], tokens, pos, tok_stride_rows, tok_off, st)) < 0) return r;
@@ -397,7 +401,7 @@ int launch_crop_stem(const uint8_t* frames, const int64_t* frame_offsets, const 
 }
 
 int launch_stem(const float* img, int S, int n, const ModelW& w, float* scratch, float* tokens,
-                int tok_stride_rows, int tok_off, cudaStream_t st) {
+                int tok_stride_rows, int tok_off, bool use_tc, cudaStream_t st) {
     if (n <= 0) return 0;
     float* a1 = scratch;
     float* a2 = a1 + (size_t)n * 6 * (S / 2) * (S / 2);
@@ -409,6 +413,10 @@ int launch_stem(const float* img, int S, int n, const ModelW& w, float* scratch,
     total += r;
     if ((r = run_conv<6, 12, 12, 2, 32, 16, true, false>(a1, S / 2, n, w.stem[1], a2, nullptr, 0, 0, st)) < 0) return r;
     total += r;
+    if (use_tc && S == kSx) {        // search branch: layers 3 and 4 on the tensor cores
+        if ((r = launch_stem34_tc(a2, n, w, a3, tokens, tok_stride_rows, tok_off, st)) < 0) return r;
+        return total + r;
+    }
     if ((r = run_conv<12, 24, 12, 2, 32, 8, true, false>(a2, S / 4, n, w.stem[2], a3, nullptr, 0, 0, st)) < 0) return r;
     total += r;
     if ((r = run_conv<24, 48, 12, 4, 16, 16, false, true>(a3, S / 8, n, w.stem[3], tokens, pos, tok_stride_rows, tok_off, st)) < 0) return r;
