@@ -41,7 +41,8 @@ struct VtContext {
     int chunk = 0;
     int num_sms = 148;
     // chunk workspace
-    float* d_scratch = nullptr;       // stem intermediates
+    float* d_scratch = nullptr;       // stem intermediates (fp32 NCHW)
+    uint8_t* d_planes = nullptr;      // tensor-core operand images of conv3 / conv4 (zero rows must stay zero); null in SIMT mode
     float* d_tokz = nullptr;          // [chunk][64][48]   (vt_forward only)
     float* d_tokx = nullptr;          // [max_tracks][256][48]
     float* d_tok = nullptr;           // [max_tracks][320][48]
@@ -147,7 +148,7 @@ struct Packer {
 void free_all(VtHandle h) {
     for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : h->evpool) cudaEventDestroy(e);
-    cudaFree(h->d_weights); cudaFree(h->d_scratch); cudaFree(h->d_tokz);
+    cudaFree(h->d_weights); cudaFree(h->d_planes); cudaFree(h->d_scratch); cudaFree(h->d_tokz);
     cudaFree(h->d_tokx); cudaFree(h->d_tok); cudaFree(h->d_state); cudaFree(h->d_tmpl);
     cudaFree(h->d_status); cudaFree(h->d_maps);
 }
@@ -229,6 +230,11 @@ int vt_create(const VtConfig* cfg, VtHandle* out) {
     cudaError_t e = cudaSuccess;
     auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
     A((void**)&h->d_scratch, ch * stem_scratch_floats(kSx) * sizeof(float));
+    if (cfg->blocks_impl == VT_BLOCKS_TCGEN05) {
+        const size_t pb = ch * (tc_planes_bytes(kConv3Cch, kConv3Wout) + tc_planes_bytes(kConv4Cch, kConv4Wout));
+        A((void**)&h->d_planes, pb);
+        if (e == cudaSuccess) e = cudaMemset(h->d_planes, 0, pb);
+    }
     A((void**)&h->d_tokz, ch * kNz * kC * sizeof(float));
     A((void**)&h->d_tokx, mt * kNx * kC * sizeof(float));     // whole-step buffers: blocks + head run once per step
     A((void**)&h->d_tok, mt * kN * kC * sizeof(float));
@@ -312,36 +318,24 @@ int vt_finalize_weights(VtHandle h, void* stream) {
                     pk.buf[stem_w[l] + ((size_t)ci * 9 + k) * co_n + co] = (float)((double)w[((size_t)co * ci_n + ci) * 9 + k] * s);
         }
     }
-    // ---- stem conv3 / conv4 for the tensor cores: fp16 hi | lo, K-major chunks [k/8][NPAD][8];
-    //      accumulator A holds taps (ky, kx in {1, 2}), accumulator B taps (ky, kx = 0); channels / outputs zero padded
+    // ---- stem conv3 / conv4 for the tensor cores: fp16 hi | lo weight blobs in the kernels' K-step order (vt_stem_tc.cu)
     size_t stc_w[2], stc_b[2];
     {
-        const int lcin[2] = {12, 24}, lcch[2] = {2, 4}, lcout[2] = {24, 48}, lnpad[2] = {32, 48};
+        const int lcin[2] = {12, 24}, lcch[2] = {kConv3Cch, kConv4Cch}, lcout[2] = {24, 48}, lnpad[2] = {32, 48};
         for (int i = 0; i < 2; ++i) {
-            const int l = 2 + i, CIN = lcin[i], CCH = lcch[i], COUT = lcout[i], NPAD = lnpad[i];
-            const size_t prec = (size_t)9 * CCH * 8 * NPAD * 2;
-            stc_w[i] = slot(2 * prec / 4);
-            stc_b[i] = slot(NPAD);
-            if (prec * 2 != stem_tc_weight_bytes(i)) return fail(h, VT_ERR_WEIGHTS, "internal: stem tc weight size mismatch");
+            const int l = 2 + i;
+            const size_t bytes = stem_tc_weight_bytes(i);
+            stc_w[i] = slot(bytes / 4);
+            stc_b[i] = slot(lnpad[i]);
             uint8_t* hi8 = reinterpret_cast<uint8_t*>(&pk.buf[stc_w[i]]);
-            uint8_t* lo8 = hi8 + prec;
-            const float* wf = &pk.buf[stem_w[l]];             // folded [ci][ky][kx][co]
-            for (int co = 0; co < COUT; ++co) pk.buf[stc_b[i] + co] = pk.buf[stem_b[l] + co];
-            for (int q = 0; q < 9 * CCH; ++q) {
-                const bool accB = q >= 6 * CCH;
-                const int tap = (accB ? q - 6 * CCH : q) / CCH, cc = q % CCH;
-                const int ky = accB ? tap : tap / 2, kx = accB ? 0 : 1 + (tap & 1);
-                for (int n = 0; n < NPAD; ++n)
-                    for (int e = 0; e < 8; ++e) {
-                        const int ci = cc * 8 + e;
-                        const float v = (ci < CIN && n < COUT) ? wf[(((size_t)ci * 3 + ky) * 3 + kx) * COUT + n] : 0.f;
-                        const __half hi = __float2half_rn(v);
-                        const __half lo = __float2half_rn(v - __half2float(hi));
-                        const size_t off = ((size_t)q * NPAD + n) * 16 + e * 2;
-                        memcpy(hi8 + off, &hi, 2);
-                        memcpy(lo8 + off, &lo, 2);
-                    }
-            }
+            for (int co = 0; co < lcout[i]; ++co) pk.buf[stc_b[i] + co] = pk.buf[stem_b[l] + co];
+            stem_tc_pack_weights(lcin[i], lcch[i], lcout[i], lnpad[i], &pk.buf[stem_w[l]], hi8, hi8 + bytes / 2,
+                                 [](float v, uint16_t* hi, uint16_t* lo) {
+                                     const __half h2 = __float2half_rn(v);
+                                     const __half l2 = __float2half_rn(v - __half2float(h2));
+                                     memcpy(hi, &h2, 2);
+                                     memcpy(lo, &l2, 2);
+                                 });
         }
     }
     // ---- blocks: Linear weights [out][in] -> K-major [in][out]
@@ -539,8 +533,8 @@ int vt_forward(VtHandle h, const float* z, const float* x, int32_t n, float* pre
     const size_t tap_stride = (size_t)n * kN * kC;
     for (int first = 0; first < n; first += h->chunk) {
         const int m = (n - first < h->chunk) ? n - first : h->chunk;
-        VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_forward/stem(z)", launch_stem(z + (size_t)first * 3 * kTz * kTz, kTz, m, h->mw, h->d_scratch, h->d_tokz, kNz, 0, h->cfg.blocks_impl == VT_BLOCKS_TCGEN05, st));
-        VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_forward/stem(x)", launch_stem(x + (size_t)first * 3 * kSx * kSx, kSx, m, h->mw, h->d_scratch, h->d_tokx, kNx, 0, h->cfg.blocks_impl == VT_BLOCKS_TCGEN05, st));
+        VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_forward/stem(z)", launch_stem(z + (size_t)first * 3 * kTz * kTz, kTz, m, h->mw, h->d_scratch, h->d_tokz, kNz, 0, h->d_planes, h->chunk, st));
+        VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_forward/stem(x)", launch_stem(x + (size_t)first * 3 * kSx * kSx, kSx, m, h->mw, h->d_scratch, h->d_tokx, kNx, 0, h->d_planes, h->chunk, st));
         VT_LAUNCH(h, VT_STAGE_BLOCKS, m, st, "vt_forward/blocks", run_blocks(h, h->d_tokz, kNz, h->d_tokx, kNx, h->d_tok, m,
                                                       taps ? taps + (size_t)first * kN * kC : nullptr, tap_stride, st));
         HeadArgs a{};
@@ -580,7 +574,7 @@ int vt_tracks_init(VtHandle h, const uint8_t* frames, const int64_t* frame_offse
         VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_tracks_init/crop+stem",
                   launch_crop_stem(frames, frame_offsets + c0, frame_hw + 2 * c0, boxes_xywh + 4 * c0, h->cfg.template_factor, kTz, m,
                                    h->mw, h->d_scratch, h->d_tmpl + (size_t)(first + c0) * kNz * kC, kNz, 0, h->d_status + first + c0,
-                                   h->cfg.blocks_impl == VT_BLOCKS_TCGEN05, st));
+                                   h->d_planes, h->chunk, st));
     }
     VT_CUDA(h, cudaMemcpyAsync(h->d_state + (size_t)first * 4, boxes_xywh, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if (out_status) VT_CUDA(h, cudaMemcpyAsync(out_status, h->d_status + first, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
@@ -603,7 +597,7 @@ int vt_tracks_step(VtHandle h, const uint8_t* frames, const int64_t* frame_offse
         VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_tracks_step/crop+stem",
                   launch_crop_stem(frames, frame_offsets + c0, frame_hw + 2 * c0, h->d_state + (size_t)t0 * 4, h->cfg.search_factor, kSx, m,
                                    h->mw, h->d_scratch, h->d_tokx + (size_t)c0 * kNx * kC, kNx, 0, h->d_status + t0,
-                                   h->cfg.blocks_impl == VT_BLOCKS_TCGEN05, st));
+                                   h->d_planes, h->chunk, st));
     }
     {
         const int m = n;

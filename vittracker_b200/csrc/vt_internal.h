@@ -67,6 +67,17 @@ struct ModelW {
     const float* lut;              // [3][256] normalisation table ((v/255 - mean)/std)
 };
 
+// ---- tensor-core operand image ("planes") of a stride-2 conv input, written by the producing layer --------
+// in[gy][gx][ci] (gy, gx in [0, 2*Wout)) is stored as fp16 hi / lo in 8-channel chunks, split by row / column parity:
+//   byte offset = ((((prec * 4 + (gy&1)*2 + (gx&1)) * CCH + ci/8) * (Wout + 1) + (gy>>1) + 1) * Wout + (gx>>1)) * 16 + (ci%8)*2
+// Row 0 of every plane is the zero padding above the image (kept zero: nobody writes it).
+__host__ __device__ constexpr size_t tc_planes_bytes(int cch, int wout) { return (size_t)2 * 4 * cch * (wout + 1) * wout * 16; }
+__host__ __device__ inline size_t tc_planes_offset(int prec, int gy, int gx, int chunk, int cch, int wout) {
+    return ((((size_t)(prec * 4 + (gy & 1) * 2 + (gx & 1)) * cch + chunk) * (wout + 1) + (gy >> 1) + 1) * wout + (gx >> 1)) * 16;
+}
+constexpr int kConv3Cch = 2, kConv3Wout = 32;     // conv3 input: 12 channels -> 2 chunks, 64x64 -> planes of 33 x 32
+constexpr int kConv4Cch = 3, kConv4Wout = 16;     // conv4 input: 24 channels -> 3 chunks, 32x32 -> planes of 17 x 16
+
 // ---- kernel launchers (each returns the number of kernels it launched, or <0 on a CUDA error) -----
 int launch_crop_normalize(const uint8_t* frames, const int64_t* frame_offsets, const int32_t* frame_hw,
                           const double* boxes, double factor, int S, int n, const float* lut,
@@ -74,19 +85,22 @@ int launch_crop_normalize(const uint8_t* frames, const int64_t* frame_offsets, c
                           int32_t* out_status, cudaStream_t st);
 
 // Stem on `n` images of side S (128 or 256): in NCHW fp32 -> tokens[(b*tok_stride) + tok_off + t][48] (+pos).
-// scratch must hold n * stem_scratch_floats(S) floats.
+// scratch must hold n * stem_scratch_floats(S) floats and be zero-initialised once (the tensor-core path keeps zero rows in it).
 size_t stem_scratch_floats(int S);
+// planes (tensor-core path only): zero-initialised buffer of plane_tracks * (tc_planes_bytes(conv3) + tc_planes_bytes(conv4)) bytes
 int launch_stem(const float* img, int S, int n, const ModelW& w, float* scratch, float* tokens,
-                int tok_stride_rows, int tok_off, bool use_tc, cudaStream_t st);
+                int tok_stride_rows, int tok_off, uint8_t* planes, int plane_tracks, cudaStream_t st);
 // Search-branch conv3 + conv4 on the tensor cores (a2: conv2 output [n][12][64][64]; a3: scratch for conv3 output)
-int launch_stem34_tc(const float* a2, int n, const ModelW& w, float* a3, float* tokens, int tok_stride_rows, int tok_off,
-                     cudaStream_t st);
+int launch_stem34_tc(const uint8_t* planes3, int n, const ModelW& w, uint8_t* planes4, float* tokens, int tok_stride_rows,
+                     int tok_off, cudaStream_t st);
 size_t stem_tc_weight_bytes(int layer);
+void stem_tc_pack_weights(int cin, int cch, int cout, int npad, const float* wf, uint8_t* hi8, uint8_t* lo8,
+                          void (*split)(float, uint16_t*, uint16_t*));
 
 // Crop + stem straight from raw uint8 frames (the first conv layer gathers its tile from the frame).
 int launch_crop_stem(const uint8_t* frames, const int64_t* frame_offsets, const int32_t* frame_hw, const double* boxes,
                      double factor, int S, int n, const ModelW& w, float* scratch, float* tokens, int tok_stride_rows,
-                     int tok_off, int32_t* out_status, bool use_tc, cudaStream_t st);
+                     int tok_off, int32_t* out_status, uint8_t* planes, int plane_tracks, cudaStream_t st);
 
 // ViT blocks (fp32 SIMT): tokens_z [n][64][48] (stride z_stride rows per track), tokens_x likewise; in place
 // result written to out [n][320][48]; taps (or null) receives [depth][n][320][48].

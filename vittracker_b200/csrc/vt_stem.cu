@@ -10,6 +10,7 @@
 // token-major [token][48]) with the positional embedding added (vit_dist.py:53,81-82).
 #include "vt_geom.cuh"
 #include "vt_internal.h"
+#include "vt_tc.cuh"
 
 namespace vt {
 
@@ -50,7 +51,7 @@ struct ConvCfg {
 };
 
 // Accumulate and store: the tile / weights / bias are in shared memory (see ConvCfg for the tile layout).
-template <int CIN, int COUT, int QG, int P, int TW, int TH, bool HSWISH, bool TOKENS>
+template <int CIN, int COUT, int QG, int P, int TW, int TH, bool HSWISH, bool TOKENS, int TCOUT_CCH = 0>
 __device__ __forceinline__ void conv_compute(const float* tile, const float* ws, const float* bs, int tx0, int ty0, int Hout,
                                              int Wout, int b, float* __restrict__ out, const float* __restrict__ pos,
                                              int tok_stride_rows, int tok_off) {
@@ -119,7 +120,23 @@ __device__ __forceinline__ void conv_compute(const float* tile, const float* ws,
             if (HSWISH) v = v * fminf(fmaxf(v + 3.f, 0.f), 6.f) / 6.f;     // x * relu6(x + 3) / 6
             acc[p][q] = v;
         }
-        if (TOKENS) {
+        if (TCOUT_CCH > 0) {
+            // the next layer runs on the tensor cores: write its operand image (fp16 hi | lo, 8-channel chunks, parity planes)
+            static_assert(TCOUT_CCH == 0 || QG == COUT, "thread must own every channel of the pixel");
+            uint8_t* ob = reinterpret_cast<uint8_t*>(out) + (size_t)b * tc_planes_bytes(TCOUT_CCH, Wout / 2);
+#pragma unroll
+            for (int c = 0; c < TCOUT_CCH; ++c) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float v0 = (8 * c + 2 * j < COUT) ? acc[p][(8 * c + 2 * j) % QG] : 0.f;
+                    const float v1 = (8 * c + 2 * j + 1 < COUT) ? acc[p][(8 * c + 2 * j + 1) % QG] : 0.f;
+                    tc::split_pack2(v0, v1, hi[j], lo[j]);
+                }
+                *reinterpret_cast<uint4*>(ob + tc_planes_offset(0, oy, ox, c, TCOUT_CCH, Wout / 2)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(ob + tc_planes_offset(1, oy, ox, c, TCOUT_CCH, Wout / 2)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        } else if (TOKENS) {
             const int t = oy * Wout + ox;
             float* o = out + ((size_t)b * tok_stride_rows + tok_off + t) * COUT + cg * QG;
             const float* pe = pos + (size_t)t * COUT + cg * QG;
@@ -137,7 +154,7 @@ __device__ __forceinline__ void conv_compute(const float* tile, const float* ws,
     }
 }
 
-template <int CIN, int COUT, int QG, int P, int TW, int TH, bool HSWISH, bool TOKENS>
+template <int CIN, int COUT, int QG, int P, int TW, int TH, bool HSWISH, bool TOKENS, int TCOUT_CCH = 0>
 __global__ void __launch_bounds__(ConvCfg<CIN, COUT, QG, P, TW, TH>::kThreads)
 conv3x3s2_kernel(const float* __restrict__ in, int Hin, int Win, const float* __restrict__ wg,
                  const float* __restrict__ bg, float* __restrict__ out, const float* __restrict__ pos,
@@ -205,7 +222,7 @@ conv3x3s2_kernel(const float* __restrict__ in, int Hin, int Win, const float* __
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncthreads();
 
-    conv_compute<CIN, COUT, QG, P, TW, TH, HSWISH, TOKENS>(tile, ws, bs, tx0, ty0, Hout, Wout, b, out, pos, tok_stride_rows, tok_off);
+    conv_compute<CIN, COUT, QG, P, TW, TH, HSWISH, TOKENS, TCOUT_CCH>(tile, ws, bs, tx0, ty0, Hout, Wout, b, out, pos, tok_stride_rows, tok_off);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -322,11 +339,11 @@ crop_conv1_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict_
     conv_compute<3, 6, 6, 4, 32, 32, true, false>(tile, ws, bs, tx0, ty0, Hout, Hout, item, out, nullptr, 0, 0);
 }
 
-template <int CIN, int COUT, int QG, int P, int TW, int TH, bool HSWISH, bool TOKENS>
+template <int CIN, int COUT, int QG, int P, int TW, int TH, bool HSWISH, bool TOKENS, int TCOUT_CCH = 0>
 static int run_conv(const float* in, int Hin, int n, const StemLayerW& w, float* out, const float* pos,
                     int tok_stride_rows, int tok_off, cudaStream_t st) {
     using K = ConvCfg<CIN, COUT, QG, P, TW, TH>;
-    auto kern = conv3x3s2_kernel<CIN, COUT, QG, P, TW, TH, HSWISH, TOKENS>;
+    auto kern = conv3x3s2_kernel<CIN, COUT, QG, P, TW, TH, HSWISH, TOKENS, TCOUT_CCH>;
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::kSmemBytes) != cudaSuccess) return -1;
@@ -339,7 +356,8 @@ static int run_conv(const float* in, int Hin, int n, const StemLayerW& w, float*
         const int m = min(32768, n - first);
         dim3 grid(tiles, m);
         const float* inp = in + (size_t)first * CIN * Hin * Hin;
-        float* o = TOKENS ? out + (size_t)first * tok_stride_rows * COUT : out + (size_t)first * COUT * Hout * Hout;
+        float* o = TCOUT_CCH > 0 ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(out) + (size_t)first * tc_planes_bytes(TCOUT_CCH, Hout / 2))
+                   : TOKENS ? out + (size_t)first * tok_stride_rows * COUT : out + (size_t)first * COUT * Hout * Hout;
         kern<<<grid, K::kThreads, K::kSmemBytes, st>>>(inp, Hin, Hin, w.w, w.b, o, pos, tok_stride_rows, tok_off);
         ++launched;
     }
@@ -375,7 +393,7 @@ static int run_crop_conv1(const uint8_t* frames, const int64_t* frame_offsets, c
 // Crop + stem straight from raw frames (fused first layer); same outputs as launch_crop_normalize + launch_stem.
 int launch_crop_stem(const uint8_t* frames, const int64_t* frame_offsets, const int32_t* frame_hw, const double* boxes,
                      double factor, int S, int n, const ModelW& w, float* scratch, float* tokens, int tok_stride_rows,
-                     int tok_off, int32_t* out_status, bool use_tc, cudaStream_t st) {
+                     int tok_off, int32_t* out_status, uint8_t* planes, int plane_tracks, cudaStream_t st) {
     if (n <= 0) return 0;
     float* a1 = scratch;
     float* a2 = a1 + (size_t)n * 6 * (S / 2) * (S / 2);
@@ -387,12 +405,17 @@ int launch_crop_stem(const uint8_t* frames, const int64_t* frame_offsets, const 
     else return -1;
     if (r < 0) return r;
     total += r;
-    if ((r = run_conv<6, 12, 12, 2, 32, 16, true, false>(a1, S / 2, n, w.stem[1], a2, nullptr, 0, 0, st)) < 0) return r;
-    total += r;
-    if (use_tc && S == kSx) {        // search branch: layers 3 and 4 on the tensor cores
-        if ((r = launch_stem34_tc(a2, n, w, a3, tokens, tok_stride_rows, tok_off, st)) < 0) return r;
+    if (planes && S == kSx && n <= plane_tracks) {
+        // search branch: conv2 writes conv3's tensor-core operand image, layers 3 and 4 run on tcgen05
+        uint8_t* planes3 = planes;
+        uint8_t* planes4 = planes + (size_t)plane_tracks * tc_planes_bytes(kConv3Cch, kConv3Wout);
+        if ((r = run_conv<6, 12, 12, 2, 32, 16, true, false, kConv3Cch>(a1, S / 2, n, w.stem[1], reinterpret_cast<float*>(planes3), nullptr, 0, 0, st)) < 0) return r;
+        total += r;
+        if ((r = launch_stem34_tc(planes3, n, w, planes4, tokens, tok_stride_rows, tok_off, st)) < 0) return r;
         return total + r;
     }
+    if ((r = run_conv<6, 12, 12, 2, 32, 16, true, false>(a1, S / 2, n, w.stem[1], a2, nullptr, 0, 0, st)) < 0) return r;
+    total += r;
     if ((r = run_conv<12, 24, 12, 2, 32, 8, true, false>(a2, S / 4, n, w.stem[2], a3, nullptr, 0, 0, st)) < 0) return r;
     total += r;
     if ((r = run_conv<24, 48, 12, 4, 16, 16, false, true>(a3, S / 8, n, w.stem[3], tokens, pos, tok_stride_rows, tok_off, st)) < 0) return r;
@@ -401,7 +424,7 @@ int launch_crop_stem(const uint8_t* frames, const int64_t* frame_offsets, const 
 }
 
 int launch_stem(const float* img, int S, int n, const ModelW& w, float* scratch, float* tokens,
-                int tok_stride_rows, int tok_off, bool use_tc, cudaStream_t st) {
+                int tok_stride_rows, int tok_off, uint8_t* planes, int plane_tracks, cudaStream_t st) {
     if (n <= 0) return 0;
     float* a1 = scratch;
     float* a2 = a1 + (size_t)n * 6 * (S / 2) * (S / 2);
@@ -411,12 +434,17 @@ int launch_stem(const float* img, int S, int n, const ModelW& w, float* scratch,
     //                CIN COUT QG P  TW  TH  hswish tokens
     if ((r = run_conv<3, 6, 6, 4, 32, 32, true, false>(img, S, n, w.stem[0], a1, nullptr, 0, 0, st)) < 0) return r;
     total += r;
-    if ((r = run_conv<6, 12, 12, 2, 32, 16, true, false>(a1, S / 2, n, w.stem[1], a2, nullptr, 0, 0, st)) < 0) return r;
-    total += r;
-    if (use_tc && S == kSx) {        // search branch: layers 3 and 4 on the tensor cores
-        if ((r = launch_stem34_tc(a2, n, w, a3, tokens, tok_stride_rows, tok_off, st)) < 0) return r;
+    if (planes && S == kSx && n <= plane_tracks) {
+        // search branch: conv2 writes conv3's tensor-core operand image, layers 3 and 4 run on tcgen05
+        uint8_t* planes3 = planes;
+        uint8_t* planes4 = planes + (size_t)plane_tracks * tc_planes_bytes(kConv3Cch, kConv3Wout);
+        if ((r = run_conv<6, 12, 12, 2, 32, 16, true, false, kConv3Cch>(a1, S / 2, n, w.stem[1], reinterpret_cast<float*>(planes3), nullptr, 0, 0, st)) < 0) return r;
+        total += r;
+        if ((r = launch_stem34_tc(planes3, n, w, planes4, tokens, tok_stride_rows, tok_off, st)) < 0) return r;
         return total + r;
     }
+    if ((r = run_conv<6, 12, 12, 2, 32, 16, true, false>(a1, S / 2, n, w.stem[1], a2, nullptr, 0, 0, st)) < 0) return r;
+    total += r;
     if ((r = run_conv<12, 24, 12, 2, 32, 8, true, false>(a2, S / 4, n, w.stem[2], a3, nullptr, 0, 0, st)) < 0) return r;
     total += r;
     if ((r = run_conv<24, 48, 12, 4, 16, 16, false, true>(a3, S / 8, n, w.stem[3], tokens, pos, tok_stride_rows, tok_off, st)) < 0) return r;
