@@ -416,25 +416,37 @@ int vt_finalize_weights(VtHandle h, void* stream) {
             }
         }
     }
-    // head conv1 for the tensor cores: piece (h, kx) holds B[n = co - 48 h][k = ky * 48 + ci] as fp16 hi | lo
-    const size_t o_htc = slot(6 * kHeadTcPieceBytes / 4);
+    // head conv1 / conv2 for the tensor cores (fp16 hi | lo, K-major [k/8][n][8]); see vt_head.cu
+    const size_t o_htc = slot(18 * kHeadTcPieceBytes / 4), o_htc2 = slot(kHeadTcW2Bytes / 4);
     {
+        auto put = [&](uint8_t* hi8, uint8_t* lo8, size_t off, float v) {
+            const __half hi = __float2half_rn(v);
+            const __half lo = __float2half_rn(v - __half2float(hi));
+            memcpy(hi8 + off, &hi, 2);
+            memcpy(lo8 + off, &lo, 2);
+        };
         uint8_t* base8 = reinterpret_cast<uint8_t*>(&pk.buf[o_htc]);
         const float* w1 = &pk.buf[hw[0]];                       // folded, [ci][ky*3+kx][96]
         for (int h2 = 0; h2 < 2; ++h2)
-            for (int kx = 0; kx < 3; ++kx) {
-                uint8_t* hi8 = base8 + (size_t)(h2 * 3 + kx) * kHeadTcPieceBytes;
-                uint8_t* lo8 = hi8 + kHeadTcPieceBytes / 2;
-                for (int n = 0; n < 48; ++n)
+            for (int kx = 0; kx < 3; ++kx)
+                for (int ky = 0; ky < 3; ++ky) {                // piece p = (h * 3 + kx) * 3 + ky: B[n = co - 48 h][k = ci]
+                    uint8_t* hi8 = base8 + (size_t)((h2 * 3 + kx) * 3 + ky) * kHeadTcPieceBytes;
+                    uint8_t* lo8 = hi8 + kHeadTcPieceBytes / 2;
+                    for (int n = 0; n < 48; ++n)
+                        for (int ci = 0; ci < 48; ++ci)
+                            put(hi8, lo8, ((size_t)(ci / 8) * 48 + n) * 16 + (ci % 8) * 2, w1[((size_t)ci * 9 + ky * 3 + kx) * 96 + h2 * 48 + n]);
+                }
+        uint8_t* base2 = reinterpret_cast<uint8_t*>(&pk.buf[o_htc2]);
+        const float* w2 = &pk.buf[hw[1]];                       // folded, [ci][ky*3+kx][tower][16]
+        for (int t = 0; t < 3; ++t)
+            for (int kx = 0; kx < 3; ++kx) {                    // blob (tower, kx): B[n = co][k = ky * 32 + ci]
+                uint8_t* hi8 = base2 + (size_t)(t * 3 + kx) * 6144;
+                uint8_t* lo8 = hi8 + 3072;
+                for (int n = 0; n < 16; ++n)
                     for (int ky = 0; ky < 3; ++ky)
-                        for (int ci = 0; ci < 48; ++ci) {
-                            const int k = ky * 48 + ci;
-                            const float v = w1[((size_t)ci * 9 + ky * 3 + kx) * 96 + h2 * 48 + n];
-                            const __half hi = __float2half_rn(v);
-                            const __half lo = __float2half_rn(v - __half2float(hi));
-                            const size_t off = ((size_t)(k / 8) * 48 + n) * 16 + (k % 8) * 2;
-                            memcpy(hi8 + off, &hi, 2);
-                            memcpy(lo8 + off, &lo, 2);
+                        for (int ci = 0; ci < 32; ++ci) {
+                            const int k = ky * 32 + ci;
+                            put(hi8, lo8, ((size_t)(k / 8) * 16 + n) * 16 + (k % 8) * 2, w2[(((size_t)ci * 9 + ky * 3 + kx) * 3 + t) * 16 + n]);
                         }
             }
     }
@@ -500,6 +512,7 @@ int vt_finalize_weights(VtHandle h, void* stream) {
     m.head.w3 = base + hw[2]; m.head.b3 = base + hb[2]; m.head.w4 = base + hw[3]; m.head.b4 = base + hb[3];
     m.head.w5 = base + hw[4]; m.head.b5 = base + hb[4];
     m.head_tc_w1 = reinterpret_cast<const uint8_t*>(base + o_htc);
+    m.head_tc_w2 = reinterpret_cast<const uint8_t*>(base + o_htc2);
     for (int i = 0; i < 2; ++i) { m.stem_tc_w[i] = reinterpret_cast<const uint8_t*>(base + stc_w[i]); m.stem_tc_b[i] = base + stc_b[i]; }
     m.hann = base + o_hann; m.lut = base + o_lut;
     h->finalized = true;

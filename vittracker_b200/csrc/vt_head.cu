@@ -8,8 +8,8 @@
 // The three towers' first convolutions share their input and are merged into one 48->96 layer whose
 // 166 KB of weights are streamed through a double-buffered cp.async ring; later layers reuse the ring.
 //
-// head_kernel<true> runs that first 48 -> 96 convolution (69 % of the head's FLOPs) on the tcgen05 tensor
-// cores instead: the LayerNorm output is written to shared memory as fp16 hi/lo in 8-channel chunks
+// head_tc_kernel runs the first two convolution layers (48 -> 96 merged and 32 -> 16 per tower, 92 % of the head's
+// FLOPs) on the tcgen05 tensor cores instead: the LayerNorm output is written to shared memory as fp16 hi/lo in 8-channel chunks
 // [chunk][row 0..17][x 0..15][8] (a zero row above and below), which a no-swizzle K-major UMMA descriptor can
 // address for any vertical tap by moving its start row.  Horizontal taps are not gathered at all: for each kx
 // one accumulator T_kx[y][x'] = sum_{ky,ci} in[y+ky-1][x'][ci] W[ci][ky][kx][co] is built in TMEM over the
@@ -20,6 +20,14 @@
 #include "vt_tc.cuh"
 
 namespace vt {
+
+#ifdef VT_HEAD_TRACE
+__device__ long long g_head_trace[32];
+#define HEAD_TRACE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_head_trace[i] = clock64(); } while (0)
+extern "C" int vt_head_trace_read(long long* host) { cudaDeviceSynchronize(); return (int)cudaMemcpyFromSymbol(host, g_head_trace, sizeof(long long) * 32); }
+#else
+#define HEAD_TRACE(i) do {} while (0)
+#endif
 
 constexpr int kHeadThreads = 256;
 constexpr int kPlane = 18 * 18;                      // zero-bordered 16x16 plane
@@ -34,17 +42,24 @@ constexpr int kHeadFloats = kOffRed + 32;
 constexpr size_t kHeadSmemBytes = (size_t)kHeadFloats * sizeof(float);
 static_assert(kHeadSmemBytes <= 227 * 1024, "head smem");
 
-// ---- tensor-core conv1 (head_kernel<true>) -------------------------------------------------------------
-constexpr int kTcAChunk = 18 * 16 * 16;                 // bytes per 8-channel chunk: 18 rows x 16 px x 16 B
-constexpr int kTcAHi = 0, kTcALo = 6 * kTcAChunk;       // inside the (otherwise unused) feat region
-static_assert(2 * 6 * kTcAChunk <= 48 * kPlane * 4, "A operand fits the feat region");
-constexpr int kTcWBuf0 = kOffW * 4;                     // weight piece ring: buffer 0 = the cp.async ring area,
-constexpr int kTcWBuf1 = (kOffOut1 + 48 * kPlane) * 4;  // buffer 1 = conv1-output planes 48..95 (written only at the very end)
-static_assert(2 * kWChunk * 4 >= kHeadTcPieceBytes, "weight piece fits ring buffer 0");
-constexpr int kOffTcBar = kOffRed + 32;                 // 5 mbarriers + TMEM base (floats)
-constexpr int kHeadTcFloats = kOffTcBar + 16;
-constexpr size_t kHeadTcSmemBytes = (size_t)kHeadTcFloats * sizeof(float);
-static_assert(kHeadTcSmemBytes <= 227 * 1024 && (kOffTcBar * 4) % 8 == 0, "head smem (tc)");
+// ---- tensor-core head (head_tc_kernel): shared-memory plan, byte offsets ---------------------------------------
+//   R0   conv1 A operand: LayerNorm output, fp16 hi | lo, [chunk 0..5][row 0..17][x 0..15][8 ch]; later conv2's weights
+//   RING conv1 weight pieces (3 x 9216 B ring); later the cp.async ring of the CUDA-core layers
+//   R1   conv2 A operand: conv1 output (96 ch = 12 chunks), same chunk-image layout, hi | lo;
+//        later the zero-bordered fp32 planes of conv2 / conv3 / conv4 outputs
+constexpr int kTcAChunk = 18 * 16 * 16;                 // bytes of one 8-channel chunk image: 18 rows x 16 px x 16 B
+constexpr int kT_R0 = 0, kT_R0Bytes = 2 * 6 * kTcAChunk;                   // 55296
+constexpr int kT_Ring = kT_R0 + kT_R0Bytes, kT_PieceBytes = 2 * 6 * 48 * 16;   // piece (h, kx, ky): hi | lo, N = 48, K = 48 -> 9216
+constexpr int kT_R1 = kT_Ring + 3 * kT_PieceBytes, kT_R1Half = 12 * kTcAChunk; // 55296 per precision
+constexpr int kT_Out2 = kT_R1, kT_Out3 = kT_Out2 + 48 * kPlane * 4, kT_Out4 = kT_Out3 + 24 * kPlane * 4;
+constexpr int kT_Bias = kT_R1 + 2 * kT_R1Half;
+constexpr int kT_Maps = kT_Bias + 256 * 4;
+constexpr int kT_Red = kT_Maps + 6 * 256 * 4;
+constexpr int kT_Bar = kT_Red + 32 * 4;                 // loaded[3], consumed[3], acc_ready, w2_loaded, tmem base
+constexpr size_t kHeadTcSmemBytes = kT_Bar + 9 * 8;
+constexpr int kT_W2Bytes = 9 * 2 * 12 * 16 * 16;        // conv2 weights: (tower, kx) x [hi | lo] x K-major [12 chunks][16][8] = 55296
+static_assert(kT_W2Bytes <= kT_R0Bytes && kT_Out4 + 12 * kPlane * 4 <= kT_Bias && 3 * kT_PieceBytes >= 2 * kWChunk * 4, "head tc smem plan");
+static_assert(kHeadTcSmemBytes <= 227 * 1024 && kT_Bar % 8 == 0 && kT_R1 % 128 == 0, "head smem (tc)");
 
 __device__ __forceinline__ void cp_async16(float* dst_smem, const float* src_gmem) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
@@ -152,185 +167,38 @@ __device__ __forceinline__ float sigmoid_clamp(float v) {
     return fminf(fmaxf(s, 1e-4f), 0.9999f);               // torch.clamp(x.sigmoid_(), 1e-4, 1 - 1e-4)
 }
 
-template <bool TC>
-__global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(HeadArgs a, ModelW w) {
-    extern __shared__ __align__(128) float smem[];
-    float* feat = smem + kOffFeat;
-    float* out1 = smem + kOffOut1;
-    float* wbuf = smem + kOffW;
-    float* sb = smem + kOffBias;
-    float* maps = smem + kOffMaps;
-    float* red = smem + kOffRed;
-    const int trk = blockIdx.x;
+// Final LayerNorm of one token row (vit_dist.py:94); optionally stores the normalised row (tokens_norm tap).
+__device__ __forceinline__ void head_norm_row(const HeadArgs& a, const ModelW& w, int trk, int row, float (&y)[kC]) {
+    const float* src = a.tokens + ((size_t)trk * kN + row) * kC;
+    float x[kC];
+#pragma unroll
+    for (int k = 0; k < kC; k += 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + k));
+        x[k] = v.x; x[k + 1] = v.y; x[k + 2] = v.z; x[k + 3] = v.w;
+    }
+    float mean = 0.f;
+#pragma unroll
+    for (int k = 0; k < kC; ++k) mean += x[k];
+    mean *= (1.f / kC);
+    float var = 0.f;
+#pragma unroll
+    for (int k = 0; k < kC; ++k) { const float d = x[k] - mean; var = fmaf(d, d, var); }
+    const float rstd = rsqrtf(var * (1.f / kC) + kLnEps);
+#pragma unroll
+    for (int k = 0; k < kC; ++k) y[k] = (x[k] - mean) * rstd * __ldg(w.norm_g + k) + __ldg(w.norm_b + k);
+    if (a.tokens_norm) {
+        float* t = a.tokens_norm + ((size_t)trk * kN + row) * kC;
+#pragma unroll
+        for (int k = 0; k < kC; k += 4) *reinterpret_cast<float4*>(t + k) = make_float4(y[k], y[k + 1], y[k + 2], y[k + 3]);
+    }
+}
+
+// conv5 (1x1) + sigmoid/clamp, raw and Hann-weighted arg-max, box decode, state update (thread = pixel).
+// out4: [3 towers][4][324] zero-bordered planes; sb: bias block (w5 at +180, b5 at +204).
+__device__ __forceinline__ void head_finish(const HeadArgs& a, const ModelW& w, int trk, const float* out4, const float* sb,
+                                            float* maps, float* red, uint32_t tmem_to_free) {
     const int tid = threadIdx.x;
-
-    // zero the activation planes once: layer outputs only ever write interiors, borders stay zero
-    for (int i = tid * 4; i < kOffW; i += kHeadThreads * 4) *reinterpret_cast<float4*>(smem + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tid < 96) sb[tid] = w.head.b1[tid];
-    if (tid < 48) sb[96 + tid] = w.head.b2[tid];
-    if (tid < 24) sb[144 + tid] = w.head.b3[tid];
-    if (tid < 12) sb[168 + tid] = w.head.b4[tid];
-    if (tid < 24) sb[180 + tid] = w.head.w5[tid];
-    if (tid < 6) sb[204 + tid] = w.head.b5[tid];
-    uint64_t* tc_bar = reinterpret_cast<uint64_t*>(smem + kOffTcBar);      // [0,1] piece loaded, [2,3] piece consumed, [4] accumulators ready
-    uint32_t* tc_tmem = reinterpret_cast<uint32_t*>(tc_bar + 5);
-    if (TC) {
-        if (tid < 32) tc::tmem_alloc(tc_tmem, 512);
-        if (tid == 32) {
-            tc::mbar_init(tc_bar + 0, 1); tc::mbar_init(tc_bar + 1, 1);
-            tc::mbar_init(tc_bar + 2, 1); tc::mbar_init(tc_bar + 3, 1);
-            tc::mbar_init(tc_bar + 4, 1);
-            tc::mbar_fence_init();
-        }
-        tc::tc_fence_before();
-    }
-    __syncthreads();
-    if (TC) tc::tc_fence_after();
-
-    // ---- final LayerNorm (vit_dist.py:94) on search token `tid`; tokens -> (C,16,16) (vit_dist.py:126-129)
-    {
-        auto norm_row = [&](int row, float (&y)[kC]) {
-            const float* src = a.tokens + ((size_t)trk * kN + row) * kC;
-            float x[kC];
-#pragma unroll
-            for (int k = 0; k < kC; k += 4) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(src + k));
-                x[k] = v.x; x[k + 1] = v.y; x[k + 2] = v.z; x[k + 3] = v.w;
-            }
-            float mean = 0.f;
-#pragma unroll
-            for (int k = 0; k < kC; ++k) mean += x[k];
-            mean *= (1.f / kC);
-            float var = 0.f;
-#pragma unroll
-            for (int k = 0; k < kC; ++k) { const float d = x[k] - mean; var = fmaf(d, d, var); }
-            const float rstd = rsqrtf(var * (1.f / kC) + kLnEps);
-#pragma unroll
-            for (int k = 0; k < kC; ++k) y[k] = (x[k] - mean) * rstd * __ldg(w.norm_g + k) + __ldg(w.norm_b + k);
-            if (a.tokens_norm) {
-                float* t = a.tokens_norm + ((size_t)trk * kN + row) * kC;
-#pragma unroll
-                for (int k = 0; k < kC; k += 4) *reinterpret_cast<float4*>(t + k) = make_float4(y[k], y[k + 1], y[k + 2], y[k + 3]);
-            }
-        };
-        float y[kC];
-        norm_row(kNz + tid, y);
-        const int py = tid >> 4, px = tid & 15;
-        if (!TC) {
-#pragma unroll
-            for (int k = 0; k < kC; ++k) feat[k * kPlane + (py + 1) * 18 + px + 1] = y[k];
-        } else {
-            uint8_t* ab = reinterpret_cast<uint8_t*>(smem) + ((py + 1) * 16 + px) * 16;
-#pragma unroll
-            for (int c = 0; c < 6; ++c) {
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) tc::split_pack2(y[8 * c + 2 * j], y[8 * c + 2 * j + 1], hi[j], lo[j]);
-                *reinterpret_cast<uint4*>(ab + kTcAHi + c * kTcAChunk) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4*>(ab + kTcALo + c * kTcAChunk) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            }
-            tc::fence_async_smem();
-        }
-        if (a.tokens_norm && tid < kNz) { float yz[kC]; norm_row(tid, yz); }
-    }
-    __syncthreads();
-
-    // ---- conv towers ---------------------------------------------------------------------------
-    if (!TC) {
-        head_conv<48, 24, 4, false, 4>(feat, out1, w.head.w1, sb, wbuf);           // 48 -> 3x32 (merged)
-    } else {
-        const uint32_t tbase = __shfl_sync(0xffffffffu, *tc_tmem, 0);
-        const uint32_t sbase = tc::smem_u32(smem);
-        const int warp = tid >> 5, lane = tid & 31;
-        const uint32_t id48 = tc::instr_desc_f16(128, 48, false);
-        // piece p = 3 h + kx lives in ring buffer p & 1; D region of (tile, kx) = columns (tile * 3 + kx) * 48
-        auto load_piece = [&](int p) {
-            tc::bulk_g2s_elect(reinterpret_cast<uint8_t*>(smem) + ((p & 1) ? kTcWBuf1 : kTcWBuf0),
-                               w.head_tc_w1 + (size_t)p * kHeadTcPieceBytes, kHeadTcPieceBytes, tc_bar + (p & 1));
-        };
-        if (warp == 0) load_piece(0);
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-            if (warp == 0) {                     // convergent: every lane runs the program, one elected lane issues
-#pragma unroll 1
-                for (int kx = 0; kx < 3; ++kx) {
-                    const int p = 3 * h + kx;
-                    if (p + 1 < 6) {
-                        if (p >= 1) tc::mbar_wait(tc_bar + 2 + ((p + 1) & 1), ((p - 1) >> 1) & 1);   // piece p-1 consumed
-                        load_piece(p + 1);
-                    }
-                    tc::mbar_wait(tc_bar + (p & 1), (p >> 1) & 1);                                   // piece p landed
-                    tc::tc_fence_after();
-                    const uint32_t wb = sbase + ((p & 1) ? kTcWBuf1 : kTcWBuf0);
-#pragma unroll
-                    for (int tile = 0; tile < 2; ++tile) {
-                        const uint32_t d = tbase + (tile * 3 + kx) * 48;
-#pragma unroll
-                        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                            for (int ks = 0; ks < 3; ++ks) {
-                                const uint32_t aoff = (2 * ks) * kTcAChunk + (8 * tile + ky) * 256;
-                                const uint64_t ah = tc::smem_desc(sbase + kTcAHi + aoff, kTcAChunk, 128);
-                                const uint64_t al = tc::smem_desc(sbase + kTcALo + aoff, kTcAChunk, 128);
-                                const uint32_t boff = (ky * 6 + 2 * ks) * 768;
-                                const uint64_t bh = tc::smem_desc(wb + boff, 768, 128);
-                                const uint64_t bl = tc::smem_desc(wb + kHeadTcPieceBytes / 2 + boff, 768, 128);
-                                tc::mma_ss_elect(d, ah, bh, id48, (ky | ks) != 0);
-                                tc::mma_ss_elect(d, al, bh, id48, 1);
-                                tc::mma_ss_elect(d, ah, bl, id48, 1);
-                            }
-                    }
-                    tc::mma_commit_elect(tc_bar + 2 + (p & 1));
-                }
-                tc::mma_commit_elect(tc_bar + 4);
-            }
-            tc::mbar_wait(tc_bar + 4, h);
-            tc::tc_fence_after();
-            if (h == 1) {
-                // every MMA has completed: the fp16 operand (feat region, soon the conv2 output planes) and ring buffer 1
-                // (output planes 48..) are dead - restore the all-zero planes whose borders the CUDA-core layers rely on
-                for (int i = tid * 4; i < 48 * kPlane; i += kHeadThreads * 4)
-                    *reinterpret_cast<float4*>(feat + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int i = tid * 4; i < kHeadTcPieceBytes / 4; i += kHeadThreads * 4)
-                    *reinterpret_cast<float4*>(out1 + 48 * kPlane + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-                __syncthreads();
-            }
-            // epilogue: pixel = tid (tile = warp / 4, TMEM lane quarter = warp % 4); combine the three horizontal taps
-            {
-                const int tile = warp >> 2;
-                const uint32_t ta = tbase + ((uint32_t)(32 * (warp & 3)) << 16) + tile * 144;
-                const int py = tid >> 4, px = tid & 15;
-                float* op = out1 + (h * 48) * kPlane + (py + 1) * 18 + px + 1;
-#pragma unroll 1
-                for (int c0 = 0; c0 < 48; c0 += 16) {
-                    uint32_t r0[16], r1[16], r2[16];
-                    tc::tmem_ld16(ta + c0, r0);
-                    tc::tmem_ld16(ta + 48 + c0, r1);
-                    tc::tmem_ld16(ta + 96 + c0, r2);
-                    tc::tc_wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float t0 = __shfl_up_sync(0xffffffffu, __uint_as_float(r0[j]), 1);     // T_0[y][x-1]
-                        float t2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[j]), 1);   // T_2[y][x+1]
-                        if (px == 0) t0 = 0.f;
-                        if (px == 15) t2 = 0.f;
-                        const float v = (t0 + __uint_as_float(r1[j])) + t2 + sb[h * 48 + c0 + j];
-                        op[(c0 + j) * kPlane] = fmaxf(v, 0.f);                                   // ReLU
-                    }
-                }
-            }
-            tc::tc_fence_before();
-            __syncthreads();
-            tc::tc_fence_after();
-        }
-    }
-    float* out2 = feat;                                                            // [3][16] planes
-    head_conv<32, 16, 3, true, 8>(out1, out2, w.head.w2, sb + 96, wbuf);           // 32 -> 16 per tower
-    float* out3 = out1;                                                            // [3][8] planes
-    head_conv<16, 8, 3, true, 16>(out2, out3, w.head.w3, sb + 144, wbuf);          // 16 -> 8
-    float* out4 = out1 + 24 * kPlane;                                              // [3][4] planes
-    head_conv<8, 4, 3, true, 8>(out3, out4, w.head.w4, sb + 168, wbuf);            // 8 -> 4
-
+    HEAD_TRACE(5);
     // ---- conv5 (1x1) + sigmoid/clamp: thread = pixel ---------------------------------------------
     float* m_score = maps; float* m_size = maps + 256; float* m_off = maps + 768; float* m_resp = maps + 1280;
     {
@@ -364,7 +232,8 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(HeadArgs a, Model
     block_argmax256(m_score[tid], tid, red, raw_max, raw_idx);
     float win_max; int win_idx;
     block_argmax256(m_resp[tid], tid, red, win_max, win_idx);
-    if (TC && tid < 32) tc::tmem_dealloc(__shfl_sync(0xffffffffu, *tc_tmem, 0), 512);     // all TMEM reads ended before the barriers above
+    HEAD_TRACE(6);
+    if (tmem_to_free != 0xffffffffu && tid < 32) tc::tmem_dealloc(tmem_to_free, 512);     // all TMEM reads ended before the barriers above
     if (tid != 0) return;
 
     if (a.pred_boxes) {
@@ -420,16 +289,275 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(HeadArgs a, Model
     }
 }
 
+__global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(HeadArgs a, ModelW w) {
+    extern __shared__ __align__(128) float smem[];
+    float* feat = smem + kOffFeat;
+    float* out1 = smem + kOffOut1;
+    float* wbuf = smem + kOffW;
+    float* sb = smem + kOffBias;
+    float* maps = smem + kOffMaps;
+    float* red = smem + kOffRed;
+    const int trk = blockIdx.x;
+    const int tid = threadIdx.x;
+
+    HEAD_TRACE(0);
+    // zero the activation planes once: layer outputs only ever write interiors, borders stay zero
+    for (int i = tid * 4; i < kOffW; i += kHeadThreads * 4) *reinterpret_cast<float4*>(smem + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < 96) sb[tid] = w.head.b1[tid];
+    if (tid < 48) sb[96 + tid] = w.head.b2[tid];
+    if (tid < 24) sb[144 + tid] = w.head.b3[tid];
+    if (tid < 12) sb[168 + tid] = w.head.b4[tid];
+    if (tid < 24) sb[180 + tid] = w.head.w5[tid];
+    if (tid < 6) sb[204 + tid] = w.head.b5[tid];
+    __syncthreads();
+
+    // ---- final LayerNorm (vit_dist.py:94) on search token `tid`; tokens -> (C,16,16) (vit_dist.py:126-129)
+    {
+        float y[kC];
+        head_norm_row(a, w, trk, kNz + tid, y);
+        const int py = tid >> 4, px = tid & 15;
+#pragma unroll
+        for (int k = 0; k < kC; ++k) feat[k * kPlane + (py + 1) * 18 + px + 1] = y[k];
+        if (a.tokens_norm && tid < kNz) { float yz[kC]; head_norm_row(a, w, trk, tid, yz); }
+    }
+    __syncthreads();
+
+    HEAD_TRACE(1);
+    // ---- conv towers ---------------------------------------------------------------------------
+    head_conv<48, 24, 4, false, 4>(feat, out1, w.head.w1, sb, wbuf);               // 48 -> 3x32 (merged)
+    HEAD_TRACE(2);
+    float* out2 = feat;                                                            // [3][16] planes
+    head_conv<32, 16, 3, true, 8>(out1, out2, w.head.w2, sb + 96, wbuf);           // 32 -> 16 per tower
+    HEAD_TRACE(3);
+    float* out3 = out1;                                                            // [3][8] planes
+    head_conv<16, 8, 3, true, 16>(out2, out3, w.head.w3, sb + 144, wbuf);          // 16 -> 8
+    HEAD_TRACE(4);
+    float* out4 = out1 + 24 * kPlane;                                              // [3][4] planes
+    head_conv<8, 4, 3, true, 8>(out3, out4, w.head.w4, sb + 168, wbuf);            // 8 -> 4
+
+    head_finish(a, w, trk, out4, sb, maps, red, 0xffffffffu);
+}
+
+// Tensor-core head: conv1 (48 -> 96 merged) and conv2 (32 -> 16 per tower) on tcgen05, conv3-5 on CUDA cores.
+__global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, ModelW w) {
+    extern __shared__ __align__(128) float smem[];
+    uint8_t* sm8 = reinterpret_cast<uint8_t*>(smem);
+    float* sb = reinterpret_cast<float*>(sm8 + kT_Bias);
+    float* maps = reinterpret_cast<float*>(sm8 + kT_Maps);
+    float* red = reinterpret_cast<float*>(sm8 + kT_Red);
+    float* wbuf = reinterpret_cast<float*>(sm8 + kT_Ring);
+    uint64_t* bar_loaded = reinterpret_cast<uint64_t*>(sm8 + kT_Bar);      // [3]
+    uint64_t* bar_consumed = bar_loaded + 3;                               // [3]
+    uint64_t* bar_acc = bar_loaded + 6;
+    uint64_t* bar_w2 = bar_loaded + 7;
+    uint32_t* tc_tmem = reinterpret_cast<uint32_t*>(bar_loaded + 8);
+    const int trk = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int py = tid >> 4, px = tid & 15;
+
+    HEAD_TRACE(0);
+    // zero rows 0 and 17 of every chunk image (the vertical zero padding of both tensor-core convolutions)
+    for (int i = tid; i < 36 * 2 * 16; i += kHeadThreads) {
+        const int cimg = i / 32, rsel = (i / 16) & 1, q = i & 15;          // 12 + 24 chunk images (hi and lo), row 0 / 17, 16 px
+        const int base = cimg < 12 ? kT_R0 + cimg * kTcAChunk : kT_R1 + (cimg - 12) * kTcAChunk;
+        *reinterpret_cast<float4*>(sm8 + base + (rsel ? 17 * 256 : 0) + q * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (tid < 96) sb[tid] = w.head.b1[tid];
+    if (tid < 48) sb[96 + tid] = w.head.b2[tid];
+    if (tid < 24) sb[144 + tid] = w.head.b3[tid];
+    if (tid < 12) sb[168 + tid] = w.head.b4[tid];
+    if (tid < 24) sb[180 + tid] = w.head.w5[tid];
+    if (tid < 6) sb[204 + tid] = w.head.b5[tid];
+    if (warp == 0) tc::tmem_alloc(tc_tmem, 512);
+    if (tid == 32) {
+        for (int i = 0; i < 8; ++i) tc::mbar_init(bar_loaded + i, 1);
+        tc::mbar_fence_init();
+    }
+    // ---- final LayerNorm -> conv1's operand image (fp16 hi | lo, 8-channel chunks) ----------------------------------
+    {
+        float y[kC];
+        head_norm_row(a, w, trk, kNz + tid, y);
+        uint8_t* ab = sm8 + kT_R0 + ((py + 1) * 16 + px) * 16;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tc::split_pack2(y[8 * c + 2 * j], y[8 * c + 2 * j + 1], hi[j], lo[j]);
+            *reinterpret_cast<uint4*>(ab + c * kTcAChunk) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(ab + (6 + c) * kTcAChunk) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        if (a.tokens_norm && tid < kNz) { float yz[kC]; head_norm_row(a, w, trk, tid, yz); }
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    HEAD_TRACE(1);
+
+    const uint32_t tbase = __shfl_sync(0xffffffffu, *tc_tmem, 0);
+    const uint32_t sbase = tc::smem_u32(smem);
+    const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
+    const int tile = warp >> 2;                                            // epilogue: pixel = tid, M tile = warp / 4
+
+    // ---- conv1: 18 weight pieces p = (h * 3 + kx) * 3 + ky through a 3-deep ring; D(tile, kx) = columns (tile * 3 + kx) * 48 ----
+    {
+        const uint32_t id48 = tc::instr_desc_f16(128, 48, false);
+        auto load_piece = [&](int p) {
+            tc::bulk_g2s_elect(sm8 + kT_Ring + (p % 3) * kT_PieceBytes, w.head_tc_w1 + (size_t)p * kT_PieceBytes, kT_PieceBytes, bar_loaded + p % 3);
+        };
+        if (warp == 0) { load_piece(0); load_piece(1); }
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            if (warp == 0) {                     // convergent: every lane runs the program, one elected lane issues
+#pragma unroll 1
+                for (int q = 0; q < 9; ++q) {
+                    const int p = 9 * h + q, kx = q / 3, ky = q % 3;
+                    if (p + 2 < 18) {
+                        if (p >= 1) tc::mbar_wait(bar_consumed + (p - 1) % 3, ((p - 1) / 3) & 1);    // ring slot of piece p-1 is free
+                        load_piece(p + 2);
+                    }
+                    tc::mbar_wait(bar_loaded + p % 3, (p / 3) & 1);
+                    tc::tc_fence_after();
+                    const uint32_t wb = sbase + kT_Ring + (p % 3) * kT_PieceBytes;
+#pragma unroll
+                    for (int tl = 0; tl < 2; ++tl) {
+                        const uint32_t d = tbase + (tl * 3 + kx) * 48;
+#pragma unroll
+                        for (int ks = 0; ks < 3; ++ks) {
+                            const uint32_t aoff = kT_R0 + (2 * ks) * kTcAChunk + (8 * tl + ky) * 256;
+                            const uint64_t ah = tc::smem_desc(sbase + aoff, kTcAChunk, 128);
+                            const uint64_t al = tc::smem_desc(sbase + aoff + 6 * kTcAChunk, kTcAChunk, 128);
+                            const uint64_t bh = tc::smem_desc(wb + (2 * ks) * 768, 768, 128);
+                            const uint64_t bl = tc::smem_desc(wb + kT_PieceBytes / 2 + (2 * ks) * 768, 768, 128);
+                            tc::mma_ss_elect(d, ah, bh, id48, (ky | ks) != 0);
+                            tc::mma_ss_elect(d, al, bh, id48, 1);
+                            tc::mma_ss_elect(d, ah, bl, id48, 1);
+                        }
+                    }
+                    tc::mma_commit_elect(bar_consumed + p % 3);
+                }
+                tc::mma_commit_elect(bar_acc);
+            }
+            tc::mbar_wait(bar_acc, h);
+            tc::tc_fence_after();
+            if (h == 1 && warp == 0)             // conv1's operand is dead: conv2's weights stream into its place
+                tc::bulk_g2s_elect(sm8 + kT_R0, w.head_tc_w2, kT_W2Bytes, bar_w2);
+            // epilogue: combine the three horizontal taps, bias, ReLU -> conv2's operand image (channels 48 h ..)
+            {
+                const uint32_t ta = tbase + lane_addr + tile * 144;
+                uint8_t* ob = sm8 + kT_R1 + ((py + 1) * 16 + px) * 16;
+#pragma unroll 1
+                for (int c0 = 0; c0 < 48; c0 += 16) {
+                    uint32_t r0[16], r1[16], r2[16];
+                    tc::tmem_ld16(ta + c0, r0);
+                    tc::tmem_ld16(ta + 48 + c0, r1);
+                    tc::tmem_ld16(ta + 96 + c0, r2);
+                    tc::tc_wait_ld();
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float t0 = __shfl_up_sync(0xffffffffu, __uint_as_float(r0[j]), 1);     // T_0[y][x-1]
+                        float t2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[j]), 1);   // T_2[y][x+1]
+                        if (px == 0) t0 = 0.f;
+                        if (px == 15) t2 = 0.f;
+                        v[j] = fmaxf((t0 + __uint_as_float(r1[j])) + t2 + sb[h * 48 + c0 + j], 0.f);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) tc::split_pack2(v[8 * c + 2 * j], v[8 * c + 2 * j + 1], hi[j], lo[j]);
+                        const int chunk = (h * 48 + c0) / 8 + c;
+                        *reinterpret_cast<uint4*>(ob + chunk * kTcAChunk) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(ob + kT_R1Half + chunk * kTcAChunk) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
+            }
+            tc::fence_async_smem();
+            tc::tc_fence_before();
+            __syncthreads();
+            tc::tc_fence_after();
+        }
+    }
+    HEAD_TRACE(2);
+
+    // ---- conv2 (per tower 32 -> 16): D(tower, tile, kx) = columns ((tower * 2 + tile) * 3 + kx) * 16 ----------------------
+    if (warp == 0) {
+        const uint32_t id16 = tc::instr_desc_f16(128, 16, false);
+        tc::mbar_wait(bar_w2, 0);
+        tc::tc_fence_after();
+#pragma unroll 1
+        for (int tw = 0; tw < 3; ++tw)
+#pragma unroll
+            for (int tl = 0; tl < 2; ++tl)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const uint32_t d = tbase + ((tw * 2 + tl) * 3 + kx) * 16;
+                    const uint32_t wb = sbase + kT_R0 + (tw * 3 + kx) * 6144;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                        for (int kp = 0; kp < 2; ++kp) {
+                            const uint32_t aoff = kT_R1 + (4 * tw + 2 * kp) * kTcAChunk + (8 * tl + ky) * 256;
+                            const uint64_t ah = tc::smem_desc(sbase + aoff, kTcAChunk, 128);
+                            const uint64_t al = tc::smem_desc(sbase + aoff + kT_R1Half, kTcAChunk, 128);
+                            const uint64_t bh = tc::smem_desc(wb + (ky * 4 + 2 * kp) * 256, 256, 128);
+                            const uint64_t bl = tc::smem_desc(wb + 3072 + (ky * 4 + 2 * kp) * 256, 256, 128);
+                            tc::mma_ss_elect(d, ah, bh, id16, (ky | kp) != 0);
+                            tc::mma_ss_elect(d, al, bh, id16, 1);
+                            tc::mma_ss_elect(d, ah, bl, id16, 1);
+                        }
+                }
+        tc::mma_commit_elect(bar_acc);
+    }
+    tc::mbar_wait(bar_acc, 0);
+    tc::tc_fence_after();
+    // conv2's operand is dead: its place becomes the zero-bordered fp32 planes of the remaining (CUDA-core) layers
+    for (int i = tid * 4; i < (48 + 24 + 12) * kPlane; i += kHeadThreads * 4)
+        *reinterpret_cast<float4*>(sm8 + kT_Out2 + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    float* out2 = reinterpret_cast<float*>(sm8 + kT_Out2);
+    float* out3 = reinterpret_cast<float*>(sm8 + kT_Out3);
+    float* out4 = reinterpret_cast<float*>(sm8 + kT_Out4);
+    {
+        float* op = out2 + (py + 1) * 18 + px + 1;
+#pragma unroll 1
+        for (int tw = 0; tw < 3; ++tw) {
+            const uint32_t ta = tbase + lane_addr + ((tw * 2 + tile) * 3) * 16;
+            uint32_t r0[16], r1[16], r2[16];
+            tc::tmem_ld16(ta, r0);
+            tc::tmem_ld16(ta + 16, r1);
+            tc::tmem_ld16(ta + 32, r2);
+            tc::tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float t0 = __shfl_up_sync(0xffffffffu, __uint_as_float(r0[j]), 1);
+                float t2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[j]), 1);
+                if (px == 0) t0 = 0.f;
+                if (px == 15) t2 = 0.f;
+                op[(tw * 16 + j) * kPlane] = fmaxf((t0 + __uint_as_float(r1[j])) + t2 + sb[96 + tw * 16 + j], 0.f);
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    HEAD_TRACE(3);
+    head_conv<16, 8, 3, true, 16>(out2, out3, w.head.w3, sb + 144, wbuf);          // 16 -> 8
+    HEAD_TRACE(4);
+    head_conv<8, 4, 3, true, 8>(out3, out4, w.head.w4, sb + 168, wbuf);            // 8 -> 4
+    head_finish(a, w, trk, out4, sb, maps, red, tbase);
+}
+
 int launch_head(const HeadArgs& a, const ModelW& w, cudaStream_t st) {
     if (a.n <= 0) return 0;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(head_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmemBytes) != cudaSuccess) return -1;
-        if (cudaFuncSetAttribute(head_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadTcSmemBytes) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmemBytes) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadTcSmemBytes) != cudaSuccess) return -1;
         configured = true;
     }
-    if (a.use_tc) head_kernel<true><<<a.n, kHeadThreads, kHeadTcSmemBytes, st>>>(a, w);
-    else head_kernel<false><<<a.n, kHeadThreads, kHeadSmemBytes, st>>>(a, w);
+    if (a.use_tc) head_tc_kernel<<<a.n, kHeadThreads, kHeadTcSmemBytes, st>>>(a, w);
+    else head_kernel<<<a.n, kHeadThreads, kHeadSmemBytes, st>>>(a, w);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
