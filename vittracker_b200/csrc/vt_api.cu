@@ -231,7 +231,7 @@ int vt_create(const VtConfig* cfg, VtHandle* out) {
     auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
     A((void**)&h->d_scratch, ch * stem_scratch_floats(kSx) * sizeof(float));
     if (cfg->blocks_impl == VT_BLOCKS_TCGEN05) {
-        const size_t pb = ch * (tc_planes_bytes(kConv3Cch, kConv3Wout) + tc_planes_bytes(kConv4Cch, kConv4Wout));
+        const size_t pb = ch * tc_planes_bytes_per_track();
         A((void**)&h->d_planes, pb);
         if (e == cudaSuccess) e = cudaMemset(h->d_planes, 0, pb);
     }
@@ -319,11 +319,11 @@ int vt_finalize_weights(VtHandle h, void* stream) {
         }
     }
     // ---- stem conv3 / conv4 for the tensor cores: fp16 hi | lo weight blobs in the kernels' K-step order (vt_stem_tc.cu)
-    size_t stc_w[2], stc_b[2];
+    size_t stc_w[3], stc_b[3];
     {
-        const int lcin[2] = {12, 24}, lcch[2] = {kConv3Cch, kConv4Cch}, lcout[2] = {24, 48}, lnpad[2] = {32, 48};
-        for (int i = 0; i < 2; ++i) {
-            const int l = 2 + i;
+        const int lcin[3] = {6, 12, 24}, lcch[3] = {kConv2Cch, kConv3Cch, kConv4Cch}, lcout[3] = {12, 24, 48}, lnpad[3] = {16, 32, 48};
+        for (int i = 0; i < 3; ++i) {
+            const int l = 1 + i;
             const size_t bytes = stem_tc_weight_bytes(i);
             stc_w[i] = slot(bytes / 4);
             stc_b[i] = slot(lnpad[i]);
@@ -513,7 +513,7 @@ int vt_finalize_weights(VtHandle h, void* stream) {
     m.head.w5 = base + hw[4]; m.head.b5 = base + hb[4];
     m.head_tc_w1 = reinterpret_cast<const uint8_t*>(base + o_htc);
     m.head_tc_w2 = reinterpret_cast<const uint8_t*>(base + o_htc2);
-    for (int i = 0; i < 2; ++i) { m.stem_tc_w[i] = reinterpret_cast<const uint8_t*>(base + stc_w[i]); m.stem_tc_b[i] = base + stc_b[i]; }
+    for (int i = 0; i < 3; ++i) { m.stem_tc_w[i] = reinterpret_cast<const uint8_t*>(base + stc_w[i]); m.stem_tc_b[i] = base + stc_b[i]; }
     m.hann = base + o_hann; m.lut = base + o_lut;
     h->finalized = true;
     return VT_OK;

@@ -61,8 +61,8 @@ struct ModelW {
     const float *norm_g, *norm_b;
     const float *pos_z, *pos_x;    // [64][48], [256][48]
     HeadW head;
-    const uint8_t* stem_tc_w[2];   // stem conv3 / conv4 for tcgen05 (vt_stem_tc.cu): fp16 hi | lo, K-major chunks, T_A taps then T_B taps
-    const float* stem_tc_b[2];     // biases padded to the MMA N
+    const uint8_t* stem_tc_w[3];   // stem conv2 / conv3 / conv4 for tcgen05 (vt_stem_tc.cu): fp16 hi | lo blobs in K-step order
+    const float* stem_tc_b[3];     // biases
     const uint8_t* head_tc_w1;     // head conv1 for tcgen05: 18 pieces (half h, kx, ky) x [hi | lo] x K-major [ci/8][48][8]
     const uint8_t* head_tc_w2;     // head conv2 for tcgen05: 9 blobs (tower, kx) x [hi | lo] x K-major [k/8][16][8], k = ky*32 + ci
     const float* hann;             // [256] fp32 window (lib/test/utils/hann.py)
@@ -77,6 +77,7 @@ __host__ __device__ constexpr size_t tc_planes_bytes(int cch, int wout) { return
 __host__ __device__ inline size_t tc_planes_offset(int prec, int gy, int gx, int chunk, int cch, int wout) {
     return ((((size_t)(prec * 4 + (gy & 1) * 2 + (gx & 1)) * cch + chunk) * (wout + 1) + (gy >> 1) + 1) * wout + (gx >> 1)) * 16;
 }
+constexpr int kConv2Cch = 1, kConv2Wout = 64;     // conv2 input:  6 channels -> 1 chunk, 128x128 -> planes of 65 x 64
 constexpr int kConv3Cch = 2, kConv3Wout = 32;     // conv3 input: 12 channels -> 2 chunks, 64x64 -> planes of 33 x 32
 constexpr int kConv4Cch = 3, kConv4Wout = 16;     // conv4 input: 24 channels -> 3 chunks, 32x32 -> planes of 17 x 16
 
@@ -89,12 +90,15 @@ int launch_crop_normalize(const uint8_t* frames, const int64_t* frame_offsets, c
 // Stem on `n` images of side S (128 or 256): in NCHW fp32 -> tokens[(b*tok_stride) + tok_off + t][48] (+pos).
 // scratch must hold n * stem_scratch_floats(S) floats and be zero-initialised once (the tensor-core path keeps zero rows in it).
 size_t stem_scratch_floats(int S);
-// planes (tensor-core path only): zero-initialised buffer of plane_tracks * (tc_planes_bytes(conv3) + tc_planes_bytes(conv4)) bytes
+// planes (tensor-core path only): zero-initialised buffer of plane_tracks * tc_planes_bytes_per_track() bytes
 int launch_stem(const float* img, int S, int n, const ModelW& w, float* scratch, float* tokens,
                 int tok_stride_rows, int tok_off, uint8_t* planes, int plane_tracks, cudaStream_t st);
 // Search-branch conv3 + conv4 on the tensor cores (a2: conv2 output [n][12][64][64]; a3: scratch for conv3 output)
-int launch_stem34_tc(const uint8_t* planes3, int n, const ModelW& w, uint8_t* planes4, float* tokens, int tok_stride_rows,
-                     int tok_off, cudaStream_t st);
+int launch_stem234_tc(const uint8_t* planes2, int n, const ModelW& w, uint8_t* planes3, uint8_t* planes4, float* tokens,
+                      int tok_stride_rows, int tok_off, cudaStream_t st);
+__host__ __device__ constexpr size_t tc_planes_bytes_per_track() {
+    return tc_planes_bytes(kConv2Cch, kConv2Wout) + tc_planes_bytes(kConv3Cch, kConv3Wout) + tc_planes_bytes(kConv4Cch, kConv4Wout);
+}
 size_t stem_tc_weight_bytes(int layer);
 void stem_tc_pack_weights(int cin, int cch, int cout, int npad, const float* wf, uint8_t* hi8, uint8_t* lo8,
                           void (*split)(float, uint16_t*, uint16_t*));

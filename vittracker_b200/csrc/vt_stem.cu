@@ -236,7 +236,7 @@ constexpr int kCc1Threads = Conv1Cfg::kThreads;                         // 256
 constexpr int kCc1TileSide = 2 * 32 + 1;                                // 65 resized-crop pixels per side
 constexpr size_t kCc1SmemBytes = Conv1Cfg::kSmemBytes + 64 + 2 * 80 * sizeof(int4);     // 4 CTAs / SM
 
-template <int S>
+template <int S, int TCOUT_CCH>
 __global__ void __launch_bounds__(kCc1Threads)
 crop_conv1_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict__ frame_offsets,
                   const int32_t* __restrict__ frame_hw, const double* __restrict__ boxes, double factor,
@@ -336,7 +336,7 @@ crop_conv1_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict_
     }
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncthreads();
-    conv_compute<3, 6, 6, 4, 32, 32, true, false>(tile, ws, bs, tx0, ty0, Hout, Hout, item, out, nullptr, 0, 0);
+    conv_compute<3, 6, 6, 4, 32, 32, true, false, TCOUT_CCH>(tile, ws, bs, tx0, ty0, Hout, Hout, item, out, nullptr, 0, 0);
 }
 
 template <int CIN, int COUT, int QG, int P, int TW, int TH, bool HSWISH, bool TOKENS, int TCOUT_CCH = 0>
@@ -369,10 +369,10 @@ size_t stem_scratch_floats(int S) {
     return (size_t)6 * (S / 2) * (S / 2) + (size_t)12 * (S / 4) * (S / 4) + (size_t)24 * (S / 8) * (S / 8);
 }
 
-template <int S>
+template <int S, int TCOUT_CCH>
 static int run_crop_conv1(const uint8_t* frames, const int64_t* frame_offsets, const int32_t* frame_hw, const double* boxes,
                           double factor, int n, const ModelW& w, float* out, int32_t* out_status, cudaStream_t st) {
-    auto kern = crop_conv1_kernel<S>;
+    auto kern = crop_conv1_kernel<S, TCOUT_CCH>;
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCc1SmemBytes) != cudaSuccess) return -1;
@@ -383,7 +383,9 @@ static int run_crop_conv1(const uint8_t* frames, const int64_t* frame_offsets, c
     for (int first = 0; first < n; first += 32768) {
         const int m = min(32768, n - first);
         kern<<<dim3(tiles, m), kCc1Threads, kCc1SmemBytes, st>>>(frames, frame_offsets + first, frame_hw + 2 * first, boxes + 4 * first, factor,
-                                                                 w.lut, w.stem[0].w, w.stem[0].b, out + (size_t)first * 6 * (S / 2) * (S / 2),
+                                                                 w.lut, w.stem[0].w, w.stem[0].b,
+                                                                 TCOUT_CCH > 0 ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(out) + (size_t)first * tc_planes_bytes(TCOUT_CCH, S / 4))
+                                                                               : out + (size_t)first * 6 * (S / 2) * (S / 2),
                                                                  out_status ? out_status + first : nullptr);
         ++launched;
     }
@@ -400,20 +402,21 @@ int launch_crop_stem(const uint8_t* frames, const int64_t* frame_offsets, const 
     float* a3 = a2 + (size_t)n * 12 * (S / 4) * (S / 4);
     const float* pos = (S == kSx) ? w.pos_x : w.pos_z;
     int total = 0, r;
-    if (S == 256) r = run_crop_conv1<256>(frames, frame_offsets, frame_hw, boxes, factor, n, w, a1, out_status, st);
-    else if (S == 128) r = run_crop_conv1<128>(frames, frame_offsets, frame_hw, boxes, factor, n, w, a1, out_status, st);
+    if (planes && S == kSx && n <= plane_tracks) {
+        // search branch: conv1 writes conv2's tensor-core operand image; layers 2-4 run on tcgen05
+        uint8_t* planes2 = planes;
+        uint8_t* planes3 = planes2 + (size_t)plane_tracks * tc_planes_bytes(kConv2Cch, kConv2Wout);
+        uint8_t* planes4 = planes3 + (size_t)plane_tracks * tc_planes_bytes(kConv3Cch, kConv3Wout);
+        if ((r = run_crop_conv1<256, kConv2Cch>(frames, frame_offsets, frame_hw, boxes, factor, n, w, reinterpret_cast<float*>(planes2), out_status, st)) < 0) return r;
+        total += r;
+        if ((r = launch_stem234_tc(planes2, n, w, planes3, planes4, tokens, tok_stride_rows, tok_off, st)) < 0) return r;
+        return total + r;
+    }
+    if (S == 256) r = run_crop_conv1<256, 0>(frames, frame_offsets, frame_hw, boxes, factor, n, w, a1, out_status, st);
+    else if (S == 128) r = run_crop_conv1<128, 0>(frames, frame_offsets, frame_hw, boxes, factor, n, w, a1, out_status, st);
     else return -1;
     if (r < 0) return r;
     total += r;
-    if (planes && S == kSx && n <= plane_tracks) {
-        // search branch: conv2 writes conv3's tensor-core operand image, layers 3 and 4 run on tcgen05
-        uint8_t* planes3 = planes;
-        uint8_t* planes4 = planes + (size_t)plane_tracks * tc_planes_bytes(kConv3Cch, kConv3Wout);
-        if ((r = run_conv<6, 12, 12, 2, 32, 16, true, false, kConv3Cch>(a1, S / 2, n, w.stem[1], reinterpret_cast<float*>(planes3), nullptr, 0, 0, st)) < 0) return r;
-        total += r;
-        if ((r = launch_stem34_tc(planes3, n, w, planes4, tokens, tok_stride_rows, tok_off, st)) < 0) return r;
-        return total + r;
-    }
     if ((r = run_conv<6, 12, 12, 2, 32, 16, true, false>(a1, S / 2, n, w.stem[1], a2, nullptr, 0, 0, st)) < 0) return r;
     total += r;
     if ((r = run_conv<12, 24, 12, 2, 32, 8, true, false>(a2, S / 4, n, w.stem[2], a3, nullptr, 0, 0, st)) < 0) return r;
@@ -432,17 +435,18 @@ int launch_stem(const float* img, int S, int n, const ModelW& w, float* scratch,
     const float* pos = (S == kSx) ? w.pos_x : w.pos_z;
     int total = 0, r;
     //                CIN COUT QG P  TW  TH  hswish tokens
-    if ((r = run_conv<3, 6, 6, 4, 32, 32, true, false>(img, S, n, w.stem[0], a1, nullptr, 0, 0, st)) < 0) return r;
-    total += r;
     if (planes && S == kSx && n <= plane_tracks) {
-        // search branch: conv2 writes conv3's tensor-core operand image, layers 3 and 4 run on tcgen05
-        uint8_t* planes3 = planes;
-        uint8_t* planes4 = planes + (size_t)plane_tracks * tc_planes_bytes(kConv3Cch, kConv3Wout);
-        if ((r = run_conv<6, 12, 12, 2, 32, 16, true, false, kConv3Cch>(a1, S / 2, n, w.stem[1], reinterpret_cast<float*>(planes3), nullptr, 0, 0, st)) < 0) return r;
+        // search branch: conv1 writes conv2's tensor-core operand image; layers 2-4 run on tcgen05
+        uint8_t* planes2 = planes;
+        uint8_t* planes3 = planes2 + (size_t)plane_tracks * tc_planes_bytes(kConv2Cch, kConv2Wout);
+        uint8_t* planes4 = planes3 + (size_t)plane_tracks * tc_planes_bytes(kConv3Cch, kConv3Wout);
+        if ((r = run_conv<3, 6, 6, 4, 32, 32, true, false, kConv2Cch>(img, S, n, w.stem[0], reinterpret_cast<float*>(planes2), nullptr, 0, 0, st)) < 0) return r;
         total += r;
-        if ((r = launch_stem34_tc(planes3, n, w, planes4, tokens, tok_stride_rows, tok_off, st)) < 0) return r;
+        if ((r = launch_stem234_tc(planes2, n, w, planes3, planes4, tokens, tok_stride_rows, tok_off, st)) < 0) return r;
         return total + r;
     }
+    if ((r = run_conv<3, 6, 6, 4, 32, 32, true, false>(img, S, n, w.stem[0], a1, nullptr, 0, 0, st)) < 0) return r;
+    total += r;
     if ((r = run_conv<6, 12, 12, 2, 32, 16, true, false>(a1, S / 2, n, w.stem[1], a2, nullptr, 0, 0, st)) < 0) return r;
     total += r;
     if ((r = run_conv<12, 24, 12, 2, 32, 8, true, false>(a2, S / 4, n, w.stem[2], a3, nullptr, 0, 0, st)) < 0) return r;

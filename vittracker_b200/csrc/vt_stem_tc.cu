@@ -1,4 +1,4 @@
-// Stem layers 3 and 4 (conv3x3 stride 2 pad 1 + folded BN [+ Hardswish], lib/models/vit_dist/vit_dist.py:36-54)
+// Stem layers 2, 3 and 4 (conv3x3 stride 2 pad 1 + folded BN [+ Hardswish], lib/models/vit_dist/vit_dist.py:36-54)
 // on the tcgen05 tensor cores, for the search branch (S = 256).
 //
 // A stride-2 convolution reads in[2oy+ky-1][2ox+kx-1].  Its input arrives as a "plane image" (vt_internal.h,
@@ -8,8 +8,8 @@
 // UMMA descriptor addresses tap (ky, kx) by picking the plane (rp = ky odd ? 0 : 1, cp = kx odd ? 0 : 1) and
 // a start row, and staging a band of 8 output rows is a handful of cp.async.bulk copies - no instructions.
 // The kx = 0 taps need column index ox-1: they accumulate UNSHIFTED into a second TMEM accumulator T_B that
-// the epilogue shifts by one TMEM lane with a warp shuffle (a warp's 32 lanes are whole image rows; the value
-// entering at ox = 0 is the zero padding).  Products are hi*hi + lo*hi + hi*lo, fp32 accumulation.
+// the epilogue shifts by one TMEM lane with a warp shuffle (a warp's 32 lanes are whole image rows - or, at W_out = 64,
+// half a row, the value crossing the middle going through shared memory; the value entering at ox = 0 is the zero padding).  Products are hi*hi + lo*hi + hi*lo, fp32 accumulation.
 #include <string.h>
 
 #include "vt_internal.h"
@@ -124,8 +124,8 @@ conv_s2_tc_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wt
         mbar_wait(bar_w, 0);
         mbar_wait(bar_a, 0);
         tc_fence_after();
-#pragma unroll
-        for (int tile = 0; tile < K::kTiles; ++tile) {
+#pragma unroll 1
+        for (int tile = 0; tile < K::kTiles; ++tile) {          // rolled: the descriptors are affine in `tile`
 #pragma unroll
             for (int acc = 0; acc < 2; ++acc) {                             // 0: T_A (kx = 1, 2)   1: T_B (kx = 0, shifted later)
                 const uint32_t d = tbase + (tile * 2 + acc) * NPAD;
@@ -139,7 +139,8 @@ conv_s2_tc_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wt
                     tcs_tap(acc, tap1, ky, kx); tcs_tap_pos(ky, kx, p1, r1);
                     const uint32_t a0 = (p0 * CCH + ch0) * K::kChunkBytes + (tile * K::kRowsPerTile + r0) * WOUT * 16;
                     const uint32_t a1 = (p1 * CCH + ch1) * K::kChunkBytes + (tile * K::kRowsPerTile + r1) * WOUT * 16;
-                    const uint32_t lbo = zero1 ? K::kChunkBytes : a1 - a0;  // > 0 by construction of the schedule (zero weights: any finite data)
+                    const uint32_t lbo = zero1 ? 16 : a1 - a0;              // > 0 by construction of the schedule; zero weights: any finite data
+                                                                            // inside the CTA's shared memory (one pixel further: at most 16 bytes into the next region)
                     const uint64_t ah = smem_desc(sbase + K::kOffA + a0, lbo, 128);
                     const uint64_t al = smem_desc(sbase + K::kOffA + K::kABytes + a0, lbo, 128);
                     const uint32_t boff = ((acc == 0 ? 0 : K::kStepsA) + s) * 2 * NPAD * 16;
@@ -156,47 +157,66 @@ conv_s2_tc_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wt
     mbar_wait(bar_d, 0);
     tc_fence_after();
 
-    // ---- epilogue: thread -> (tile, pixel) [and a channel half when the CTA has one tile] -----------------------
+    // ---- epilogue: 8 warps = 2 (tile or channel half) x 4 TMEM lane quarters; thread -> one output pixel ------------------
     {
-        constexpr int kChPerThread = (K::kTiles == 2) ? NPAD : NPAD / 2;
-        static_assert(kChPerThread % 8 == 0, "channel split");
-        const int tile = (K::kTiles == 2) ? (warp >> 2) : 0;
-        const int chb = (K::kTiles == 2) ? 0 : (warp >> 2) * kChPerThread;
-        const int r = 32 * (warp & 3) + lane;                               // row of the M tile = TMEM lane
-        const int oy = oy0 + tile * K::kRowsPerTile + r / WOUT, ox = r % WOUT;
-        const uint32_t ta = tbase + ((uint32_t)(32 * (warp & 3)) << 16) + tile * 2 * NPAD + chb;
+        constexpr int kPasses = (K::kTiles >= 2) ? K::kTiles / 2 : 1;           // two tiles per pass, or one tile split by channels
+        constexpr int kChPerThread = (K::kTiles >= 2) ? NPAD : NPAD / 2;
+        static_assert(kChPerThread % 8 == 0 && (K::kTiles == 1 || K::kTiles % 2 == 0), "epilogue split");
+        constexpr bool kSplitRows = WOUT > 32;                                  // TMEM lane quarter (= warp) shorter than an image row
+        static_assert(!kSplitRows || (WOUT == 64 && K::kTiles >= 2), "row split");
+        __shared__ float s_xchg[kSplitRows ? kPasses * (kChPerThread / 8) : 1][2][2][8];
+        const int chb = (K::kTiles >= 2) ? 0 : (warp >> 2) * kChPerThread;
+        const int r = 32 * (warp & 3) + lane;                                   // row of the M tile = TMEM lane
 #pragma unroll 1
-        for (int c0 = 0; c0 < kChPerThread; c0 += 8) {
-            uint32_t ra[8], rb[8];
-            tmem_ld8(ta + c0, ra);
-            tmem_ld8(ta + NPAD + c0, rb);
-            tc_wait_ld();
-            float v[8];
+        for (int pass = 0; pass < kPasses; ++pass) {
+            const int tile = (K::kTiles >= 2) ? 2 * pass + (warp >> 2) : 0;
+            const int oy = oy0 + tile * K::kRowsPerTile + r / WOUT, ox = r % WOUT;
+            const uint32_t ta = tbase + ((uint32_t)(32 * (warp & 3)) << 16) + tile * 2 * NPAD + chb;
+#pragma unroll 1
+            for (int c0 = 0; c0 < kChPerThread; c0 += 8) {
+                uint32_t ra[8], rb[8];
+                tmem_ld8(ta + c0, ra);
+                tmem_ld8(ta + NPAD + c0, rb);
+                tc_wait_ld();
+                if constexpr (kSplitRows) {
+                    // an image row spans two warps: column 31's T_B crosses to column 32 through shared memory
+                    float* xs = s_xchg[pass * (kChPerThread / 8) + c0 / 8][warp >> 2][(warp & 3) >> 1];
+                    if (lane == 31 && !(warp & 1)) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float tb = __shfl_up_sync(0xffffffffu, __uint_as_float(rb[j]), 1);     // T_B[oy][ox-1]
-                if (ox == 0) tb = 0.f;
-                float t = __uint_as_float(ra[j]) + tb + sBias[chb + c0 + j];
-                if (HSWISH) t = t * fminf(fmaxf(t + 3.f, 0.f), 6.f) / 6.f;
-                v[j] = t;
-            }
-            if (chb + c0 >= COUT) continue;                                 // padding channels
-            if (OUT_PLANES) {
-                // this layer's output pixel (oy, ox) is the next layer's input pixel: 8 channels = one chunk, hi | lo
-                uint32_t hi[4], lo[4];
+                        for (int j = 0; j < 8; ++j) xs[j] = __uint_as_float(rb[j]);
+                    }
+                    __syncthreads();
+                }
+                float v[8];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) split_pack2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
-                uint8_t* ob = reinterpret_cast<uint8_t*>(outp) + (size_t)b * tc_planes_bytes(NEXT_CCH, WOUT / 2);
-                const int chunk = (chb + c0) / 8;
-                *reinterpret_cast<uint4*>(ob + tc_planes_offset(0, oy, ox, chunk, NEXT_CCH, WOUT / 2)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4*>(ob + tc_planes_offset(1, oy, ox, chunk, NEXT_CCH, WOUT / 2)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            } else {
-                const int tok = oy * WOUT + ox;
-                float* o = reinterpret_cast<float*>(outp) + ((size_t)b * tok_stride_rows + tok_off + tok) * COUT + chb + c0;
-                const float* pe = pos + (size_t)tok * COUT + chb + c0;
-                const float4 e0 = __ldg(reinterpret_cast<const float4*>(pe)), e1 = __ldg(reinterpret_cast<const float4*>(pe + 4));
-                *reinterpret_cast<float4*>(o) = make_float4(v[0] + e0.x, v[1] + e0.y, v[2] + e0.z, v[3] + e0.w);
-                *reinterpret_cast<float4*>(o + 4) = make_float4(v[4] + e1.x, v[5] + e1.y, v[6] + e1.z, v[7] + e1.w);
+                for (int j = 0; j < 8; ++j) {
+                    float tb = __shfl_up_sync(0xffffffffu, __uint_as_float(rb[j]), 1);     // T_B[oy][ox-1]
+                    if constexpr (kSplitRows) {
+                        if (lane == 0 && (warp & 1)) tb = s_xchg[pass * (kChPerThread / 8) + c0 / 8][warp >> 2][(warp & 3) >> 1][j];
+                    }
+                    if (ox == 0) tb = 0.f;
+                    float t = __uint_as_float(ra[j]) + tb + sBias[chb + c0 + j];
+                    if (HSWISH) t = t * fminf(fmaxf(t + 3.f, 0.f), 6.f) / 6.f;
+                    v[j] = (chb + c0 + j < COUT) ? t : 0.f;                         // padding channels stay exactly zero
+                }
+                if (chb + c0 >= COUT) continue;
+                if (OUT_PLANES) {
+                    // this layer's output pixel (oy, ox) is the next layer's input pixel: 8 channels = one chunk, hi | lo
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) split_pack2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+                    uint8_t* ob = reinterpret_cast<uint8_t*>(outp) + (size_t)b * tc_planes_bytes(NEXT_CCH, WOUT / 2);
+                    const int chunk = (chb + c0) / 8;
+                    *reinterpret_cast<uint4*>(ob + tc_planes_offset(0, oy, ox, chunk, NEXT_CCH, WOUT / 2)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(ob + tc_planes_offset(1, oy, ox, chunk, NEXT_CCH, WOUT / 2)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                } else {
+                    const int tok = oy * WOUT + ox;
+                    float* o = reinterpret_cast<float*>(outp) + ((size_t)b * tok_stride_rows + tok_off + tok) * COUT + chb + c0;
+                    const float* pe = pos + (size_t)tok * COUT + chb + c0;
+                    const float4 e0 = __ldg(reinterpret_cast<const float4*>(pe)), e1 = __ldg(reinterpret_cast<const float4*>(pe + 4));
+                    *reinterpret_cast<float4*>(o) = make_float4(v[0] + e0.x, v[1] + e0.y, v[2] + e0.z, v[3] + e0.w);
+                    *reinterpret_cast<float4*>(o + 4) = make_float4(v[4] + e1.x, v[5] + e1.y, v[6] + e1.z, v[7] + e1.w);
+                }
             }
         }
     }
@@ -226,22 +246,27 @@ static int run_tc_conv(const uint8_t* in, int n, const uint8_t* wt, const float*
     return cudaGetLastError() == cudaSuccess ? launched : -1;
 }
 
-// conv3 (12 -> 24, 64x64 -> 32x32, Hardswish) and conv4 (24 -> 48, 32x32 -> 16x16, tokens + pos-embed) of the search branch
-int launch_stem34_tc(const uint8_t* planes3, int n, const ModelW& w, uint8_t* planes4, float* tokens, int tok_stride_rows,
-                     int tok_off, cudaStream_t st) {
+// Search-branch layers on the tensor cores: conv2 (6 -> 12, 128x128 -> 64x64), conv3 (12 -> 24, -> 32x32), both with
+// Hardswish and writing the next layer's operand image, and conv4 (24 -> 48, -> 16x16) writing tokens + pos-embed.
+int launch_stem234_tc(const uint8_t* planes2, int n, const ModelW& w, uint8_t* planes3, uint8_t* planes4, float* tokens,
+                      int tok_stride_rows, int tok_off, cudaStream_t st) {
     int total = 0, r;
-    if ((r = run_tc_conv<kConv3Cch, 24, 32, kConv3Wout, true, true, kConv4Cch>(planes3, n, w.stem_tc_w[0], w.stem_tc_b[0], planes4,
+    if ((r = run_tc_conv<kConv2Cch, 12, 16, kConv2Wout, true, true, kConv3Cch>(planes2, n, w.stem_tc_w[0], w.stem_tc_b[0], planes3,
+                                                                               tc_planes_bytes(kConv3Cch, kConv3Wout), nullptr, 0, 0, st)) < 0) return r;
+    total += r;
+    if ((r = run_tc_conv<kConv3Cch, 24, 32, kConv3Wout, true, true, kConv4Cch>(planes3, n, w.stem_tc_w[1], w.stem_tc_b[1], planes4,
                                                                                tc_planes_bytes(kConv4Cch, kConv4Wout), nullptr, 0, 0, st)) < 0) return r;
     total += r;
-    if ((r = run_tc_conv<kConv4Cch, 48, 48, kConv4Wout, false, false, 1>(planes4, n, w.stem_tc_w[1], w.stem_tc_b[1], tokens,
+    if ((r = run_tc_conv<kConv4Cch, 48, 48, kConv4Wout, false, false, 1>(planes4, n, w.stem_tc_w[2], w.stem_tc_b[2], tokens,
                                                                           (size_t)tok_stride_rows * 48 * sizeof(float), w.pos_x,
                                                                           tok_stride_rows, tok_off, st)) < 0) return r;
     total += r;
     return total;
 }
 
-size_t stem_tc_weight_bytes(int layer) {      // layer 0: conv3, 1: conv4
-    return layer == 0 ? (size_t)TcConv<kConv3Cch, 24, 32, kConv3Wout>::kWBytes : (size_t)TcConv<kConv4Cch, 48, 48, kConv4Wout>::kWBytes;
+size_t stem_tc_weight_bytes(int layer) {      // layer 0: conv2, 1: conv3, 2: conv4
+    return layer == 0 ? (size_t)TcConv<kConv2Cch, 12, 16, kConv2Wout>::kWBytes
+           : layer == 1 ? (size_t)TcConv<kConv3Cch, 24, 32, kConv3Wout>::kWBytes : (size_t)TcConv<kConv4Cch, 48, 48, kConv4Wout>::kWBytes;
 }
 
 // Host side of the K-step schedule: weight blob of one layer (fp16 hi | lo), `wf` = folded weights [ci][ky][kx][cout].
