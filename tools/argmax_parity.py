@@ -1,0 +1,107 @@
+#!/usr/bin/env python
+"""North-star parity gate: bit-exact Hann-weighted arg-max against the reference algorithm on N synthetic
+frames (default 10240), ties excepted (oracle top-1 - top-2 < 1e-5).
+
+    python tools/argmax_parity.py [--n 10240] [--blocks tcgen05|simt] [--out gpurun_out/argmax_parity.json]
+
+The CUDA path runs through the batched C-ABI entry points (vt_tracks_init / vt_tracks_step); the checker is the
+CPU oracle (cv2 crop + torch fp32 forward, batched by 32 - test infrastructure, never on the product path)."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+TIE_GAP = 1e-5
+ABS_TOL, REL_TOL = 1e-2, 1e-3
+
+
+def oracle_open_loop(sd, frames, fidx_init, fidx_step, init_boxes, step_boxes, group=32):
+    """Per track: arg-max of window * score, top-1 - top-2 gap, decoded state, confidence."""
+    from oracle import vt_oracle as O
+    model = O.OracleModel(sd)
+    win = O.hann2d(16, 16)
+    H, W = frames.shape[1:3]
+    n = len(init_boxes)
+    arg = np.zeros(n, dtype=np.int64)
+    gap = np.zeros(n)
+    conf = np.zeros(n)
+    states = np.zeros((n, 4))
+    for g0 in range(0, n, group):
+        idx = range(g0, min(n, g0 + group))
+        zs, xs, rfs = [], [], []
+        for i in idx:
+            zs.append(O.preprocess(O.sample_target_cv(frames[fidx_init[i]], list(init_boxes[i]), 2.0, 128)[0]))
+            xp, rf, _ = O.sample_target_cv(frames[fidx_step[i]], list(step_boxes[i]), 4.0, 256)
+            xs.append(O.preprocess(xp)); rfs.append(rf)
+        out = model.forward(torch.cat(zs), torch.cat(xs))
+        resp = (win * out["score_map"]).flatten(1)
+        top = torch.topk(resp, 2, dim=1).values
+        pb = model.cal_bbox(resp.view(-1, 1, 16, 16), out["size_map"], out["offset_map"])
+        for k, i in enumerate(idx):
+            arg[i] = int(resp[k].argmax())
+            gap[i] = float(top[k, 0] - top[k, 1])
+            conf[i] = float(out["score_map"][k].max())
+            pred = (pb[k] * 256 / rfs[k]).tolist()
+            states[i] = O.clip_box(O.map_box_back(list(step_boxes[i]), pred, rfs[k]), H, W, margin=10)
+    return arg, gap, conf, states
+
+
+def run(n=10240, blocks="tcgen05", H=360, W=640, F=8, seed=0, chunk=1024):
+    from oracle import vt_oracle as O
+    from vittracker_b200 import BatchedTracker, FramePool, load_cfg
+    cfg = load_cfg()
+    sd = O.make_state_dict(seed=11 + seed, stress=True)
+    # half smooth (natural-image-like taps), half white-noise frames
+    frames = np.concatenate([O.synth_frames(F // 2, H, W, seed=81 + seed, smooth=True), O.synth_frames(F - F // 2, H, W, seed=82 + seed)])
+    init_boxes = O.synth_boxes(n, H, W, seed=83 + seed)
+    step_boxes = O.synth_boxes(n, H, W, seed=84 + seed)
+    fi = np.arange(n) % F
+    fs = (np.arange(n) * 7 + 3) % F
+    bt = BatchedTracker(cfg, sd, max_tracks=n, chunk_tracks=min(chunk, n), blocks_impl=blocks)
+    pool = FramePool(frames, bt.device)
+    st = bt.initialize(pool, torch.from_numpy(fi), init_boxes)
+    assert int(st.abs().sum()) == 0
+    bt.set_state(step_boxes)
+    out, det = bt.track(pool, torch.from_numpy(fs), update_state=True, detail=True)
+    out, det = out.cpu().numpy(), det.cpu().numpy()
+    t0 = time.perf_counter()
+    arg, gap, conf, states = oracle_open_loop(sd, frames, fi, fs, init_boxes, step_boxes)
+    oracle_s = time.perf_counter() - t0
+    got = det[:, 5].astype(np.int64)
+    tie = gap < TIE_GAP
+    flip = (got != arg) & ~tie
+    ok = ~tie & ~flip
+    box_err = np.abs(out[ok, :4] - states[ok])
+    box_bad = int(np.sum(np.any(box_err > ABS_TOL + REL_TOL * np.abs(states[ok]), axis=1)))
+    return {"frames": int(n), "blocks_impl": blocks, "ties_excluded": int(tie.sum()), "argmax_flips": int(flip.sum()),
+            "flips_among_ties": int(((got != arg) & tie).sum()), "min_gap_of_compared": float(gap[~tie].min()),
+            "boxes_outside_tolerance": box_bad, "max_box_abs_err": float(box_err.max()),
+            "max_conf_abs_err": float(np.abs(out[ok, 4] - conf[ok]).max()), "oracle_seconds": round(oracle_s, 1),
+            "frame_hw": [H, W], "tolerance": {"abs": ABS_TOL, "rel": REL_TOL, "tie_gap": TIE_GAP}}
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=10240)
+    ap.add_argument("--blocks", default="tcgen05", choices=["tcgen05", "simt"])
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+    torch.set_num_threads(os.cpu_count() or 1)
+    res = run(a.n, a.blocks, seed=a.seed)
+    print(json.dumps(res))
+    if a.out:
+        os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
+        with open(a.out, "w") as f:
+            json.dump(res, f, indent=1)
+    sys.exit(0 if res["argmax_flips"] == 0 and res["boxes_outside_tolerance"] == 0 else 1)
