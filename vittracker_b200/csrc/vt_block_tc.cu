@@ -13,10 +13,10 @@
 //     accumulator), which keeps ~22 mantissa bits on the operands: single-pass fp16/bf16/TF32
 //     inputs flip the Hann-weighted arg-max the tracker depends on;
 //   - softmax row statistics are thread-local (one row per TMEM lane); the 48 / 192 / 320 columns of
-//     a row are shared by three warps (column thirds) that exchange partial sums through smem.
-// Warp roles: warps 0-11 = epilogue (lane quarter = warp % 4, column third = warp / 4),
-// warp 12 = control (bulk weight loads + single-thread MMA issue).  Control and epilogue ping-pong
-// through two mbarriers (`go`: operands ready, 12 warp arrivals; `done`: tcgen05.commit).
+//     a row are shared by kNS warps (column groups) that exchange partial sums through smem.
+// Warp roles: warps 0 .. 4 kNS - 1 = epilogue (lane quarter = warp % 4, column group = warp / 4),
+// the last warp = control (bulk weight loads + single-thread MMA issue).  Control and epilogue ping-pong
+// through two mbarriers (`go`: operands ready, one arrival per epilogue warp; `done`: tcgen05.commit).
 //
 // Algorithmic work per track: 112.07 MFLOP; issued MMA work is 3x that (split) x 1.2
 // (padding of the third tile).
@@ -41,8 +41,19 @@ __device__ int g_tc_trace_n[2];
 
 namespace {
 
-constexpr int kTcThreads = 13 * 32;
-constexpr int kEpiThreads = 12 * 32;
+// Epilogue warps: lane quarter = warp % 4 (TMEM lanes 32q .. 32q+31 = token rows), column group = warp / 4.
+// kNS column groups share the columns of a row; more groups = more warps in flight to hide TMEM / MUFU latency.
+#ifndef VT_TC_NS
+#define VT_TC_NS 6
+#endif
+constexpr int kNS = VT_TC_NS;                  // 3 or 6
+constexpr int kEpiWarps = 4 * kNS;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kTcThreads = kEpiThreads + 32;   // + the control warp
+constexpr int kCW = kC / kNS;                  // residual / LayerNorm columns per thread (16 or 8)
+constexpr int kQW = 3 * kC / kNS;              // QKV output columns per thread (48 or 24)
+constexpr int kHW = kHid / kNS;                // hidden columns per thread (64 or 32)
+static_assert(kNS == 3 || kNS == 6, "column groups");
 
 // ---- TMEM columns --------------------------------------------------------------------------------
 constexpr uint32_t kColBig = 0;        // [0,320): QKV out (2 buffers of 144 at 0 / 160), S -> P, fc1 out -> GELU operand
@@ -61,8 +72,8 @@ constexpr int kKBytes = kN * kC * 2;                      // 30720 per precision
 constexpr int kSmKhi = kSmX, kSmKlo = kSmX + kKBytes, kSmVhi = kSmX + 2 * kKBytes, kSmVlo = kSmX + 3 * kKBytes;
 constexpr int kSmW1hi = kSmX, kSmW1lo = kSmX + 18432, kSmW2hi = kSmX + 36864, kSmW2lo = kSmX + 55296;
 constexpr int kSmPar = kSmX + 4 * kKBytes;                // fp32 parameters of all blocks
-constexpr int kSmRed = kSmPar + kDepth * kTcParFloats * 4;   // 4 arrays x 3 thirds x 128 rows fp32
-constexpr int kSmBar = kSmRed + 4 * 3 * 128 * 4;          // mbarriers
+constexpr int kSmRed = kSmPar + kDepth * kTcParFloats * 4;   // 4 arrays x kNS column groups x 128 rows fp32
+constexpr int kSmBar = kSmRed + 4 * kNS * 128 * 4;        // mbarriers
 constexpr int kSmTmem = kSmBar + 12 * 8;
 constexpr int kTcSmemBytes = kSmTmem + 16;
 static_assert(kTcWbBytes <= 4 * kKBytes, "MLP weights overlay the K/V region");
@@ -76,8 +87,8 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"
 struct Epi {
     uint32_t tbase;        // TMEM base address
     uint32_t lane_addr;    // (32 * quarter) << 16
-    int q, s, lane, row;   // lane quarter, column third, lane, row inside the tile (32q + lane)
-    float* red;            // [4][3][128]
+    int q, s, lane, row;   // lane quarter, column group, lane, row inside the tile (32q + lane)
+    float* red;            // [4][kNS][128]
     uint64_t *mb_go, *mb_done;
     uint32_t done_ph;
 
@@ -108,35 +119,38 @@ struct Epi {
         if (threadIdx.x == 0) TC_TRACE(1);
     }
 
-    // sum over the 48 columns of a row (three thirds) of a per-thread partial; `arr` selects the scratch array
+    // sum over the 48 columns of a row (kNS column groups) of a per-thread partial; `arr` selects the scratch array
     __device__ __forceinline__ float row_sum(float partial, int arr) {
-        float* r = red + arr * 384;
+        float* r = red + arr * (kNS * 128);
         r[s * 128 + row] = partial;
         epi_bar();
-        return r[row] + r[128 + row] + r[256 + row];
+        float t = r[row];
+#pragma unroll
+        for (int g = 1; g < kNS; ++g) t += r[g * 128 + row];
+        return t;
     }
 
-    // LayerNorm statistics of a 48-wide row held as 3 x 16 values
-    __device__ __forceinline__ void ln16(const float (&v)[16], const float* g, const float* b, float (&y)[16]) {
+    // LayerNorm of a 48-wide row held as kNS x kCW values
+    __device__ __forceinline__ void ln(const float (&v)[kCW], const float* g, const float* b, float (&y)[kCW]) {
         float sum = 0.f;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) sum += v[i];
+        for (int i = 0; i < kCW; ++i) sum += v[i];
         const float mean = row_sum(sum, 0) * (1.f / 48.f);
         float var = 0.f;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { const float d = v[i] - mean; var = fmaf(d, d, var); }
+        for (int i = 0; i < kCW; ++i) { const float d = v[i] - mean; var = fmaf(d, d, var); }
         const float rstd = rsqrtf(row_sum(var, 1) * (1.f / 48.f) + kLnEps);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) y[i] = (v[i] - mean) * rstd * g[16 * s + i] + b[16 * s + i];
+        for (int i = 0; i < kCW; ++i) y[i] = (v[i] - mean) * rstd * g[kCW * s + i] + b[kCW * s + i];
     }
 
-    // write this thread's 16 K-elements [16s, 16s+16) of row `row` into A-operand slot t (hi cols 8s.., lo cols 24+8s..)
-    __device__ __forceinline__ void store_opa16(int t, const float (&y)[16]) {
-        uint32_t hi[8], lo[8];
+    // write this thread's K-elements [kCW s, kCW s + kCW) of row `row` into A-operand slot t (hi cols, then lo cols at +24)
+    __device__ __forceinline__ void store_opa(int t, const float (&y)[kCW]) {
+        uint32_t hi[kCW / 2], lo[kCW / 2];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) split_pack2(y[2 * j], y[2 * j + 1], hi[j], lo[j]);
-        tmem_st8(taddr(kColOpa + 48 * t + 8 * s), hi);
-        tmem_st8(taddr(kColOpa + 48 * t + 24 + 8 * s), lo);
+        for (int j = 0; j < kCW / 2; ++j) split_pack2(y[2 * j], y[2 * j + 1], hi[j], lo[j]);
+        tmem_st<kCW / 2>(taddr(kColOpa + 48 * t + (kCW / 2) * s), hi);
+        tmem_st<kCW / 2>(taddr(kColOpa + 48 * t + 24 + (kCW / 2) * s), lo);
     }
 };
 
@@ -180,20 +194,20 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
     uint64_t* mb_wb = mb_go + 3;
     uint64_t* mb_h = mb_go + 4;        // [2] fc1 output ready in H_A / H_B          (tcgen05.commit)
     uint64_t* mb_y = mb_go + 6;        // [2] fc2 output ready in Y_A / Y_B          (tcgen05.commit)
-    uint64_t* mb_g = mb_go + 8;        // [2] GELU operand written in H_A / H_B      (12 warp arrivals)
-    uint64_t* mb_yfree = mb_go + 10;   // Y_A has been read, may be overwritten      (12 warp arrivals)
+    uint64_t* mb_g = mb_go + 8;        // [2] GELU operand written in H_A / H_B      (one arrival per epilogue warp)
+    uint64_t* mb_yfree = mb_go + 10;   // Y_A has been read, may be overwritten      (one arrival per epilogue warp)
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kSmTmem);
 
-    if (warp == 12) tmem_alloc(s_tmem, 512);
+    if (warp == kEpiWarps) tmem_alloc(s_tmem, 512);
     if (tid == 0) {
-        mbar_init(mb_go, 12);
+        mbar_init(mb_go, kEpiWarps);
         mbar_init(mb_done, 1);
         mbar_init(mb_wa, 1);
         mbar_init(mb_wb, 1);
         mbar_init(mb_h, 1); mbar_init(mb_h + 1, 1);
         mbar_init(mb_y, 1); mbar_init(mb_y + 1, 1);
-        mbar_init(mb_g, 12); mbar_init(mb_g + 1, 12);
-        mbar_init(mb_yfree, 12);
+        mbar_init(mb_g, kEpiWarps); mbar_init(mb_g + 1, kEpiWarps);
+        mbar_init(mb_yfree, kEpiWarps);
         mbar_fence_init();
     }
     for (int i = tid; i < kDepth * kTcParFloats; i += kTcThreads) s_par[i] = __ldg(w.tc[i / kTcParFloats].par + i % kTcParFloats);
@@ -203,7 +217,7 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
     const uint32_t tbase = __shfl_sync(0xffffffffu, *s_tmem, 0);       // provably warp-uniform
     const uint32_t sbase = smem_u32(smem);
 
-    if (warp == 12) {
+    if (warp == kEpiWarps) {
         // =========================== control: weight loads + MMA issue (one thread) ===========================
         {   // the whole warp runs this program convergently; MMA / commit / bulk copy are done by one elected lane
             uint32_t go_ph = 0, wa_ph = 0, wb_ph = 0;
@@ -321,26 +335,32 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
         const float scale = 0.14433756729740643f;                 // 48 ** -0.5
         const float kLog2e = 1.4426950408889634f;
         uint32_t h_ph[2] = {0, 0}, y_ph[2] = {0, 0};
+        // softmax: the 20 groups of 16 score columns are dealt to the column groups (7,7,6 or 4,4,3,3,3,3)
+        constexpr int kSmBase = 20 / kNS, kSmRem = 20 % kNS;
+        const int sm_groups = kSmBase + (s < kSmRem ? 1 : 0);
+        const int sm_begin = 16 * (s * kSmBase + (s < kSmRem ? s : kSmRem));
+        // QKV epilogue: which of q / K / V this column group handles, and where inside its 48 columns
+        const int qkv_part = (s * kQW) / 48, qkv_off = (s * kQW) % 48;
 
         for (int trk = blockIdx.x; trk < n; trk += gridDim.x) {
-            // residual slice x[t][16]: tile t, row 128 t + row, columns [16 s, 16 s + 16)
-            float x[3][16];
+            // residual slice x[t][kCW]: tile t, row 128 t + row, columns [kCW s, kCW s + kCW)
+            float x[3][kCW];
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
                 const int r = 128 * t + row;
                 const float* src = nullptr;
-                if (r < kNz) src = tok_z + ((size_t)trk * z_stride_rows + r) * kC + 16 * s;
-                else if (r < kN) src = tok_x + ((size_t)trk * x_stride_rows + (r - kNz)) * kC + 16 * s;
+                if (r < kNz) src = tok_z + ((size_t)trk * z_stride_rows + r) * kC + kCW * s;
+                else if (r < kN) src = tok_x + ((size_t)trk * x_stride_rows + (r - kNz)) * kC + kCW * s;
 #pragma unroll
-                for (int i = 0; i < 16; i += 4) {
+                for (int i = 0; i < kCW; i += 4) {
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (src) v = __ldg(reinterpret_cast<const float4*>(src + i));
                     x[t][i] = v.x; x[t][i + 1] = v.y; x[t][i + 2] = v.z; x[t][i + 3] = v.w;
                 }
                 if (taps && r < kN) {
-                    float* tp = taps + ((size_t)trk * kN + r) * kC + 16 * s;
+                    float* tp = taps + ((size_t)trk * kN + r) * kC + kCW * s;
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(tp + i) = make_float4(x[t][i], x[t][i + 1], x[t][i + 2], x[t][i + 3]);
+                    for (int i = 0; i < kCW; i += 4) *reinterpret_cast<float4*>(tp + i) = make_float4(x[t][i], x[t][i + 1], x[t][i + 2], x[t][i + 3]);
                 }
             }
 
@@ -350,40 +370,43 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
 
 #pragma unroll
                 for (int t = 0; t < 3; ++t) {      // LayerNorm 1 -> the tiles' A-operand slots
-                    float y[16];
-                    e.ln16(x[t], par + kPLn1g, par + kPLn1b, y);
-                    if (e.active(t)) e.store_opa16(t, y);
+                    float y[kCW];
+                    e.ln(x[t], par + kPLn1g, par + kPLn1b, y);
+                    if (e.active(t)) e.store_opa(t, y);
                 }
                 e.signal_go(false);             // -> 1
 
-                // ---- QKV epilogue: third 0 -> q (scaled) into the tile's A slot, third 1 -> K rows, third 2 -> V rows
+                // ---- QKV epilogue: a column group handles kQW of the 144 output columns: part 0 -> q (scaled) into the
+                //      tile's A slot, part 1 -> K rows, part 2 -> V rows (shared memory, UMMA layouts)
                 auto epi_qkv = [&](int t, uint32_t col) {
                     if (!e.active(t)) return;
-                    float v[48];
+                    float v[kQW];
+                    {
+                        uint32_t r[kQW / 8][8];
 #pragma unroll
-                    for (int c = 0; c < 48; c += 16) {
-                        uint32_t r[16];
-                        tmem_ld16(e.taddr(col + 48 * s + c), r);
+                        for (int c = 0; c < kQW / 8; ++c) tmem_ld8(e.taddr(col + kQW * s + 8 * c), r[c]);
                         tc_wait_ld();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[c + j] = __uint_as_float(r[j]) + par[kPBqkv + 48 * s + c + j];
+                        for (int c = 0; c < kQW / 8; ++c)
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[8 * c + j] = __uint_as_float(r[c][j]) + par[kPBqkv + kQW * s + 8 * c + j];
                     }
                     const int key = 128 * t + row;
-                    if (s == 0) {
+                    if (qkv_part == 0) {
 #pragma unroll
-                        for (int c = 0; c < 24; c += 8) {
-                            uint32_t hi[8], lo[8];
+                        for (int c = 0; c < kQW / 2; c += 4) {
+                            uint32_t hi[4], lo[4];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) split_pack2(v[2 * (c + j)] * scale, v[2 * (c + j) + 1] * scale, hi[j], lo[j]);
-                            tmem_st8(e.taddr(kColOpa + 48 * t + c), hi);
-                            tmem_st8(e.taddr(kColOpa + 48 * t + 24 + c), lo);
+                            for (int j = 0; j < 4; ++j) split_pack2(v[2 * (c + j)] * scale, v[2 * (c + j) + 1] * scale, hi[j], lo[j]);
+                            tmem_st4(e.taddr(kColOpa + 48 * t + qkv_off / 2 + c), hi);
+                            tmem_st4(e.taddr(kColOpa + 48 * t + 24 + qkv_off / 2 + c), lo);
                         }
                     } else {
                         // K: K-major [k/8][key][8]   V: MN-major [f/8][key/8][key%8][f%8]  (both: chunk * 320*16 + key*16)
-                        uint8_t* hi_base = smem + (s == 1 ? kSmKhi : kSmVhi) + key * 16;
-                        uint8_t* lo_base = smem + (s == 1 ? kSmKlo : kSmVlo) + key * 16;
+                        uint8_t* hi_base = smem + (qkv_part == 1 ? kSmKhi : kSmVhi) + key * 16 + (qkv_off / 8) * (kN * 16);
+                        uint8_t* lo_base = smem + (qkv_part == 1 ? kSmKlo : kSmVlo) + key * 16 + (qkv_off / 8) * (kN * 16);
 #pragma unroll
-                        for (int c = 0; c < 6; ++c) {
+                        for (int c = 0; c < kQW / 8; ++c) {
                             uint32_t hi[4], lo[4];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) split_pack2(v[8 * c + 2 * j], v[8 * c + 2 * j + 1], hi[j], lo[j]);
@@ -401,80 +424,84 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                 e.signal_go(true);              // -> 3
 
                 // ---- attention per tile -------------------------------------------------------------------
-                float inv_l[3];
                 auto softmax = [&](int t) {
-                    // thirds own 112 / 112 / 96 score columns (7, 7, 6 groups of 16 keys); TMEM loads are
-                    // software pipelined (group g+1 is in flight while group g is processed)
-                    const int c_begin = 112 * s, groups = (s == 2) ? 6 : 7;
-                    const uint32_t a0 = e.taddr(kColBig + c_begin);
+                    // TMEM loads are software pipelined (group g+1 is in flight while group g is processed)
+                    constexpr int kMaxGroups = kSmBase + (kSmRem ? 1 : 0);
+                    const uint32_t a0 = e.taddr(kColBig + sm_begin);
                     float m = -INFINITY;
                     if (e.active(t)) {
                         uint32_t r[2][16];
                         tmem_ld16(a0, r[0]);
 #pragma unroll
-                        for (int g = 0; g < 7; ++g) {
-                            if (g < groups) {
+                        for (int g = 0; g < kMaxGroups; ++g) {
+                            if (g < sm_groups) {
                                 tc_wait_ld();
-                                if (g + 1 < groups) tmem_ld16(a0 + 16 * (g + 1), r[(g + 1) & 1]);
+                                if (g + 1 < sm_groups) tmem_ld16(a0 + 16 * (g + 1), r[(g + 1) & 1]);
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(r[g & 1][j]));
                             }
                         }
                     }
-                    float* rm = e.red + 2 * 384;
+                    float* rm = e.red + 2 * (kNS * 128);
                     rm[s * 128 + row] = m;
                     epi_bar();
-                    m = fmaxf(fmaxf(rm[row], rm[128 + row]), rm[256 + row]);
+                    m = rm[row];
+#pragma unroll
+                    for (int g = 1; g < kNS; ++g) m = fmaxf(m, rm[g * 128 + row]);
                     float l = 0.f;
                     if (e.active(t)) {
                         const float mb = m * kLog2e;
                         uint32_t r[2][16];
                         tmem_ld16(a0, r[0]);
 #pragma unroll
-                        for (int g = 0; g < 7; ++g) {
-                            if (g < groups) {
+                        for (int g = 0; g < kMaxGroups; ++g) {
+                            if (g < sm_groups) {
                                 tc_wait_ld();
-                                if (g + 1 < groups) tmem_ld16(a0 + 16 * (g + 1), r[(g + 1) & 1]);
+                                if (g + 1 < sm_groups) tmem_ld16(a0 + 16 * (g + 1), r[(g + 1) & 1]);
                                 uint32_t hi[8], lo[8];
+                                float l0 = 0.f, l1 = 0.f;
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) {
                                     const float p0 = ex2_approx(fmaf(__uint_as_float(r[g & 1][2 * j]), kLog2e, -mb));
                                     const float p1 = ex2_approx(fmaf(__uint_as_float(r[g & 1][2 * j + 1]), kLog2e, -mb));
-                                    l += p0 + p1;
+                                    l0 += p0; l1 += p1;
                                     split_pack2(p0, p1, hi[j], lo[j]);
                                 }
+                                l += l0 + l1;
                                 tmem_st8(a0 + 16 * g, hi);       // P overwrites S in place: [hi x8 | lo x8] per 16 keys
                                 tmem_st8(a0 + 16 * g + 8, lo);
                             }
                         }
                     }
-                    e.red[3 * 384 + s * 128 + row] = l;     // summed after the next barrier (in epi_o)
+                    e.red[3 * (kNS * 128) + s * 128 + row] = l;     // summed after the next barrier (in epi_o)
                 };
                 auto epi_o = [&](int t) {
                     epi_bar();                               // partial row sums of softmax(t) are visible
-                    const float* rl = e.red + 3 * 384;
-                    const float inv = 1.f / (rl[row] + rl[128 + row] + rl[256 + row]);
-                    inv_l[t] = inv;
-                    if (!e.active(t)) return;
-                    uint32_t r[16];
-                    tmem_ld16(e.taddr(kColOut + 16 * s), r);
-                    tc_wait_ld();
-                    float y[16];
+                    const float* rl = e.red + 3 * (kNS * 128);
+                    float lsum = rl[row];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(r[j]) * inv;
-                    e.store_opa16(t, y);
+                    for (int g = 1; g < kNS; ++g) lsum += rl[g * 128 + row];
+                    const float inv = 1.f / lsum;
+                    if (!e.active(t)) return;
+                    uint32_t r[kCW];
+                    tmem_ld<kCW>(e.taddr(kColOut + kCW * s), r);
+                    tc_wait_ld();
+                    float y[kCW];
+#pragma unroll
+                    for (int j = 0; j < kCW; ++j) y[j] = __uint_as_float(r[j]) * inv;
+                    e.store_opa(t, y);
                 };
                 auto epi_proj = [&](int t) {
                     if (e.active(t)) {
-                        uint32_t r[16];
-                        tmem_ld16(e.taddr(kColOut + 16 * s), r);
+                        uint32_t r[kCW];
+                        tmem_ld<kCW>(e.taddr(kColOut + kCW * s), r);
                         tc_wait_ld();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) x[t][j] += __uint_as_float(r[j]) + par[kPBproj + 16 * s + j];
+                        for (int j = 0; j < kCW; ++j) x[t][j] += __uint_as_float(r[j]) + par[kPBproj + kCW * s + j];
                     }
-                    float y[16];
-                    e.ln16(x[t], par + kPLn2g, par + kPLn2b, y);
-                    if (e.active(t)) e.store_opa16(t, y);
+                    float y[kCW];
+                    e.ln(x[t], par + kPLn2g, par + kPLn2b, y);
+                    if (e.active(t)) e.store_opa(t, y);
                 };
                 e.wait_done(); softmax(0); e.signal_go(false);                    // -> 4
                 e.wait_done(); epi_o(0); e.signal_go(false);                      // -> 5
@@ -487,18 +514,18 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                 // ---- MLP per tile -------------------------------------------------------------------------
                 auto gelu = [&](int t, uint32_t h_col) {
                     if (!e.active(t)) return;
-                    const uint32_t a0 = e.taddr(h_col + 64 * s);                  // third s owns hidden columns [64 s, 64 s + 64)
+                    const uint32_t a0 = e.taddr(h_col + kHW * s);                 // group s owns hidden columns [kHW s, kHW s + kHW)
                     uint32_t r[2][16];
                     tmem_ld16(a0, r[0]);
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
+                    for (int g = 0; g < kHW / 16; ++g) {
                         tc_wait_ld();
-                        if (g + 1 < 4) tmem_ld16(a0 + 16 * (g + 1), r[(g + 1) & 1]);
+                        if (g + 1 < kHW / 16) tmem_ld16(a0 + 16 * (g + 1), r[(g + 1) & 1]);
                         uint32_t hi[8], lo[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float h0 = gelu_erf(__uint_as_float(r[g & 1][2 * j]) + par[kPBfc1 + 64 * s + 16 * g + 2 * j]);
-                            const float h1 = gelu_erf(__uint_as_float(r[g & 1][2 * j + 1]) + par[kPBfc1 + 64 * s + 16 * g + 2 * j + 1]);
+                            const float h0 = gelu_erf(__uint_as_float(r[g & 1][2 * j]) + par[kPBfc1 + kHW * s + 16 * g + 2 * j]);
+                            const float h1 = gelu_erf(__uint_as_float(r[g & 1][2 * j + 1]) + par[kPBfc1 + kHW * s + 16 * g + 2 * j + 1]);
                             split_pack2(h0, h1, hi[j], lo[j]);
                         }
                         tmem_st8(a0 + 16 * g, hi);
@@ -507,21 +534,21 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                 };
                 auto epi_fc2 = [&](int t, uint32_t y_col) {
                     if (!e.active(t)) return;
-                    uint32_t r[16];
-                    tmem_ld16(e.taddr(y_col + 16 * s), r);
+                    uint32_t r[kCW];
+                    tmem_ld<kCW>(e.taddr(y_col + kCW * s), r);
                     tc_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) x[t][j] += __uint_as_float(r[j]) + par[kPBfc2 + 16 * s + j];
+                    for (int j = 0; j < kCW; ++j) x[t][j] += __uint_as_float(r[j]) + par[kPBfc2 + kCW * s + j];
                     const int rr = 128 * t + row;
                     if (taps && rr < kN) {
-                        float* tp = taps + (size_t)(blk + 1) * tap_stride + ((size_t)trk * kN + rr) * kC + 16 * s;
+                        float* tp = taps + (size_t)(blk + 1) * tap_stride + ((size_t)trk * kN + rr) * kC + kCW * s;
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(tp + i) = make_float4(x[t][i], x[t][i + 1], x[t][i + 2], x[t][i + 3]);
+                        for (int i = 0; i < kCW; i += 4) *reinterpret_cast<float4*>(tp + i) = make_float4(x[t][i], x[t][i + 1], x[t][i + 2], x[t][i + 3]);
                     }
                     if (blk == kDepth - 1 && rr < kN) {
-                        float* dst = out + ((size_t)trk * kN + rr) * kC + 16 * s;
+                        float* dst = out + ((size_t)trk * kN + rr) * kC + kCW * s;
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(x[t][i], x[t][i + 1], x[t][i + 2], x[t][i + 3]);
+                        for (int i = 0; i < kCW; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(x[t][i], x[t][i + 1], x[t][i + 2], x[t][i + 3]);
                     }
                 };
                 // MLP, pipelined over row tiles: the tensor pipe runs fc1 / fc2 of the other tiles during each GELU
@@ -531,14 +558,13 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                 e.wait_bar(mb_h, h_ph[0]);      gelu(2, kColHA);     e.signal(mb_g, false);
                 e.wait_bar(mb_y + 1, y_ph[1]);  epi_fc2(1, kColYB);
                 e.wait_bar(mb_y, y_ph[0]);      epi_fc2(2, kColYA);
-                (void)inv_l;
             }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 12) tmem_dealloc(tbase, 512);
+    if (warp == kEpiWarps) tmem_dealloc(tbase, 512);
 }
 
 #ifdef VT_TC_TRACE
