@@ -381,8 +381,21 @@ int vt_finalize_weights(VtHandle h, void* stream) {
         if (!(wqkv && wproj && w1 && w2)) continue;
         uint8_t* wa = reinterpret_cast<uint8_t*>(&pk.buf[tc_wa[b]]);
         uint8_t* wb = reinterpret_cast<uint8_t*>(&pk.buf[tc_wb[b]]);
-        pack_kmajor(wa, wa + 13824, wqkv, 144, 48);
-        pack_kmajor(wa + 27648, wa + 27648 + 4608, wproj, 48, 48);
+        // attention output projection folded into the value projection: (P V) Wp^T = P (V Wp^T), V Wp^T = LN(x) (Wp Wv)^T + Wp bv
+        // (products accumulated in float64; the block kernel then needs no separate proj GEMM)
+        const float* bqkv = T(p + "attn.qkv.bias");
+        std::vector<float> wf(wqkv, wqkv + 144 * 48), bvp(48, 0.f);
+        for (int o = 0; o < 48; ++o) {
+            for (int i = 0; i < 48; ++i) {
+                double acc = 0.0;
+                for (int j = 0; j < 48; ++j) acc += (double)wproj[o * 48 + j] * (double)wqkv[(96 + j) * 48 + i];
+                wf[(96 + o) * 48 + i] = (float)acc;
+            }
+            double accb = 0.0;
+            for (int j = 0; j < 48 && bqkv; ++j) accb += (double)wproj[o * 48 + j] * (double)bqkv[96 + j];
+            bvp[o] = (float)accb;
+        }
+        pack_kmajor(wa, wa + 13824, wf.data(), 144, 48);
         pack_kmajor(wb, wb + 18432, w1, 192, 48);
         pack_kmajor(wb + 36864, wb + 36864 + 18432, w2, 48, 192);
         float* par = &pk.buf[tc_par[b]];
@@ -391,6 +404,7 @@ int vt_finalize_weights(VtHandle h, void* stream) {
         const int cnt[8] = {48, 48, 144, 48, 48, 48, 192, 48};
         int o = 0;
         for (int i = 0; i < 8; ++i) { if (src[i]) memcpy(par + o, src[i], cnt[i] * sizeof(float)); o += cnt[i]; }
+        memcpy(par + 96 + 96, bvp.data(), 48 * sizeof(float));          // bias of the folded value projection
     }
     const size_t o_ng = slot(kC), o_nb = slot(kC), o_pz = slot(kNz * kC), o_px = slot(kNx * kC);
     copyv(o_ng, T("norm.weight"), kC); copyv(o_nb, T("norm.bias"), kC);

@@ -57,7 +57,7 @@ static_assert(kNS == 3 || kNS == 6, "column groups");
 
 // ---- TMEM columns --------------------------------------------------------------------------------
 constexpr uint32_t kColBig = 0;        // [0,320): QKV out (2 buffers of 144 at 0 / 160), S -> P, fc1 out -> GELU operand
-constexpr uint32_t kColOut = 320;      // [320,368): O, proj out, fc2 out
+constexpr uint32_t kColOut = 320;      // [320,368): free during attention (O' accumulates in the q slots); part of H_B in the MLP phase
 constexpr uint32_t kColOpa = 368;      // [368,512): three 48-column A-operand slots (hi 24 | lo 24), one per row tile
 // MLP phase (the attention regions are dead by then): two fc1-output / GELU-operand buffers and two fc2 outputs, so
 // that the GELU of one row tile overlaps the MMAs of the others.  H_B / Y_A / Y_B alias the A-operand slots; the
@@ -72,8 +72,8 @@ constexpr int kKBytes = kN * kC * 2;                      // 30720 per precision
 constexpr int kSmKhi = kSmX, kSmKlo = kSmX + kKBytes, kSmVhi = kSmX + 2 * kKBytes, kSmVlo = kSmX + 3 * kKBytes;
 constexpr int kSmW1hi = kSmX, kSmW1lo = kSmX + 18432, kSmW2hi = kSmX + 36864, kSmW2lo = kSmX + 55296;
 constexpr int kSmPar = kSmX + 4 * kKBytes;                // fp32 parameters of all blocks
-constexpr int kSmRed = kSmPar + kDepth * kTcParFloats * 4;   // 4 arrays x kNS column groups x 128 rows fp32
-constexpr int kSmBar = kSmRed + 4 * kNS * 128 * 4;        // mbarriers
+constexpr int kSmRed = kSmPar + kDepth * kTcParFloats * 4;   // 5 arrays x kNS column groups x 128 rows fp32
+constexpr int kSmBar = kSmRed + 5 * kNS * 128 * 4;        // mbarriers
 constexpr int kSmTmem = kSmBar + 12 * 8;
 constexpr int kTcSmemBytes = kSmTmem + 16;
 static_assert(kTcWbBytes <= 4 * kKBytes, "MLP weights overlay the K/V region");
@@ -240,7 +240,6 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                 }
             };
             auto qkv = [&](int t, uint32_t d_col) { gemm_k48(t, d_col, kSmWa, kSmWa + 13824, 144, id144); };
-            auto proj = [&](int t) { gemm_k48(t, kColOut, kSmWa + 27648, kSmWa + 27648 + 4608, 48, id48); };
             auto fc1 = [&](int t, uint32_t h_col) { gemm_k48(t, h_col, kSmW1hi, kSmW1lo, 192, id192); };
             // S = q k^T over 320 keys as two N = 160 halves; K operand K-major [k/8][320][8]
             auto scores = [&](int t) {
@@ -259,16 +258,18 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                     }
                 }
             };
-            // O = P V: P in TMEM (16-key group g: hi cols 16g.., lo cols 16g+8..), V MN-major [f/8][key/8][key%8][f%8]
-            auto pv = [&]() {
+            // O' = P V' accumulated in the tile's (now dead) q slot: P in TMEM (16-key group g: hi cols 16g.., lo cols 16g+8..),
+            // V' = V Wproj^T MN-major [f/8][key/8][key%8][f%8]
+            auto pv = [&](int t) {
+                const uint32_t d = tbase + kColOpa + 48 * t;
 #pragma unroll 4
                 for (int g = 0; g < kN / 16; ++g) {
                     const uint32_t a = tbase + kColBig + 16 * g;
                     const uint64_t bh = smem_desc(sbase + kSmVhi + g * 256, 128, (kN / 8) * 128);
                     const uint64_t bl = smem_desc(sbase + kSmVlo + g * 256, 128, (kN / 8) * 128);
-                    mma_ts_elect(tbase + kColOut, a, bh, id48mn, g > 0);
-                    mma_ts_elect(tbase + kColOut, a + 8, bh, id48mn, true);
-                    mma_ts_elect(tbase + kColOut, a, bl, id48mn, true);
+                    mma_ts_elect(d, a, bh, id48mn, g > 0);
+                    mma_ts_elect(d, a + 8, bh, id48mn, true);
+                    mma_ts_elect(d, a, bl, id48mn, true);
                 }
             };
             // y = gelu(h) W2^T: operand in TMEM (16-wide group g: hi 16g.., lo 16g+8..), W2 K-major [k/8][48][8], K = 192
@@ -294,14 +295,11 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                     mbar_wait(mb_wa, wa_ph); wa_ph ^= 1;
                     qkv(0, kColBig); qkv(1, kColBig + 160); mma_commit_elect(mb_done);
                     wait_go(); qkv(2, kColBig); mma_commit_elect(mb_done);             // 2
-                    wait_go(); scores(0); mma_commit_elect(mb_done);                   // 3: K, V complete
-                    wait_go(); pv(); mma_commit_elect(mb_done);                        // 4
-                    wait_go(); proj(0); scores(1); mma_commit_elect(mb_done);          // 5
-                    wait_go(); pv(); mma_commit_elect(mb_done);                        // 6
-                    wait_go(); proj(1); scores(2); mma_commit_elect(mb_done);          // 7
-                    wait_go(); pv(); mma_commit_elect(mb_done);                        // 8
-                    wait_go(); load_wb(blk); proj(2); mma_commit_elect(mb_done);       // 9: K/V dead -> MLP weights stream in
-                    wait_go();                                                   // 10: Wqkv/Wproj dead -> prefetch the next block's
+                    wait_go(); scores(0); mma_commit_elect(mb_done);                   // 3: K, V' complete
+                    wait_go(); pv(0); scores(1); mma_commit_elect(mb_done);            // 4: P(0) written; S(1) reuses the columns in issue order
+                    wait_go(); pv(1); scores(2); mma_commit_elect(mb_done);            // 5
+                    wait_go(); pv(2); mma_commit_elect(mb_done);                       // 6
+                    wait_go(); load_wb(blk);                                     // 7: attention output + LN2 of every tile done; K/V' dead
                     if (!(last_track && blk == kDepth - 1)) load_wa((blk + 1) % kDepth);
                     mbar_wait(mb_wb, wb_ph); wb_ph ^= 1;
                     // ---- MLP, pipelined over row tiles (tile 0 -> H_A/Y_A, tile 1 -> H_B/Y_B, tile 2 -> H_A/Y_A) ----
@@ -473,43 +471,32 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                             }
                         }
                     }
-                    e.red[3 * (kNS * 128) + s * 128 + row] = l;     // summed after the next barrier (in epi_o)
+                    e.red[(3 + (t & 1)) * (kNS * 128) + s * 128 + row] = l;     // summed in epi_out(t)
                 };
-                auto epi_o = [&](int t) {
+                // attention output of tile t: x += (P V')/l + bproj (V' carries the output projection), then LayerNorm 2 -> A slot.
+                // O' sits in the tile's own slot: every thread reads its columns before the LayerNorm barriers, writes after.
+                auto epi_out = [&](int t) {
                     epi_bar();                               // partial row sums of softmax(t) are visible
-                    const float* rl = e.red + 3 * (kNS * 128);
+                    const float* rl = e.red + (3 + (t & 1)) * (kNS * 128);
                     float lsum = rl[row];
 #pragma unroll
                     for (int g = 1; g < kNS; ++g) lsum += rl[g * 128 + row];
                     const float inv = 1.f / lsum;
-                    if (!e.active(t)) return;
-                    uint32_t r[kCW];
-                    tmem_ld<kCW>(e.taddr(kColOut + kCW * s), r);
-                    tc_wait_ld();
-                    float y[kCW];
-#pragma unroll
-                    for (int j = 0; j < kCW; ++j) y[j] = __uint_as_float(r[j]) * inv;
-                    e.store_opa(t, y);
-                };
-                auto epi_proj = [&](int t) {
                     if (e.active(t)) {
                         uint32_t r[kCW];
-                        tmem_ld<kCW>(e.taddr(kColOut + kCW * s), r);
+                        tmem_ld<kCW>(e.taddr(kColOpa + 48 * t + kCW * s), r);
                         tc_wait_ld();
 #pragma unroll
-                        for (int j = 0; j < kCW; ++j) x[t][j] += __uint_as_float(r[j]) + par[kPBproj + kCW * s + j];
+                        for (int j = 0; j < kCW; ++j) x[t][j] += fmaf(__uint_as_float(r[j]), inv, par[kPBproj + kCW * s + j]);
                     }
                     float y[kCW];
                     e.ln(x[t], par + kPLn2g, par + kPLn2b, y);
                     if (e.active(t)) e.store_opa(t, y);
                 };
                 e.wait_done(); softmax(0); e.signal_go(false);                    // -> 4
-                e.wait_done(); epi_o(0); e.signal_go(false);                      // -> 5
-                e.wait_done(); epi_proj(0); softmax(1); e.signal_go(false);       // -> 6
-                e.wait_done(); epi_o(1); e.signal_go(false);                      // -> 7
-                e.wait_done(); epi_proj(1); softmax(2); e.signal_go(false);       // -> 8
-                e.wait_done(); epi_o(2); e.signal_go(false);                      // -> 9
-                e.wait_done(); epi_proj(2); e.signal_go(false);                   // -> 10
+                e.wait_done(); softmax(1); e.signal_go(false); epi_out(0);        // -> 5   (epi_out overlaps P V' (1) and S(2))
+                e.wait_done(); softmax(2); e.signal_go(false); epi_out(1);        // -> 6
+                e.wait_done(); epi_out(2); e.signal_go(false);                    // -> 7
 
                 // ---- MLP per tile -------------------------------------------------------------------------
                 auto gelu = [&](int t, uint32_t h_col) {

@@ -43,11 +43,11 @@ struct HeadW {               // CENTER head, BN folded, towers ordered ctr, offs
 
 // Tensor-core block kernel operands (vt_block_tc.cu): fp16 hi/lo split weights in the UMMA
 // no-swizzle K-major layout [k/8][n][8], one bulk-copyable blob per phase, plus fp32 parameters.
-constexpr int kTcWaBytes = 2 * (144 * 48 * 2) + 2 * (48 * 48 * 2);      // Wqkv hi|lo, Wproj hi|lo = 36864
+constexpr int kTcWaBytes = 2 * (144 * 48 * 2);                         // [Wq; Wk; Wproj Wv] hi|lo = 27648 (the output projection is folded into V)
 constexpr int kTcWbBytes = 2 * (192 * 48 * 2) + 2 * (48 * 192 * 2);     // W1 hi|lo, W2 hi|lo     = 73728
 constexpr int kHeadTcPieceBytes = 2 * (48 * 48 * 2);       // one (half, kx, ky) piece of head conv1: hi | lo, N = 48, K = 48 -> 9216
 constexpr int kHeadTcW2Bytes = 9 * 2 * (96 * 16 * 2);      // head conv2: 9 (tower, kx) blobs of hi | lo, N = 16, K = 96 -> 55296
-constexpr int kTcParFloats = 624;   // ln1_g 48 | ln1_b 48 | bqkv 144 | bproj 48 | ln2_g 48 | ln2_b 48 | bfc1 192 | bfc2 48
+constexpr int kTcParFloats = 624;   // ln1_g 48 | ln1_b 48 | bq 48 | bk 48 | Wproj bv 48 | bproj 48 | ln2_g 48 | ln2_b 48 | bfc1 192 | bfc2 48
 struct BlockTcW {
     const uint8_t* wa;     // kTcWaBytes
     const uint8_t* wb;     // kTcWbBytes
