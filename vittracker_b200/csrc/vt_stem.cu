@@ -8,6 +8,8 @@
 // in shared memory as [cin][ky][kx][cout]; a thread owns P output pixels x QG output channels and
 // reads its weights with broadcast vector loads.  The last layer writes tokens (row = y*16+x,
 // token-major [token][48]) with the positional embedding added (vit_dist.py:53,81-82).
+#include <type_traits>
+
 #include "vt_geom.cuh"
 #include "vt_internal.h"
 #include "vt_tc.cuh"
@@ -267,9 +269,12 @@ crop_conv1_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict_
     if (blockIdx.x == 0 && tid == 0 && out_status) out_status[item] = g.status;
     const double scale = resize_scale(S, g.crop_sz);
 
-    // tap tables: .x/.y = byte offsets of the two taps (0 when the tap is padding), .z = weights (lo | hi << 16,
-    // 0 for a padding tap: a zero pixel and a zero weight give the same products), .w = 1 when the position is
-    // outside the resized crop (= the convolution's zero padding, which is 0.0f and not the normalised pixel 0)
+    // tap tables.  Columns: the two horizontal taps of cv::resize are the same or adjacent source pixels, so a column is
+    // one PAIR of adjacent pixels (.x = byte offset of the first, .y = weights first | second << 16; a tap that is padding
+    // or clamped away has weight 0 - a zero pixel and a zero weight give the same products - and the pair is anchored on a
+    // tap that is inside the image, so the six bytes read always are).  Rows: .x/.y = byte offsets of the two tap rows
+    // (0 when the row is padding), .z = weights lo | hi << 16.  .w = 1 when the position is outside the resized crop
+    // (= the convolution's zero padding, which is 0.0f and not the normalised pixel 0).
     if (tid < kCc1TileSide) {
         const int d = 2 * tx0 - 1 + tid;
         int4 t = make_int4(0, 0, 0, 1);
@@ -277,8 +282,11 @@ crop_conv1_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict_
             int s0, s1, a0, a1; bool w0, w1;
             tap_x(d, scale, g.crop_sz, s0, s1, a0, a1, w0, w1);
             const int ix0 = g.x1 + s0, ix1 = g.x1 + s1;
-            const bool v0 = ix0 >= 0 && ix0 <= W - 2, v1 = ix1 >= 0 && ix1 <= W - 2;
-            t = make_int4(v0 ? ix0 * 3 : 0, v1 ? ix1 * 3 : 0, (v0 ? a0 : 0) | ((v1 ? a1 : 0) << 16), 0);
+            if (!(ix0 >= 0 && ix0 <= W - 2)) a0 = 0;
+            if (!(ix1 >= 0 && ix1 <= W - 2) || ix1 == ix0) a1 = 0;      // s1 == s0 only where cv::resize clamps, and there a1 == 0
+            if (a0 != 0) t = make_int4(ix0 * 3, a0 | (a1 << 16), 0, 0);
+            else if (a1 != 0) t = make_int4(ix1 * 3, a1, 0, 0);
+            else t = make_int4(0, 0, 0, 0);
         }
         s_col[tid] = t;
     } else if (tid >= 128 && tid < 128 + kCc1TileSide) {
@@ -297,42 +305,65 @@ crop_conv1_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict_
 
     const uint8_t* __restrict__ im = frames + frame_offsets[item];
     // One resized-crop pixel (3 channels) of tile position (r, c): 2x2 source taps, 11-bit fixed point exactly as
-    // cv::resize (HResize then VResizeLinear 8U), then the normalisation table.  Padding taps carry weight 0 and a
-    // safe offset, so the twelve byte loads are unconditional and can all be in flight.
-    auto gather_px = [&](int r, const int4 ct, int slot) {
-        const int4 rt = s_row[r];
-        float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-        if (!((ct.w | rt.w) & 1)) {
-            const uint8_t* q00 = im + (rt.x + ct.x);
-            const uint8_t* q01 = im + (rt.x + ct.y);
-            const uint8_t* q10 = im + (rt.y + ct.x);
-            const uint8_t* q11 = im + (rt.y + ct.y);
-            int p00[3], p01[3], p10[3], p11[3];
+    // cv::resize (HResize then VResizeLinear 8U), then the normalisation table.  Each tap row is read as three aligned
+    // 32-bit words covering the pair's six bytes (R0 G0 B0 R1 G1 B1), realigned with funnel shifts; a channel's
+    // horizontal pass is one byte permute + one two-way dot product with the packed weights.
+    // kB tile rows of one column per batch, in three explicit phases so that every global load of the batch is in
+    // flight before its first use: (1) 6 word loads per row, (2) fixed-point bilinear + table loads, (3) tile stores.
+    // Branch-free: padding positions read offset 0 with weight 0 and are zeroed at the end.
+    auto gather_col = [&](auto kb_tag, int r_first, int r_step, int n_batches, const int4 ct, int slot) {
+        constexpr int kB = decltype(kb_tag)::value;
+        const unsigned wx = (unsigned)ct.y;
+#pragma unroll 1
+        for (int rb = 0; rb < n_batches; ++rb) {
+            uint32_t wd[kB][6];
+            unsigned sh[kB][2];
+            int bz[kB];
+            bool outside[kB];
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) { p00[ch] = __ldg(q00 + ch); p01[ch] = __ldg(q01 + ch); p10[ch] = __ldg(q10 + ch); p11[ch] = __ldg(q11 + ch); }
-            const int a0 = ct.z & 0xffff, a1 = (unsigned)ct.z >> 16, b0 = rt.z & 0xffff, b1 = (unsigned)rt.z >> 16;
-            int v[3];
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-                const int h0 = p00[ch] * a0 + p01[ch] * a1;
-                const int h1 = p10[ch] * a0 + p11[ch] * a1;
-                v[ch] = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;     // always in [0, 255]
+            for (int k = 0; k < kB; ++k) {
+                const int4 rt = s_row[r_first + (rb * kB + k) * r_step];
+                const uintptr_t q0 = reinterpret_cast<uintptr_t>(im + (rt.x + ct.x));
+                const uintptr_t q1 = reinterpret_cast<uintptr_t>(im + (rt.y + ct.x));
+                const uint32_t* p0 = reinterpret_cast<const uint32_t*>(q0 & ~static_cast<uintptr_t>(3));
+                const uint32_t* p1 = reinterpret_cast<const uint32_t*>(q1 & ~static_cast<uintptr_t>(3));
+                wd[k][0] = __ldg(p0); wd[k][1] = __ldg(p0 + 1); wd[k][2] = __ldg(p0 + 2);
+                wd[k][3] = __ldg(p1); wd[k][4] = __ldg(p1 + 1); wd[k][5] = __ldg(p1 + 2);
+                sh[k][0] = ((unsigned)q0 & 3u) * 8u; sh[k][1] = ((unsigned)q1 & 3u) * 8u;
+                bz[k] = rt.z;
+                outside[k] = ((ct.w | rt.w) & 1) != 0;
             }
-            v0 = __ldg(lut + v[0]); v1 = __ldg(lut + 256 + v[1]); v2 = __ldg(lut + 512 + v[2]);     // 3 KB table, L1 resident
+            float val[kB][3];
+#pragma unroll
+            for (int k = 0; k < kB; ++k) {
+                const uint32_t u0 = __funnelshift_r(wd[k][0], wd[k][1], sh[k][0]), u1 = __funnelshift_r(wd[k][1], wd[k][2], sh[k][0]);   // R0 G0 B0 R1 | G1 B1 . .
+                const uint32_t t0 = __funnelshift_r(wd[k][3], wd[k][4], sh[k][1]), t1 = __funnelshift_r(wd[k][4], wd[k][5], sh[k][1]);
+                const int b0 = bz[k] & 0xffff, b1 = (unsigned)bz[k] >> 16;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const unsigned sel = ch == 0 ? 0x0030u : ch == 1 ? 0x0041u : 0x0052u;             // (first, second) pixel's byte
+                    const int h0 = (int)__dp2a_lo(wx, __byte_perm(u0, u1, sel), 0u);
+                    const int h1 = (int)__dp2a_lo(wx, __byte_perm(t0, t1, sel), 0u);
+                    const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;     // always in [0, 255]
+                    val[k][ch] = __ldg(lut + 256 * ch + v);                                           // 3 KB table, L1 resident
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kB; ++k) {
+                float* dst = tile + (r_first + (rb * kB + k) * r_step) * K::kPitch + slot;
+                dst[0] = outside[k] ? 0.f : val[k][0];
+                dst[K::kInRows * K::kPitch] = outside[k] ? 0.f : val[k][1];
+                dst[2 * K::kInRows * K::kPitch] = outside[k] ? 0.f : val[k][2];
+            }
         }
-        float* dst = tile + r * K::kPitch + slot;
-        dst[0] = v0;
-        dst[K::kInRows * K::kPitch] = v1;
-        dst[2 * K::kInRows * K::kPitch] = v2;
     };
     {
-        // threads own a fixed column (taps in registers) and walk down rows: columns 0..63 x 4 row phases, then column 64
+        // threads own a fixed column (taps in registers) and walk down rows 0..63 in 4 row phases; row 64 and column 64
+        // (the tile's halo) are 129 single pixels
         const int c = tid & 63;
-        const int4 ct = s_col[c];
-        const int slot = (c & 1) ? (K::kOOff + (c >> 1)) : (K::kEOff + (c >> 1));
-#pragma unroll 4
-        for (int r = tid >> 6; r < kCc1TileSide; r += 4) gather_px(r, ct, slot);
-        if (tid < kCc1TileSide) gather_px(tid, s_col[64], K::kEOff + 32);
+        gather_col(std::integral_constant<int, 4>{}, tid >> 6, 4, 4, s_col[c], (c & 1) ? (K::kOOff + (c >> 1)) : (K::kEOff + (c >> 1)));
+        if (tid < 64) gather_col(std::integral_constant<int, 1>{}, 64, 0, 1, s_col[tid], (tid & 1) ? (K::kOOff + (tid >> 1)) : (K::kEOff + (tid >> 1)));
+        else if (tid < 129) gather_col(std::integral_constant<int, 1>{}, tid - 64, 0, 1, s_col[64], K::kEOff + 32);
     }
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncthreads();
