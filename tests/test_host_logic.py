@@ -72,8 +72,11 @@ def test_unsupported_config_rejected():
     from vittracker_b200 import _lib
     lib = _lib.load()
     h = C.c_void_p()
-    cfg = _lib.VtConfig(768, 12, 12, 4, 256, 16, 128, 256, 2.0, 4.0, 1, 0, 0, 0)
-    assert lib.vt_create(C.byref(cfg), C.byref(h)) == -5
+    # stride 8, embed dim not a multiple of 8, depth out of range: no kernels -> VT_ERR_UNSUPPORTED before any device work
+    for bad in ((48, 1, 3, 4, 32, 8, 128, 256), (50, 1, 3, 4, 32, 16, 128, 256), (768, 12, 64, 4, 256, 16, 128, 256),
+                (48, 1, 3, 4, 32, 16, 128, 320)):
+        cfg = _lib.VtConfig(*bad, 2.0, 4.0, 1, 0, 0, 0)
+        assert lib.vt_create(C.byref(cfg), C.byref(h)) == -5, bad
     assert lib.vt_create(None, C.byref(h)) == -1
 
 

@@ -41,8 +41,9 @@ class BatchedTracker:
     the batched counterpart of ``Vit_dist.initialize`` / ``Vit_dist.track``."""
 
     def __init__(self, cfg, state_dict, max_tracks: int, device: Optional[int] = None, chunk_tracks: int = 0,
-                 blocks_impl: str = "tcgen05"):
-        self.engine = Engine(cfg, max_tracks=max_tracks, chunk_tracks=chunk_tracks, device=device, blocks_impl=blocks_impl)
+                 blocks_impl: str = "tcgen05", depth: Optional[int] = None):
+        depth = int(getattr(cfg.MODEL.BACKBONE, "DEPTH", 3)) if depth is None else int(depth)
+        self.engine = Engine(cfg, max_tracks=max_tracks, chunk_tracks=chunk_tracks, device=device, blocks_impl=blocks_impl, depth=depth)
         self.engine.load_state_dict(state_dict)
         self.device = self.engine.device
         self.max_tracks = max_tracks

@@ -48,7 +48,8 @@ def default_cfg() -> Node:
             "BACKBONE": {"TYPE": "vit_base_patch16_224", "STRIDE": 16, "MID_PE": False, "SEP_SEG": False,
                          "CAT_MODE": "direct", "MERGE_LAYER": 0, "ADD_CLS_TOKEN": False,
                          "CLS_TOKEN_USE_MODE": "ignore", "CHANNELS": 768, "HEADS": 12, "CE_LOC": [],
-                         "CE_KEEP_RATIO": [], "CE_TEMPLATE_RANGE": "ALL"},
+                         "CE_KEEP_RATIO": [], "CE_TEMPLATE_RANGE": "ALL",
+                         "DEPTH": 3},      # DEPTH: this package only (build_ostrack_dist(cfg, depth=3) in the reference)
             "HEAD": {"TYPE": "CENTER", "NUM_CHANNELS": 256},
         },
         "TRAIN": {"LR": 0.0001, "WEIGHT_DECAY": 0.0001, "EPOCH": 500, "LR_DROP_EPOCH": 400, "BATCH_SIZE": 16,

@@ -52,6 +52,11 @@ struct VtContext {
     int32_t* d_status = nullptr;      // [max_tracks]
     float* d_maps = nullptr;          // [max_tracks][1280] score | size | offset of the last step
     int last_first = 0, last_n = 0;
+    // generic-configuration path (every configuration other than vit_48_h32; vt_generic.cu)
+    bool generic = false;
+    GenModelW gw{};
+    GenWork gws{};
+    float* d_gwork = nullptr;
     // optional per-stage timing (vt_profile_*)
     struct ProfRec { int stage; int items; cudaEvent_t a, b; };
     bool profiling = false;
@@ -150,7 +155,7 @@ void free_all(VtHandle h) {
     for (auto e : h->evpool) cudaEventDestroy(e);
     cudaFree(h->d_weights); cudaFree(h->d_planes); cudaFree(h->d_scratch); cudaFree(h->d_tokz);
     cudaFree(h->d_tokx); cudaFree(h->d_tok); cudaFree(h->d_state); cudaFree(h->d_tmpl);
-    cudaFree(h->d_status); cudaFree(h->d_maps);
+    cudaFree(h->d_status); cudaFree(h->d_maps); cudaFree(h->d_gwork);
 }
 
 int check_ready(VtHandle h, bool need_tracks) {
@@ -190,6 +195,133 @@ int run_blocks(VtHandle h, const float* tokz, int zs, const float* tokx, int xs,
     return launch_blocks_tc(tokz, zs, tokx, xs, out, n, h->mw, taps, tap_stride, h->num_sms, st);
 }
 
+
+// Hann window (hann.py:6-16; the tracker's own tensor when it was handed over) and normalisation table (data_utils.py:8-14)
+void fill_hann_and_lut(VtHandle h, float* hann, float* lut) {
+    auto it = h->tensors.find("tracker.output_window");
+    if (it != h->tensors.end()) {
+        memcpy(hann, it->second.data.data(), 256 * sizeof(float));
+    } else {
+        float w1[16];
+        const float step = (float)(2.0 * M_PI / 17.0);
+        for (int k = 0; k < 16; ++k) w1[k] = 0.5f * (1.f - cosf(step * (float)(k + 1)));
+        for (int y = 0; y < 16; ++y)
+            for (int x = 0; x < 16; ++x) hann[y * 16 + x] = w1[y] * w1[x];
+    }
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+    for (int c = 0; c < 3; ++c)
+        for (int v = 0; v < 256; ++v) {
+            volatile float a = (float)v / 255.0f;        // (x / 255.0) - mean) / std, each step rounded to fp32
+            volatile float d = a - mean[c];
+            volatile float r = d / stdv[c];
+            lut[c * 256 + v] = r;
+        }
+}
+
+// Weights of the generic path: the reference's own layouts ([out][in]; conv [cout][ky][kx][cin]) with BatchNorm(eval) folded
+// in float64 (Conv2d_BN.fuse vit_dist.py:22-33; head conv + bias -> BN, head.py:16-21).
+int finalize_generic(VtHandle h, cudaStream_t st) {
+    const VtConfig& c = h->cfg;
+    const int C = c.embed_dim, hc = c.head_channels, hid = c.mlp_ratio * C;
+    std::string missing;
+    auto T = [&](const std::string& n) -> const float* {
+        auto it = h->tensors.find(n);
+        if (it == h->tensors.end()) { if (missing.size() < 300) missing += n + " "; return nullptr; }
+        return it->second.data.data();
+    };
+    Packer pk;
+    auto put = [&](const float* src, size_t n) { const size_t o = pk.alloc(n); if (src) memcpy(&pk.buf[o], src, n * sizeof(float)); return o; };
+    const double eps = 1e-5;
+    // conv [co][ci][3][3] (+ optional conv bias) with BN -> [co][(ky, kx, ci)], bias
+    auto fold_conv = [&](const float* w, const float* cb, const float* g, const float* b, const float* m, const float* v, int co_n, int ci_n,
+                         size_t& ow, size_t& ob) {
+        ow = pk.alloc((size_t)co_n * 9 * ci_n); ob = pk.alloc(co_n);
+        if (!(w && g && b && m && v)) return;
+        for (int co = 0; co < co_n; ++co) {
+            const double sc = (double)g[co] / sqrt((double)v[co] + eps);
+            pk.buf[ob + co] = (float)((((cb ? (double)cb[co] : 0.0) - (double)m[co]) * sc) + (double)b[co]);
+            for (int ci = 0; ci < ci_n; ++ci)
+                for (int k = 0; k < 9; ++k)
+                    pk.buf[ow + ((size_t)co * 9 + k) * ci_n + ci] = (float)((double)w[((size_t)co * ci_n + ci) * 9 + k] * sc);
+        }
+    };
+    const int ch[5] = {3, C / 8, C / 4, C / 2, C};
+    size_t sw[4], sb[4];
+    for (int l = 0; l < 4; ++l) {
+        const std::string p = "patch_embed.net." + std::to_string(2 * l) + ".";
+        fold_conv(T(p + "c.weight"), nullptr, T(p + "bn.weight"), T(p + "bn.bias"), T(p + "bn.running_mean"), T(p + "bn.running_var"), ch[l + 1], ch[l], sw[l], sb[l]);
+    }
+    struct BO { size_t v[12]; };
+    std::vector<BO> bo(c.depth);
+    for (int b = 0; b < c.depth; ++b) {
+        const std::string p = "blocks." + std::to_string(b) + ".";
+        const char* names[12] = {"norm1.weight", "norm1.bias", "attn.qkv.weight", "attn.qkv.bias", "attn.proj.weight", "attn.proj.bias",
+                                 "norm2.weight", "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight", "mlp.fc2.bias"};
+        const size_t cnt[12] = {(size_t)C, (size_t)C, (size_t)3 * C * C, (size_t)3 * C, (size_t)C * C, (size_t)C,
+                                (size_t)C, (size_t)C, (size_t)hid * C, (size_t)hid, (size_t)C * hid, (size_t)C};
+        for (int i = 0; i < 12; ++i) bo[b].v[i] = put(T(p + names[i]), cnt[i]);
+    }
+    const size_t o_ng = put(T("norm.weight"), C), o_nb = put(T("norm.bias"), C);
+    const size_t o_pz = put(T("pos_embed_z"), (size_t)kNz * C), o_px = put(T("pos_embed_x"), (size_t)kNx * C);
+    // head: layer 1 merged over the towers (ctr | offset | size), layers 2-4 per tower, conv5 rows ctr, off x, off y, size w, size h
+    const int hch[5] = {C, hc, hc / 2, hc / 4, hc / 8};
+    const size_t o_w1 = pk.alloc((size_t)3 * hc * 9 * C), o_b1 = pk.alloc((size_t)3 * hc);
+    size_t hw[3][3], hb[3][3];
+    for (int t = 0; t < 3; ++t) {
+        for (int i = 0; i < 4; ++i) {
+            const std::string p = std::string("box_head.conv") + std::to_string(i + 1) + "_" + kTowers[t] + ".";
+            size_t ow, ob;
+            fold_conv(T(p + "0.weight"), T(p + "0.bias"), T(p + "1.weight"), T(p + "1.bias"), T(p + "1.running_mean"), T(p + "1.running_var"),
+                      hch[i + 1], hch[i], ow, ob);
+            if (i == 0) {       // copy into the merged layer (alloc moves pk.buf: index, do not hold pointers)
+                for (size_t k = 0; k < (size_t)hc * 9 * C; ++k) pk.buf[o_w1 + (size_t)t * hc * 9 * C + k] = pk.buf[ow + k];
+                for (int k = 0; k < hc; ++k) pk.buf[o_b1 + (size_t)t * hc + k] = pk.buf[ob + k];
+            } else { hw[t][i - 1] = ow; hb[t][i - 1] = ob; }
+        }
+    }
+    const size_t o_w5 = pk.alloc((size_t)5 * hch[4]), o_b5 = pk.alloc(5);
+    {
+        const int row0[3] = {0, 1, 3}, outs[3] = {1, 2, 2};
+        for (int t = 0; t < 3; ++t) {
+            const std::string p = std::string("box_head.conv5_") + kTowers[t] + ".";
+            const float *w = T(p + "weight"), *b = T(p + "bias");
+            if (!(w && b)) continue;
+            for (int o = 0; o < outs[t]; ++o) {
+                pk.buf[o_b5 + row0[t] + o] = b[o];
+                for (int k = 0; k < hch[4]; ++k) pk.buf[o_w5 + (size_t)(row0[t] + o) * hch[4] + k] = w[(size_t)o * hch[4] + k];
+            }
+        }
+    }
+    if (!missing.empty()) return fail(h, VT_ERR_WEIGHTS, "missing tensors: %s", missing.c_str());
+    const size_t o_hann = pk.alloc(256), o_lut = pk.alloc(768);
+    fill_hann_and_lut(h, &pk.buf[o_hann], &pk.buf[o_lut]);
+
+    if (h->d_weights && h->weights_floats < pk.buf.size()) { cudaFree(h->d_weights); h->d_weights = nullptr; }
+    if (!h->d_weights) {
+        VT_CUDA(h, cudaMalloc((void**)&h->d_weights, pk.buf.size() * sizeof(float)));
+        h->weights_floats = pk.buf.size();
+    }
+    VT_CUDA(h, cudaMemcpyAsync(h->d_weights, pk.buf.data(), pk.buf.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    VT_CUDA(h, cudaStreamSynchronize(st));
+    const float* base = h->d_weights;
+    GenModelW& g = h->gw;
+    for (int l = 0; l < 4; ++l) { g.stem_w[l] = base + sw[l]; g.stem_b[l] = base + sb[l]; }
+    for (int b = 0; b < c.depth; ++b) {
+        const float* q[12];
+        for (int i = 0; i < 12; ++i) q[i] = base + bo[b].v[i];
+        g.blk[b] = GenBlockW{q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8], q[9], q[10], q[11]};
+    }
+    g.norm_g = base + o_ng; g.norm_b = base + o_nb; g.pos_z = base + o_pz; g.pos_x = base + o_px;
+    g.head_w1 = base + o_w1; g.head_b1 = base + o_b1;
+    for (int t = 0; t < 3; ++t)
+        for (int l = 0; l < 3; ++l) { g.head_w[t][l] = base + hw[t][l]; g.head_b[t][l] = base + hb[t][l]; }
+    g.head_w5 = base + o_w5; g.head_b5 = base + o_b5;
+    g.hann = base + o_hann;
+    h->mw.hann = base + o_hann; h->mw.lut = base + o_lut;         // the crop kernel reads the table through ModelW
+    h->finalized = true;
+    return VT_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -201,11 +333,15 @@ const char* vt_last_error(VtHandle h) { return h ? h->err.c_str() : g_create_err
 int vt_create(const VtConfig* cfg, VtHandle* out) {
     if (!cfg || !out) return fail(nullptr, VT_ERR_INVALID_ARG, "vt_create: null argument");
     *out = nullptr;
-    if (cfg->embed_dim != kC || cfg->num_heads != 1 || cfg->depth != kDepth || cfg->mlp_ratio != 4 ||
-        cfg->head_channels != kHeadC || cfg->stride != 16 || cfg->template_size != kTz || cfg->search_size != kSx)
+    const bool fast = cfg->embed_dim == kC && cfg->num_heads == 1 && cfg->depth == kDepth && cfg->head_channels == kHeadC;
+    if (cfg->mlp_ratio != 4 || cfg->stride != 16 || cfg->template_size != kTz || cfg->search_size != kSx)
         return fail(nullptr, VT_ERR_UNSUPPORTED,
-                    "unsupported configuration (this build has kernels for vit_48_h32: C=48, heads=1, depth=3, "
-                    "mlp_ratio=4, head=32, stride=16, template 128, search 256)");
+                    "unsupported configuration (this build needs mlp_ratio=4, stride=16, template 128, search 256)");
+    if (!fast && (cfg->embed_dim < 8 || cfg->embed_dim % 8 != 0 || cfg->num_heads < 1 || cfg->embed_dim % cfg->num_heads != 0 ||
+                  cfg->depth < 1 || cfg->depth > kGenMaxDepth || cfg->head_channels < 8 || cfg->head_channels % 8 != 0))
+        return fail(nullptr, VT_ERR_UNSUPPORTED,
+                    "unsupported configuration (embed_dim and head_channels must be multiples of 8, embed_dim divisible by "
+                    "num_heads, 1 <= depth <= %d)", kGenMaxDepth);
     if (cfg->max_tracks < 1 || !(cfg->template_factor > 0) || !(cfg->search_factor > 0))
         return fail(nullptr, VT_ERR_INVALID_ARG, "vt_create: max_tracks >= 1 and positive crop factors required");
     if (cfg->blocks_impl != VT_BLOCKS_SIMT_FP32 && cfg->blocks_impl != VT_BLOCKS_TCGEN05)
@@ -223,23 +359,35 @@ int vt_create(const VtConfig* cfg, VtHandle* out) {
     VtHandle h = new VtContext();
     h->cfg = *cfg;
     h->num_sms = prop.multiProcessorCount;
-    h->chunk = cfg->chunk_tracks > 0 ? cfg->chunk_tracks : 1024;
+    h->generic = !fast;
+    h->chunk = cfg->chunk_tracks > 0 ? cfg->chunk_tracks : (fast ? 1024 : 8);
     if (h->chunk > cfg->max_tracks) h->chunk = cfg->max_tracks;
     if (cudaSetDevice(cfg->device) != cudaSuccess) { delete h; return fail(nullptr, VT_ERR_CUDA, "cudaSetDevice failed"); }
-    const size_t ch = h->chunk, mt = cfg->max_tracks;
+    const size_t ch = h->chunk, mt = cfg->max_tracks, Cd = cfg->embed_dim;
     cudaError_t e = cudaSuccess;
     auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
-    A((void**)&h->d_scratch, ch * stem_scratch_floats(kSx) * sizeof(float));
-    if (cfg->blocks_impl == VT_BLOCKS_TCGEN05) {
-        const size_t pb = ch * tc_planes_bytes_per_track();
-        A((void**)&h->d_planes, pb);
-        if (e == cudaSuccess) e = cudaMemset(h->d_planes, 0, pb);
+    if (fast) {
+        A((void**)&h->d_scratch, ch * stem_scratch_floats(kSx) * sizeof(float));
+        if (cfg->blocks_impl == VT_BLOCKS_TCGEN05) {
+            const size_t pb = ch * tc_planes_bytes_per_track();
+            A((void**)&h->d_planes, pb);
+            if (e == cudaSuccess) e = cudaMemset(h->d_planes, 0, pb);
+        }
+        A((void**)&h->d_tokz, ch * kNz * kC * sizeof(float));
+        A((void**)&h->d_tokx, mt * kNx * kC * sizeof(float));     // whole-step buffers: blocks + head run once per step
+        A((void**)&h->d_tok, mt * kN * kC * sizeof(float));
+    } else {
+        h->gw.C = cfg->embed_dim; h->gw.heads = cfg->num_heads; h->gw.depth = cfg->depth; h->gw.hc = cfg->head_channels;
+        size_t off[17];
+        const size_t tot = gen_work_floats(h->gw, h->chunk, off);
+        A((void**)&h->d_gwork, tot * sizeof(float));
+        float** members[17] = {&h->gws.crop, &h->gws.col, &h->gws.act1, &h->gws.act2, &h->gws.act3, &h->gws.tokz, &h->gws.tok, &h->gws.ln,
+                               &h->gws.qkv, &h->gws.scores, &h->gws.attn, &h->gws.hid, &h->gws.t1, &h->gws.t2, &h->gws.t3, &h->gws.t4, &h->gws.raw5};
+        for (int i = 0; i < 17; ++i) *members[i] = h->d_gwork ? h->d_gwork + off[i] : nullptr;
+        h->gws.chunk = h->chunk;
     }
-    A((void**)&h->d_tokz, ch * kNz * kC * sizeof(float));
-    A((void**)&h->d_tokx, mt * kNx * kC * sizeof(float));     // whole-step buffers: blocks + head run once per step
-    A((void**)&h->d_tok, mt * kN * kC * sizeof(float));
     A((void**)&h->d_state, mt * 4 * sizeof(double));
-    A((void**)&h->d_tmpl, mt * kNz * kC * sizeof(float));
+    A((void**)&h->d_tmpl, mt * kNz * Cd * sizeof(float));
     A((void**)&h->d_status, mt * sizeof(int32_t));
     A((void**)&h->d_maps, mt * 1280 * sizeof(float));
     if (e == cudaSuccess) e = cudaMemset(h->d_state, 0, mt * 4 * sizeof(double));
@@ -290,6 +438,7 @@ int vt_finalize_weights(VtHandle h, void* stream) {
     if (!h) return VT_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     VT_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (h->generic) return finalize_generic(h, st);
     std::string missing;
     auto T = [&](const std::string& n) -> const float* {
         auto it = h->tensors.find(n);
@@ -479,26 +628,7 @@ int vt_finalize_weights(VtHandle h, void* stream) {
 
     // ---- Hann window (hann.py:6-16) and normalisation table (data_utils.py:8-14) -----------------
     const size_t o_hann = slot(256), o_lut = slot(768);
-    auto it = h->tensors.find("tracker.output_window");
-    if (it != h->tensors.end()) {
-        copyv(o_hann, it->second.data.data(), 256);
-    } else {
-        float w1[16];
-        const float step = (float)(2.0 * M_PI / 17.0);
-        for (int k = 0; k < 16; ++k) w1[k] = 0.5f * (1.f - cosf(step * (float)(k + 1)));
-        for (int y = 0; y < 16; ++y)
-            for (int x = 0; x < 16; ++x) pk.buf[o_hann + y * 16 + x] = w1[y] * w1[x];
-    }
-    {
-        const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
-        for (int c = 0; c < 3; ++c)
-            for (int v = 0; v < 256; ++v) {
-                volatile float a = (float)v / 255.0f;        // (x / 255.0) - mean) / std, each step rounded to fp32
-                volatile float d = a - mean[c];
-                volatile float r = d / stdv[c];
-                pk.buf[o_lut + c * 256 + v] = r;
-            }
-    }
+    fill_hann_and_lut(h, &pk.buf[o_hann], &pk.buf[o_lut]);
 
     if (h->d_weights && h->weights_floats < pk.buf.size()) { cudaFree(h->d_weights); h->d_weights = nullptr; }
     if (!h->d_weights) {
@@ -557,6 +687,24 @@ int vt_forward(VtHandle h, const float* z, const float* x, int32_t n, float* pre
     if (!z || !x || n < 0) return fail(h, VT_ERR_INVALID_ARG, "vt_forward: null input or negative n");
     cudaStream_t st = (cudaStream_t)stream;
     VT_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (h->generic) {
+        const int C = h->cfg.embed_dim;
+        const size_t gtap = (size_t)n * kN * C;
+        for (int first = 0; first < n; first += h->chunk) {
+            const int m = (n - first < h->chunk) ? n - first : h->chunk;
+            VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_forward/stem(z)", gen_launch_stem(z + (size_t)first * 3 * kTz * kTz, kTz, m, h->gw, h->gws, h->gws.tok, kN, 0, st));
+            VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_forward/stem(x)", gen_launch_stem(x + (size_t)first * 3 * kSx * kSx, kSx, m, h->gw, h->gws, h->gws.tok, kN, kNz, st));
+            HeadArgs a{};
+            a.n = m;
+            a.pred_boxes = pred_boxes ? pred_boxes + (size_t)first * 4 : nullptr;
+            a.score_map = score_map ? score_map + (size_t)first * 256 : nullptr;
+            a.size_map = size_map ? size_map + (size_t)first * 512 : nullptr;
+            a.offset_map = offset_map ? offset_map + (size_t)first * 512 : nullptr;
+            VT_LAUNCH(h, VT_STAGE_BLOCKS, m, st, "vt_forward/blocks+head",
+                      gen_launch_blocks_head(h->gws.tok, m, h->gw, h->gws, a, taps ? taps + (size_t)first * kN * C : nullptr, gtap, st));
+        }
+        return VT_OK;
+    }
     const size_t tap_stride = (size_t)n * kN * kC;
     for (int first = 0; first < n; first += h->chunk) {
         const int m = (n - first < h->chunk) ? n - first : h->chunk;
@@ -596,7 +744,15 @@ int vt_tracks_init(VtHandle h, const uint8_t* frames, const int64_t* frame_offse
     if (first < 0 || n < 0 || first + n > h->cfg.max_tracks) return fail(h, VT_ERR_INVALID_ARG, "vt_tracks_init: tracks [%d, %d) exceed max_tracks %d", first, first + n, h->cfg.max_tracks);
     cudaStream_t st = (cudaStream_t)stream;
     VT_CUDA(h, cudaSetDevice(h->cfg.device));
-    for (int c0 = 0; c0 < n; c0 += h->chunk) {
+    for (int c0 = 0; c0 < n && h->generic; c0 += h->chunk) {
+        const int m = (n - c0 < h->chunk) ? n - c0 : h->chunk;
+        VT_LAUNCH(h, VT_STAGE_CROP, m, st, "vt_tracks_init/crop",
+                  launch_crop_normalize(frames, frame_offsets + c0, frame_hw + 2 * c0, boxes_xywh + 4 * c0, h->cfg.template_factor, kTz, m, h->mw.lut,
+                                        h->gws.crop, nullptr, nullptr, nullptr, h->d_status + first + c0, st));
+        VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_tracks_init/stem",
+                  gen_launch_stem(h->gws.crop, kTz, m, h->gw, h->gws, h->d_tmpl + (size_t)(first + c0) * kNz * h->cfg.embed_dim, kNz, 0, st));
+    }
+    for (int c0 = 0; c0 < n && !h->generic; c0 += h->chunk) {
         const int m = (n - c0 < h->chunk) ? n - c0 : h->chunk;
         VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_tracks_init/crop+stem",
                   launch_crop_stem(frames, frame_offsets + c0, frame_hw + 2 * c0, boxes_xywh + 4 * c0, h->cfg.template_factor, kTz, m,
@@ -617,6 +773,35 @@ int vt_tracks_step(VtHandle h, const uint8_t* frames, const int64_t* frame_offse
     if (first < 0 || n < 0 || first + n > h->cfg.max_tracks) return fail(h, VT_ERR_INVALID_ARG, "vt_tracks_step: tracks [%d, %d) exceed max_tracks %d", first, first + n, h->cfg.max_tracks);
     cudaStream_t st = (cudaStream_t)stream;
     VT_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (h->generic) {
+        // every stage runs per chunk: crop -> stem into the chunk's token buffer, cached template tokens copied in front
+        const int C = h->cfg.embed_dim;
+        for (int c0 = 0; c0 < n; c0 += h->chunk) {
+            const int m = (n - c0 < h->chunk) ? n - c0 : h->chunk;
+            const int t0 = first + c0;
+            VT_LAUNCH(h, VT_STAGE_CROP, m, st, "vt_tracks_step/crop",
+                      launch_crop_normalize(frames, frame_offsets + c0, frame_hw + 2 * c0, h->d_state + (size_t)t0 * 4, h->cfg.search_factor, kSx, m,
+                                            h->mw.lut, h->gws.crop, nullptr, nullptr, nullptr, h->d_status + t0, st));
+            VT_CUDA(h, cudaMemcpy2DAsync(h->gws.tok, (size_t)kN * C * sizeof(float), h->d_tmpl + (size_t)t0 * kNz * C, (size_t)kNz * C * sizeof(float),
+                                         (size_t)kNz * C * sizeof(float), m, cudaMemcpyDeviceToDevice, st));
+            VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_tracks_step/stem", gen_launch_stem(h->gws.crop, kSx, m, h->gw, h->gws, h->gws.tok, kN, kNz, st));
+            HeadArgs a{};
+            a.n = m;
+            a.score_map = h->d_maps + (size_t)t0 * 256;
+            a.size_map = h->d_maps + (size_t)h->cfg.max_tracks * 256 + (size_t)t0 * 512;
+            a.offset_map = h->d_maps + (size_t)h->cfg.max_tracks * 768 + (size_t)t0 * 512;
+            a.state = h->d_state + (size_t)t0 * 4;
+            a.frame_hw = frame_hw + 2 * c0;
+            a.status = h->d_status + t0;
+            a.out_boxes = out_boxes + (size_t)c0 * 5;
+            a.out_detail = out_detail ? out_detail + (size_t)c0 * 8 : nullptr;
+            a.update_state = update_state;
+            a.search_factor = h->cfg.search_factor;
+            VT_LAUNCH(h, VT_STAGE_BLOCKS, m, st, "vt_tracks_step/blocks+head", gen_launch_blocks_head(h->gws.tok, m, h->gw, h->gws, a, nullptr, 0, st));
+        }
+        h->last_first = first; h->last_n = n;
+        return VT_OK;
+    }
     // crop + stem run per chunk (their intermediates are large); blocks + head run once over all n tracks
     for (int c0 = 0; c0 < n; c0 += h->chunk) {
         const int m = (n - c0 < h->chunk) ? n - c0 : h->chunk;

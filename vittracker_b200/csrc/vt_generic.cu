@@ -1,0 +1,342 @@
+// Generic-configuration path: OstrackDist.forward for ANY member of the vit_dist family (embed dim C, heads, depth,
+// head width), used for every configuration other than vit_48_h32 - in particular the widest one (C = 768, 12 heads,
+// depth 12, head 256; BASELINE configs[4]).  Same arithmetic as the reference graph, fp32 on CUDA cores:
+//   LevitPatchEmbedding   lib/models/vit_dist/vit_dist.py:10-54   conv3x3 s2 + BN(eval, folded) [+ Hardswish] x4
+//   OstrackDist.forward   lib/models/vit_dist/vit_dist.py:77-100  pos-embed add, cat(z, x), blocks, LayerNorm
+//   timm Block            tracking/onnxexport.py:126-225          LN -> qkv -> MHSA (h heads) -> proj, LN -> fc1 -> GELU -> fc2
+//   CenterPredictor       lib/models/layers/head.py:98-201        three conv towers, sigmoid / clamp
+// Convolutions are im2col (NHWC, k = (ky, kx, ci)) + one tiled GEMM with a fused bias / activation / residual epilogue;
+// attention is two batched GEMMs (batch = track x head) around a row softmax.  The decode is the code the fused head
+// kernels use (vt_decode.cuh).  This path favours coverage over speed; the tuned kernels are vit_48_h32's.
+#include "vt_decode.cuh"
+#include "vt_internal.h"
+
+namespace vt {
+
+namespace {
+
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_HSWISH = 2, ACT_GELU = 3 };
+
+struct GemmArgs {
+    const float* A; const float* B; float* C; const float* bias; const float* R;
+    int M, N, K;
+    int lda, ldb, ldc, ldr;
+    // batch z -> (z / nh, z % nh); element offset of each operand = (z / nh) * s?1 + (z % nh) * s?2
+    int nh;
+    long long sa1, sa2, sb1, sb2, sc1, sc2, sr1, sr2;
+    int rmod;            // > 0: residual row = m % rmod (broadcast over groups of rows, e.g. the positional embedding)
+    float alpha;
+    int act;
+};
+
+constexpr int kBM = 64, kBN = 64, kBK = 16;
+
+// C[m][n] = act(alpha * sum_k A[m][k] * B(n, k) + bias[n]) + R[m][n];  B(n, k) = B[n * ldb + k] (NN = false) or B[k * ldb + n]
+template <bool NN>
+__global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
+    __shared__ float As[kBK][kBM + 4];
+    __shared__ float Bs[kBK][kBN + 4];
+    const int z = blockIdx.z, z1 = z / g.nh, z2 = z % g.nh;
+    const float* A = g.A + z1 * g.sa1 + z2 * g.sa2;
+    const float* B = g.B + z1 * g.sb1 + z2 * g.sb2;
+    float* C = g.C + z1 * g.sc1 + z2 * g.sc2;
+    const float* R = g.R ? g.R + z1 * g.sr1 + z2 * g.sr2 : nullptr;
+    const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < g.K; k0 += kBK) {
+        {   // A tile: 64 rows x 16 k; thread -> row tid / 4, k (tid % 4) * 4 .. + 3
+            const int r = tid >> 2, c = (tid & 3) * 4;
+            const int m = m0 + r;
+            const float* ap = A + (size_t)m * g.lda + k0 + c;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) As[c + i][r] = (m < g.M && k0 + c + i < g.K) ? __ldg(ap + i) : 0.f;
+        }
+        if (!NN) {
+            const int r = tid >> 2, c = (tid & 3) * 4;
+            const int n = n0 + r;
+            const float* bp = B + (size_t)n * g.ldb + k0 + c;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) Bs[c + i][r] = (n < g.N && k0 + c + i < g.K) ? __ldg(bp + i) : 0.f;
+        } else {
+            const int kr = tid >> 4, c = (tid & 15) * 4;
+            const float* bp = B + (size_t)(k0 + kr) * g.ldb + n0 + c;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) Bs[kr][c + i] = (k0 + kr < g.K && n0 + c + i < g.N) ? __ldg(bp + i) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kBK; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= g.N) continue;
+            float v = acc[i][j] * g.alpha;
+            if (g.bias) v += __ldg(g.bias + n);
+            if (g.act == ACT_RELU) v = fmaxf(v, 0.f);
+            else if (g.act == ACT_HSWISH) v = v * fminf(fmaxf(v + 3.f, 0.f), 6.f) / 6.f;
+            else if (g.act == ACT_GELU) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+            if (R) v += R[(size_t)(g.rmod > 0 ? m % g.rmod : m) * g.ldr + n];
+            C[(size_t)m * g.ldc + n] = v;
+        }
+    }
+}
+
+int run_gemm(const GemmArgs& g, int batch, bool nn, cudaStream_t st) {
+    if (g.M <= 0 || g.N <= 0 || batch <= 0) return 0;
+    dim3 grid((g.N + kBN - 1) / kBN, (g.M + kBM - 1) / kBM, batch);
+    if (nn) sgemm_kernel<true><<<grid, 256, 0, st>>>(g);
+    else sgemm_kernel<false><<<grid, 256, 0, st>>>(g);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+GemmArgs gemm_args(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K, const float* bias, int act) {
+    GemmArgs g{};
+    g.A = A; g.B = B; g.C = C; g.bias = bias; g.R = nullptr;
+    g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldc = ldc; g.ldr = 0;
+    g.nh = 1; g.alpha = 1.f; g.act = act; g.rmod = 0;
+    return g;
+}
+
+// 3x3 patches, pad 1: out[(b * Ho + oy) * Wo + ox][(ky * 3 + kx) * Cin + ci] = in(b, stride * oy + ky - 1, stride * ox + kx - 1, ci)
+//   NCHW: in[((b * Cin + ci) * H + y) * W + x]      NHWC: in[b * bstride + (y * W + x) * ld + choff + ci]
+template <bool NCHW>
+__global__ void __launch_bounds__(256) im2col3x3_kernel(const float* __restrict__ in, long long bstride, int ld, int choff, int Cin,
+                                                       int H, int W, int stride, int Ho, int Wo, float* __restrict__ out, long long total) {
+    const int K = 9 * Cin;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int k = (int)(i % K);
+        const long long row = i / K;
+        const int ci = k % Cin, tap = k / Cin, ky = tap / 3, kx = tap % 3;
+        const int ox = (int)(row % Wo), oy = (int)((row / Wo) % Ho);
+        const long long b = row / ((long long)Wo * Ho);
+        const int y = stride * oy + ky - 1, x = stride * ox + kx - 1;
+        float v = 0.f;
+        if (y >= 0 && y < H && x >= 0 && x < W)
+            v = NCHW ? __ldg(in + ((b * Cin + ci) * H + y) * W + x) : __ldg(in + b * bstride + ((long long)y * W + x) * ld + choff + ci);
+        out[i] = v;
+    }
+}
+
+int run_im2col(bool nchw, const float* in, long long bstride, int ld, int choff, int Cin, int H, int stride, int n, float* out, cudaStream_t st) {
+    const int Ho = (H + 2 - 3) / stride + 1;
+    const long long total = (long long)n * Ho * Ho * 9 * Cin;
+    if (total <= 0) return 0;
+    const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    if (nchw) im2col3x3_kernel<true><<<blocks, 256, 0, st>>>(in, bstride, ld, choff, Cin, H, H, stride, Ho, Ho, out, total);
+    else im2col3x3_kernel<false><<<blocks, 256, 0, st>>>(in, bstride, ld, choff, Cin, H, H, stride, Ho, Ho, out, total);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// LayerNorm over the last dim C (eps 1e-5), one warp per row; two passes over the row (mean, then variance) like torch
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ g,
+                                                       const float* __restrict__ b, int rows, int C) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* x = in + (size_t)row * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += x[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)C;
+    float v = 0.f;
+    for (int c = lane; c < C; c += 32) { const float d = x[c] - mean; v = fmaf(d, d, v); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const float rstd = rsqrtf(v / (float)C + kLnEps);
+    float* y = out + (size_t)row * C;
+    for (int c = lane; c < C; c += 32) y[c] = (x[c] - mean) * rstd * __ldg(g + c) + __ldg(b + c);
+}
+
+// softmax over rows of `cols` values in place, one warp per row
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ s, long long rows, int cols) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float* x = s + row * cols;
+    float m = -INFINITY;
+    for (int c = lane; c < cols; c += 32) m = fmaxf(m, x[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float l = 0.f;
+    for (int c = lane; c < cols; c += 32) { const float e = expf(x[c] - m); x[c] = e; l += e; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    const float inv = 1.f / l;
+    for (int c = lane; c < cols; c += 32) x[c] *= inv;
+}
+
+// raw conv5 outputs [n][256][5] (ctr, offset x, offset y, size w, size h) -> maps, arg-max, boxes, tracker state
+__global__ void __launch_bounds__(256) gen_decode_kernel(const float* __restrict__ raw5, HeadArgs a, const float* __restrict__ hann) {
+    __shared__ float maps[6 * 256];
+    __shared__ float red[32];
+    const int trk = blockIdx.x, tid = threadIdx.x;
+    float* m_score = maps; float* m_size = maps + 256; float* m_off = maps + 768; float* m_resp = maps + 1280;
+    const float* r = raw5 + ((size_t)trk * 256 + tid) * 5;
+    const float sc = sigmoid_clamp(r[0]), sw = sigmoid_clamp(r[3]), sh = sigmoid_clamp(r[4]);
+    const float ox = r[1], oy = r[2];
+    m_score[tid] = sc; m_size[tid] = sw; m_size[256 + tid] = sh; m_off[tid] = ox; m_off[256 + tid] = oy;
+    m_resp[tid] = __ldg(hann + tid) * sc;
+    if (a.score_map) a.score_map[(size_t)trk * 256 + tid] = sc;
+    if (a.size_map) { a.size_map[(size_t)trk * 512 + tid] = sw; a.size_map[(size_t)trk * 512 + 256 + tid] = sh; }
+    if (a.offset_map) { a.offset_map[(size_t)trk * 512 + tid] = ox; a.offset_map[(size_t)trk * 512 + 256 + tid] = oy; }
+    __syncthreads();
+    float raw_max, win_max; int raw_idx, win_idx;
+    decode_argmax(m_score, m_resp, red, raw_max, raw_idx, win_max, win_idx);
+    if (tid == 0) decode_box(a, trk, m_size, m_off, raw_max, raw_idx, win_max, win_idx);
+}
+
+#define GEN_TRY(expr)                      \
+    do {                                   \
+        const int r__ = (expr);            \
+        if (r__ < 0) return r__;           \
+        total += r__;                      \
+    } while (0)
+
+}  // namespace
+
+// workspace plan for `chunk` tracks; offsets[i] in floats, order = the pointer members of GenWork
+size_t gen_work_floats(const GenModelW& w, int chunk, size_t* off) {
+    const size_t C = w.C, hc = w.hc, n = chunk;
+    const size_t sizes[17] = {
+        n * 3 * kSx * kSx,                                    // crop
+        n * 4096 * 9 * (C / 8) > n * 256 * 9 * C ? n * 4096 * 9 * (C / 8) : n * 256 * 9 * C,   // col (largest: conv2 or head conv1; conv1 is 16384 x 27)
+        n * 16384 * (C / 8), n * 4096 * (C / 4), n * 1024 * (C / 2),              // act1..3
+        n * kNz * C, n * kN * C, n * kN * C, n * kN * 3 * C,                    // tokz, tok, ln, qkv
+        n * w.heads * (size_t)kN * kN, n * kN * C, n * kN * 4 * C,              // scores, attn, hid
+        n * 256 * 3 * hc, n * 256 * 3 * (hc / 2), n * 256 * 3 * (hc / 4), n * 256 * 3 * (hc / 8), n * 256 * 5};   // t1..t4, raw5
+    size_t tot = 0;
+    for (int i = 0; i < 17; ++i) {
+        size_t s = sizes[i];
+        if (i == 1 && s < n * 16384 * 27) s = n * 16384 * 27;
+        off[i] = tot;
+        tot += (s + 63) / 64 * 64;
+    }
+    return tot;
+}
+
+int gen_launch_stem(const float* img, int S, int n, const GenModelW& w, const GenWork& ws, float* tokens, int tok_stride_rows,
+                    int tok_off, cudaStream_t st) {
+    if (n <= 0) return 0;
+    int total = 0;
+    const int C = w.C;
+    const int ch[5] = {3, C / 8, C / 4, C / 2, C};
+    float* acts[3] = {ws.act1, ws.act2, ws.act3};
+    int H = S;
+    for (int l = 0; l < 4; ++l) {
+        const int Ho = H / 2, K = 9 * ch[l];
+        if (l == 0) GEN_TRY(run_im2col(true, img, 0, 0, 0, 3, H, 2, n, ws.col, st));
+        else GEN_TRY(run_im2col(false, acts[l - 1], (long long)H * H * ch[l], ch[l], 0, ch[l], H, 2, n, ws.col, st));
+        if (l < 3) {
+            GemmArgs g = gemm_args(ws.col, K, w.stem_w[l], K, acts[l], ch[l + 1], n * Ho * Ho, ch[l + 1], K, w.stem_b[l], ACT_HSWISH);
+            GEN_TRY(run_gemm(g, 1, false, st));
+        } else {
+            // last layer: one GEMM per track (batch), rows = tokens, + positional embedding (broadcast residual)
+            GemmArgs g = gemm_args(ws.col, K, w.stem_w[l], K, tokens + (size_t)tok_off * C, C, Ho * Ho, C, K, w.stem_b[l], ACT_NONE);
+            g.sa1 = (long long)Ho * Ho * K; g.sc1 = (long long)tok_stride_rows * C;
+            g.R = (S == kSx) ? w.pos_x : w.pos_z; g.ldr = C;
+            GEN_TRY(run_gemm(g, n, false, st));
+        }
+        H = Ho;
+    }
+    return total;
+}
+
+int gen_launch_blocks_head(float* tokens, int n, const GenModelW& w, const GenWork& ws, const HeadArgs& a, float* taps,
+                           size_t tap_stride, cudaStream_t st) {
+    if (n <= 0) return 0;
+    int total = 0;
+    const int C = w.C, hd = C / w.heads, rows = n * kN;
+    const size_t tok_bytes = (size_t)rows * C * sizeof(float);
+    auto ln = [&](const float* in, float* out, const float* g, const float* b) {
+        layernorm_kernel<<<(rows + 7) / 8, 256, 0, st>>>(in, out, g, b, rows, C);
+        return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    };
+    if (taps && cudaMemcpyAsync(taps, tokens, tok_bytes, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return -1;
+    for (int b = 0; b < w.depth; ++b) {
+        const GenBlockW& B = w.blk[b];
+        GEN_TRY(ln(tokens, ws.ln, B.ln1g, B.ln1b));
+        GEN_TRY(run_gemm(gemm_args(ws.ln, C, B.wqkv, C, ws.qkv, 3 * C, rows, 3 * C, C, B.bqkv, ACT_NONE), 1, false, st));
+        {   // scores[b][h] = (q k^T) * hd^-0.5, batch = track x head
+            GemmArgs g = gemm_args(ws.qkv, 3 * C, ws.qkv + C, 3 * C, ws.scores, kN, kN, kN, hd, nullptr, ACT_NONE);
+            g.nh = w.heads;
+            g.sa1 = g.sb1 = (long long)kN * 3 * C; g.sa2 = g.sb2 = hd;
+            g.sc1 = (long long)w.heads * kN * kN; g.sc2 = (long long)kN * kN;
+            g.alpha = 1.f / sqrtf((float)hd);
+            GEN_TRY(run_gemm(g, n * w.heads, false, st));
+        }
+        {
+            const long long srows = (long long)n * w.heads * kN;
+            softmax_rows_kernel<<<(unsigned)((srows + 7) / 8), 256, 0, st>>>(ws.scores, srows, kN);
+            if (cudaGetLastError() != cudaSuccess) return -1;
+            ++total;
+        }
+        {   // attn[b][:, h] = P V, V = qkv[..., 2C + h hd ...] as [key][hd]
+            GemmArgs g = gemm_args(ws.scores, kN, ws.qkv + 2 * C, 3 * C, ws.attn, C, kN, hd, kN, nullptr, ACT_NONE);
+            g.nh = w.heads;
+            g.sa1 = (long long)w.heads * kN * kN; g.sa2 = (long long)kN * kN;
+            g.sb1 = (long long)kN * 3 * C; g.sb2 = hd;
+            g.sc1 = (long long)kN * C; g.sc2 = hd;
+            GEN_TRY(run_gemm(g, n * w.heads, true, st));
+        }
+        {   // x = x + proj(attn)
+            GemmArgs g = gemm_args(ws.attn, C, B.wproj, C, tokens, C, rows, C, C, B.bproj, ACT_NONE);
+            g.R = tokens; g.ldr = C;
+            GEN_TRY(run_gemm(g, 1, false, st));
+        }
+        GEN_TRY(ln(tokens, ws.ln, B.ln2g, B.ln2b));
+        GEN_TRY(run_gemm(gemm_args(ws.ln, C, B.wfc1, C, ws.hid, 4 * C, rows, 4 * C, C, B.bfc1, ACT_GELU), 1, false, st));
+        {
+            GemmArgs g = gemm_args(ws.hid, 4 * C, B.wfc2, 4 * C, tokens, C, rows, C, 4 * C, B.bfc2, ACT_NONE);
+            g.R = tokens; g.ldr = C;
+            GEN_TRY(run_gemm(g, 1, false, st));
+        }
+        if (taps && cudaMemcpyAsync(taps + (size_t)(b + 1) * tap_stride, tokens, tok_bytes, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return -1;
+    }
+    GEN_TRY(ln(tokens, ws.ln, w.norm_g, w.norm_b));
+    if (taps && cudaMemcpyAsync(taps + (size_t)(w.depth + 1) * tap_stride, ws.ln, tok_bytes, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return -1;
+
+    // ---- CENTER head on the 16 x 16 search feature map (tokens 64..319 of every track, NHWC) ----
+    const int hc = w.hc, prow = n * 256;
+    const int co[5] = {C, hc, hc / 2, hc / 4, hc / 8};
+    GEN_TRY(run_im2col(false, ws.ln + (size_t)kNz * C, (long long)kN * C, C, 0, C, kFeat, 1, n, ws.col, st));
+    GEN_TRY(run_gemm(gemm_args(ws.col, 9 * C, w.head_w1, 9 * C, ws.t1, 3 * hc, prow, 3 * hc, 9 * C, w.head_b1, ACT_RELU), 1, false, st));
+    float* tbuf[4] = {ws.t1, ws.t2, ws.t3, ws.t4};
+    for (int l = 1; l < 4; ++l)
+        for (int t = 0; t < 3; ++t) {
+            const int ci = co[l], cn = co[l + 1];
+            GEN_TRY(run_im2col(false, tbuf[l - 1], (long long)256 * 3 * ci, 3 * ci, t * ci, ci, kFeat, 1, n, ws.col, st));
+            GEN_TRY(run_gemm(gemm_args(ws.col, 9 * ci, w.head_w[t][l - 1], 9 * ci, tbuf[l] + t * cn, 3 * cn, prow, cn, 9 * ci, w.head_b[t][l - 1], ACT_RELU), 1, false, st));
+        }
+    {   // conv5 (1x1): tower t -> its columns of raw5 (ctr 0 | offset 1, 2 | size 3, 4)
+        const int c4 = co[4];
+        const int col0[3] = {0, 1, 3}, outs[3] = {1, 2, 2};
+        for (int t = 0; t < 3; ++t)
+            GEN_TRY(run_gemm(gemm_args(ws.t4 + t * c4, 3 * c4, w.head_w5 + (size_t)col0[t] * c4, c4, ws.raw5 + col0[t], 5, prow, outs[t], c4,
+                                       w.head_b5 + col0[t], ACT_NONE), 1, false, st));
+    }
+    gen_decode_kernel<<<n, 256, 0, st>>>(ws.raw5, a, w.hann);
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    return total + 1;
+}
+
+}  // namespace vt

@@ -18,6 +18,7 @@
 #include "vt_geom.cuh"
 #include "vt_internal.h"
 #include "vt_tc.cuh"
+#include "vt_decode.cuh"
 
 namespace vt {
 
@@ -143,30 +144,6 @@ __device__ __forceinline__ void head_conv(const float* in, float* outp, const fl
     __syncthreads();
 }
 
-// arg-max with first-index tie-break over 256 values (one per thread); result broadcast to all threads.
-__device__ __forceinline__ void block_argmax256(float v, int idx, float* red, float& best, int& best_idx) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-        if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
-    }
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = v; red[8 + (threadIdx.x >> 5)] = __int_as_float(idx); }
-    __syncthreads();
-    best = red[0]; best_idx = __float_as_int(red[8]);
-#pragma unroll
-    for (int k = 1; k < 8; ++k) {
-        const float ov = red[k]; const int oi = __float_as_int(red[8 + k]);
-        if (ov > best || (ov == best && oi < best_idx)) { best = ov; best_idx = oi; }
-    }
-}
-
-__device__ __forceinline__ float sigmoid_clamp(float v) {
-    const float s = 1.f / (1.f + expf(-v));
-    return fminf(fmaxf(s, 1e-4f), 0.9999f);               // torch.clamp(x.sigmoid_(), 1e-4, 1 - 1e-4)
-}
-
 // Final LayerNorm of one token row (vit_dist.py:94); optionally stores the normalised row (tokens_norm tap).
 __device__ __forceinline__ void head_norm_row(const HeadArgs& a, const ModelW& w, int trk, int row, float (&y)[kC]) {
     const float* src = a.tokens + ((size_t)trk * kN + row) * kC;
@@ -228,65 +205,12 @@ __device__ __forceinline__ void head_finish(const HeadArgs& a, const ModelW& w, 
     __syncthreads();
 
     // ---- cal_bbox on the raw score (forward's pred_boxes) and on the windowed response (tracker) ----
-    float raw_max; int raw_idx;
-    block_argmax256(m_score[tid], tid, red, raw_max, raw_idx);
-    float win_max; int win_idx;
-    block_argmax256(m_resp[tid], tid, red, win_max, win_idx);
+    float raw_max, win_max; int raw_idx, win_idx;
+    decode_argmax(m_score, m_resp, red, raw_max, raw_idx, win_max, win_idx);
     HEAD_TRACE(6);
     if (tmem_to_free != 0xffffffffu && tid < 32) tc::tmem_dealloc(tmem_to_free, 512);     // all TMEM reads ended before the barriers above
     if (tid != 0) return;
-
-    if (a.pred_boxes) {
-        float* pb = a.pred_boxes + (size_t)trk * 4;
-        pb[0] = ((float)(raw_idx & 15) + m_off[raw_idx]) / 16.f;
-        pb[1] = ((float)(raw_idx >> 4) + m_off[256 + raw_idx]) / 16.f;
-        pb[2] = m_size[raw_idx];
-        pb[3] = m_size[256 + raw_idx];
-    }
-    if (a.state) {
-        double* st = a.state + (size_t)trk * 4;
-        const double sx = st[0], sy = st[1], sw = st[2], sh = st[3];
-        const int H = a.frame_hw[2 * trk], W = a.frame_hw[2 * trk + 1];
-        const CropGeom g = crop_geometry(sx, sy, sw, sh, a.search_factor, kSx, H, W);
-        const int status = a.status ? a.status[trk] : g.status;
-        double* ob = a.out_boxes + (size_t)trk * 5;
-        double* od = a.out_detail ? a.out_detail + (size_t)trk * 8 : nullptr;
-        if (status != 0) {            // the reference raises here; keep the state and flag the track
-            ob[0] = sx; ob[1] = sy; ob[2] = sw; ob[3] = sh; ob[4] = -1.0;
-            if (od) { od[0] = od[1] = od[2] = od[3] = 0.0; od[4] = g.resize_factor; od[5] = -1.0; od[6] = (double)status; od[7] = 0.0; }
-            return;
-        }
-        // pred_box = (pred_boxes.mean(0) * search_size / resize_factor).tolist()   (fp32 on the device)
-        const float rf32 = (float)g.resize_factor;
-        const float bx = ((float)(win_idx & 15) + m_off[win_idx]) / 16.f;
-        const float by = ((float)(win_idx >> 4) + m_off[256 + win_idx]) / 16.f;
-        const float pcx = __fdiv_rn(__fmul_rn(bx, 256.f), rf32);
-        const float pcy = __fdiv_rn(__fmul_rn(by, 256.f), rf32);
-        const float pw = __fdiv_rn(__fmul_rn(m_size[win_idx], 256.f), rf32);
-        const float ph = __fdiv_rn(__fmul_rn(m_size[256 + win_idx], 256.f), rf32);
-        // map_box_back (float64, Python semantics)
-        const double cx_prev = __dadd_rn(sx, __dmul_rn(0.5, sw)), cy_prev = __dadd_rn(sy, __dmul_rn(0.5, sh));
-        const double half_side = __ddiv_rn(__dmul_rn(0.5, (double)kSx), g.resize_factor);
-        const double cx_real = __dadd_rn((double)pcx, __dsub_rn(cx_prev, half_side));
-        const double cy_real = __dadd_rn((double)pcy, __dsub_rn(cy_prev, half_side));
-        double x1 = __dsub_rn(cx_real, __dmul_rn(0.5, (double)pw));
-        double y1 = __dsub_rn(cy_real, __dmul_rn(0.5, (double)ph));
-        double bw = (double)pw, bh = (double)ph;
-        // clip_box(box, H, W, margin=10)
-        double x2 = __dadd_rn(x1, bw), y2 = __dadd_rn(y1, bh);
-        x1 = fmin(fmax(0.0, x1), (double)(W - 10));
-        x2 = fmin(fmax(10.0, x2), (double)W);
-        y1 = fmin(fmax(0.0, y1), (double)(H - 10));
-        y2 = fmin(fmax(10.0, y2), (double)H);
-        bw = fmax(10.0, __dsub_rn(x2, x1));
-        bh = fmax(10.0, __dsub_rn(y2, y1));
-        ob[0] = x1; ob[1] = y1; ob[2] = bw; ob[3] = bh; ob[4] = (double)raw_max;
-        if (od) {
-            od[0] = (double)pcx; od[1] = (double)pcy; od[2] = (double)pw; od[3] = (double)ph;
-            od[4] = g.resize_factor; od[5] = (double)win_idx; od[6] = 0.0; od[7] = (double)win_max;
-        }
-        if (a.update_state) { st[0] = x1; st[1] = y1; st[2] = bw; st[3] = bh; }
-    }
+    decode_box(a, trk, m_size, m_off, raw_max, raw_idx, win_max, win_idx);
 }
 
 __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(HeadArgs a, ModelW w) {

@@ -138,4 +138,34 @@ int launch_head(const HeadArgs& a, const ModelW& w, cudaStream_t st);
 int launch_cal_bbox(const float* score, const float* size_map, const float* offset_map, int n, float* boxes,
                     cudaStream_t st);
 
+// ---- generic-configuration path (vt_generic.cu): any embed dim / heads / depth / head width of the vit_dist family ----
+// (BASELINE configs[4]: the widest config, C = 768, 12 heads, depth 12, head 256).  fp32 CUDA-core kernels: im2col + tiled
+// GEMM with fused bias / activation / residual epilogues, LayerNorm, softmax, and the shared decode.  Activations are NHWC
+// (= token-major), weights keep the reference's [out][in] layout (conv: [cout][ky][kx][cin], BN folded).
+constexpr int kGenMaxDepth = 32;
+struct GenBlockW {
+    const float *ln1g, *ln1b, *wqkv, *bqkv, *wproj, *bproj, *ln2g, *ln2b, *wfc1, *bfc1, *wfc2, *bfc2;
+};
+struct GenModelW {
+    int C, heads, depth, hc;
+    const float* stem_w[4]; const float* stem_b[4];          // [cout][9 cin], [cout]
+    GenBlockW blk[kGenMaxDepth];
+    const float *norm_g, *norm_b, *pos_z, *pos_x;
+    const float* head_w1; const float* head_b1;              // three towers merged: [3 hc][9 C], [3 hc]  (ctr | offset | size)
+    const float* head_w[3][3]; const float* head_b[3][3];    // [tower][layer 2..4]: [co][9 ci], [co]
+    const float* head_w5; const float* head_b5;              // [5][hc / 8] rows ctr, offset x, offset y, size w, size h; [5]
+    const float* hann;
+};
+struct GenWork {             // device scratch for `chunk` tracks
+    int chunk;
+    float *crop, *col, *act1, *act2, *act3, *tokz, *tok, *ln, *qkv, *scores, *attn, *hid, *t1, *t2, *t3, *t4, *raw5;
+};
+size_t gen_work_floats(const GenModelW& w, int chunk, size_t* offsets /*[17]*/);
+// Stem of n images (NCHW fp32, side S) -> tokens[(b * tok_stride_rows + tok_off + t)][C] (+ pos)
+int gen_launch_stem(const float* img, int S, int n, const GenModelW& w, const GenWork& ws, float* tokens, int tok_stride_rows,
+                    int tok_off, cudaStream_t st);
+// Blocks (in place on tokens [n][320][C]) + final LayerNorm (-> ws.ln) + head + decode.  taps: [depth + 2][n][320][C] or null.
+int gen_launch_blocks_head(float* tokens, int n, const GenModelW& w, const GenWork& ws, const HeadArgs& a, float* taps,
+                           size_t tap_stride, cudaStream_t st);
+
 }  // namespace vt

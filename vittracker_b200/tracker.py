@@ -52,7 +52,8 @@ class Vit_dist(BaseTracker):
     def __init__(self, params, dataset_name=None):
         super().__init__(params)
         self.cfg = params.cfg
-        network = build_ostrack_dist(params.cfg, blocks_impl=getattr(params, "blocks_impl", "tcgen05"))
+        depth = int(getattr(params, "depth", getattr(params.cfg.MODEL.BACKBONE, "DEPTH", 3)))
+        network = build_ostrack_dist(params.cfg, depth=depth, blocks_impl=getattr(params, "blocks_impl", "tcgen05"))
         ckpt = getattr(params, "checkpoint", None)
         state_dict = getattr(params, "state_dict", None)         # in-memory alternative to a checkpoint file
         if state_dict is None:
