@@ -305,17 +305,15 @@ def main():
     host_pools = [torch.from_numpy(O.synth_frames(F, FRAME_H, FRAME_W, seed=5000 + rank + k)).pin_memory() for k in range(2)]
     host_boxes = step_boxes.cpu().pin_memory()
     host_out = torch.empty((n * world if world > 1 else n, 5), dtype=torch.float64).pin_memory()
-    dev_boxes = torch.empty((n, 4), dtype=torch.float64, device=dev)
-    feeder = PipelinedFrameFeeder(F, FRAME_H, FRAME_W, dev)
+    feeder = PipelinedFrameFeeder(F, FRAME_H, FRAME_W, dev, max_tracks=n)
 
     def e2e_run(steps):
-        feeder.upload(host_pools[0])
+        feeder.upload(host_pools[0], host_boxes[0])
         for t in range(steps):
             fp = feeder.acquire()
             if t + 1 < steps:
-                feeder.upload(host_pools[(t + 1) % 2])
-            dev_boxes.copy_(host_boxes[t % nsets], non_blocking=True)
-            bt.engine.tracks_set_state(dev_boxes, first=0)
+                feeder.upload(host_pools[(t + 1) % 2], host_boxes[(t + 1) % nsets])
+            bt.engine.tracks_set_state(fp.boxes, first=0)
             out = bt.track_offsets(fp.data, step_offsets[t % F], update_state=True)
             if sharded is not None:
                 out = sharded.gather(out)
@@ -364,7 +362,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "note": "per step: H2D of all %d frames + boxes from pinned host memory (upload of step t+1 overlaps compute "
-                        "of step t on a copy stream), step, D2H of the boxes" % F},
+                        "of step t on a copy stream), step, D2H of the boxes; H2D link measured at 55 GB/s (tools/h2d_probe.py)" % F},
         "gpu_launches": int(launches),
     }
     if crop["ms"] > 0:

@@ -83,26 +83,35 @@ class BatchedTracker:
 class PipelinedFrameFeeder:
     """Host -> HBM frame ingest overlapped with tracking: two device frame pools and a copy stream.
 
-    ``upload(host_frames)`` starts the asynchronous copy of the next step's frames (pinned uint8
-    [F, H, W, 3]) into the idle pool; ``acquire()`` makes the compute stream wait for the oldest
-    pending upload and returns that pool; ``release(pool)`` marks the pool reusable once the work
-    queued so far on the compute stream (the step that read it) has finished."""
+    ``upload(host_frames, host_boxes)`` starts the asynchronous copy of the next step's frames (pinned uint8
+    [F, H, W, 3]) - and optionally of that step's per-track boxes (pinned float64 [n, 4]) - into the idle pool;
+    ``acquire()`` makes the compute stream wait for the oldest pending upload and returns that pool (its boxes, if
+    any, are ``pool.boxes``); ``release(pool)`` marks the pool reusable once the work queued so far on the compute
+    stream (the step that read it) has finished.
 
-    def __init__(self, F: int, H: int, W: int, device: torch.device):
+    Every host-to-device copy of a step goes through the copy stream, small ones first: a copy engine serves its
+    queue in submission order, so a small upload issued on the compute stream would wait behind the next step's
+    frames and stall the step that needs it."""
+
+    def __init__(self, F: int, H: int, W: int, device: torch.device, max_tracks: int = 0):
         self.device = device
         self.pools = [FramePool(torch.zeros((F, H, W, 3), dtype=torch.uint8), device) for _ in range(2)]
+        for p in self.pools:
+            p.boxes = torch.zeros((max_tracks, 4), dtype=torch.float64, device=device) if max_tracks > 0 else None
         self.copy_stream = torch.cuda.Stream(device=device)
         self._ready = [torch.cuda.Event(), torch.cuda.Event()]
         self._free = [None, None]
         self._pending = []
         self._next = 0
 
-    def upload(self, host_frames: torch.Tensor) -> None:
+    def upload(self, host_frames: torch.Tensor, host_boxes: Optional[torch.Tensor] = None) -> None:
         i = self._next
         self._next ^= 1
         with torch.cuda.stream(self.copy_stream):
             if self._free[i] is not None:
                 self.copy_stream.wait_event(self._free[i])
+            if host_boxes is not None:
+                self.pools[i].boxes[: host_boxes.shape[0]].copy_(host_boxes, non_blocking=True)
             self.pools[i].data.copy_(host_frames, non_blocking=True)
             self._ready[i].record(self.copy_stream)
         self._pending.append(i)
