@@ -55,9 +55,17 @@ __host__ __device__ inline void tcs_step(int cch, int acc, int s, int& tap0, int
 
 namespace {
 
-template <int CCH, int COUT, int NPAD, int WOUT>
+#ifndef VT_CONV2_BR
+#define VT_CONV2_BR 4
+#endif
+#ifndef VT_CONV3_BR
+#define VT_CONV3_BR 4
+#endif
+constexpr int kConv2BR = VT_CONV2_BR, kConv3BR = VT_CONV3_BR;     // output rows per CTA
+
+template <int CCH, int COUT, int NPAD, int WOUT, int BR>
 struct TcConv {
-    static constexpr int kBR = 8;                               // output rows per CTA
+    static constexpr int kBR = BR;                              // output rows per CTA (smaller band = more CTAs per SM, more halo)
     static constexpr int kRowsPerTile = 128 / WOUT;
     static constexpr int kTiles = kBR / kRowsPerTile;            // M tiles per CTA
     static constexpr int kPlaneRows = kBR + 1;                   // band row 0 <-> plane row oy0 - 1
@@ -84,11 +92,11 @@ struct TcConv {
 // grid: (Hout / 8 bands, n tracks).  in: plane images [n][tc_planes_bytes(CCH, WOUT)]; wt: packed fp16 hi|lo weight blob
 // in K-step order; bias fp32 [COUT].  OUT_PLANES: write the next layer's plane image (NEXT_CCH chunks, WOUT/2 wide),
 // else tokens [n][tok_stride_rows][COUT] + positional embedding.
-template <int CCH, int COUT, int NPAD, int WOUT, bool HSWISH, bool OUT_PLANES, int NEXT_CCH>
+template <int CCH, int COUT, int NPAD, int WOUT, int BR, bool HSWISH, bool OUT_PLANES, int NEXT_CCH>
 __global__ void __launch_bounds__(256)
 conv_s2_tc_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wt, const float* __restrict__ bias,
                   void* __restrict__ outp, const float* __restrict__ pos, int tok_stride_rows, int tok_off) {
-    using K = TcConv<CCH, COUT, NPAD, WOUT>;
+    using K = TcConv<CCH, COUT, NPAD, WOUT, BR>;
     extern __shared__ __align__(128) uint8_t smem_tc[];
     uint8_t* sA = smem_tc + K::kOffA;
     uint8_t* sW = smem_tc + K::kOffW;
@@ -225,11 +233,11 @@ conv_s2_tc_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wt
     if (warp == 0) tmem_dealloc(tbase, K::kTmemCols);
 }
 
-template <int CCH, int COUT, int NPAD, int WOUT, bool HSWISH, bool OUT_PLANES, int NEXT_CCH>
+template <int CCH, int COUT, int NPAD, int WOUT, int BR, bool HSWISH, bool OUT_PLANES, int NEXT_CCH>
 static int run_tc_conv(const uint8_t* in, int n, const uint8_t* wt, const float* bias, void* out, size_t out_track_bytes,
                        const float* pos, int tok_stride_rows, int tok_off, cudaStream_t st) {
-    using K = TcConv<CCH, COUT, NPAD, WOUT>;
-    auto kern = conv_s2_tc_kernel<CCH, COUT, NPAD, WOUT, HSWISH, OUT_PLANES, NEXT_CCH>;
+    using K = TcConv<CCH, COUT, NPAD, WOUT, BR>;
+    auto kern = conv_s2_tc_kernel<CCH, COUT, NPAD, WOUT, BR, HSWISH, OUT_PLANES, NEXT_CCH>;
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::kSmemBytes) != cudaSuccess) return -1;
@@ -251,13 +259,13 @@ static int run_tc_conv(const uint8_t* in, int n, const uint8_t* wt, const float*
 int launch_stem234_tc(const uint8_t* planes2, int n, const ModelW& w, uint8_t* planes3, uint8_t* planes4, float* tokens,
                       int tok_stride_rows, int tok_off, cudaStream_t st) {
     int total = 0, r;
-    if ((r = run_tc_conv<kConv2Cch, 12, 16, kConv2Wout, true, true, kConv3Cch>(planes2, n, w.stem_tc_w[0], w.stem_tc_b[0], planes3,
+    if ((r = run_tc_conv<kConv2Cch, 12, 16, kConv2Wout, kConv2BR, true, true, kConv3Cch>(planes2, n, w.stem_tc_w[0], w.stem_tc_b[0], planes3,
                                                                                tc_planes_bytes(kConv3Cch, kConv3Wout), nullptr, 0, 0, st)) < 0) return r;
     total += r;
-    if ((r = run_tc_conv<kConv3Cch, 24, 32, kConv3Wout, true, true, kConv4Cch>(planes3, n, w.stem_tc_w[1], w.stem_tc_b[1], planes4,
+    if ((r = run_tc_conv<kConv3Cch, 24, 32, kConv3Wout, kConv3BR, true, true, kConv4Cch>(planes3, n, w.stem_tc_w[1], w.stem_tc_b[1], planes4,
                                                                                tc_planes_bytes(kConv4Cch, kConv4Wout), nullptr, 0, 0, st)) < 0) return r;
     total += r;
-    if ((r = run_tc_conv<kConv4Cch, 48, 48, kConv4Wout, false, false, 1>(planes4, n, w.stem_tc_w[2], w.stem_tc_b[2], tokens,
+    if ((r = run_tc_conv<kConv4Cch, 48, 48, kConv4Wout, 8, false, false, 1>(planes4, n, w.stem_tc_w[2], w.stem_tc_b[2], tokens,
                                                                           (size_t)tok_stride_rows * 48 * sizeof(float), w.pos_x,
                                                                           tok_stride_rows, tok_off, st)) < 0) return r;
     total += r;
@@ -265,8 +273,8 @@ int launch_stem234_tc(const uint8_t* planes2, int n, const ModelW& w, uint8_t* p
 }
 
 size_t stem_tc_weight_bytes(int layer) {      // layer 0: conv2, 1: conv3, 2: conv4
-    return layer == 0 ? (size_t)TcConv<kConv2Cch, 12, 16, kConv2Wout>::kWBytes
-           : layer == 1 ? (size_t)TcConv<kConv3Cch, 24, 32, kConv3Wout>::kWBytes : (size_t)TcConv<kConv4Cch, 48, 48, kConv4Wout>::kWBytes;
+    return layer == 0 ? (size_t)TcConv<kConv2Cch, 12, 16, kConv2Wout, kConv2BR>::kWBytes
+           : layer == 1 ? (size_t)TcConv<kConv3Cch, 24, 32, kConv3Wout, kConv3BR>::kWBytes : (size_t)TcConv<kConv4Cch, 48, 48, kConv4Wout, 8>::kWBytes;
 }
 
 // Host side of the K-step schedule: weight blob of one layer (fp16 hi | lo), `wf` = folded weights [ci][ky][kx][cout].
