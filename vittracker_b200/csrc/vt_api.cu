@@ -42,6 +42,7 @@ struct VtContext {
     int num_sms = 148;
     // chunk workspace
     float* d_scratch = nullptr;       // stem intermediates (fp32 NCHW)
+    void* d_taps = nullptr;           // per-track tap tables of the fused crop gather
     uint8_t* d_planes = nullptr;      // tensor-core operand images of conv3 / conv4 (zero rows must stay zero); null in SIMT mode
     float* d_tokz = nullptr;          // [chunk][64][48]   (vt_forward only)
     float* d_tokx = nullptr;          // [max_tracks][256][48]
@@ -153,7 +154,7 @@ struct Packer {
 void free_all(VtHandle h) {
     for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : h->evpool) cudaEventDestroy(e);
-    cudaFree(h->d_weights); cudaFree(h->d_planes); cudaFree(h->d_scratch); cudaFree(h->d_tokz);
+    cudaFree(h->d_weights); cudaFree(h->d_planes); cudaFree(h->d_scratch); cudaFree(h->d_taps); cudaFree(h->d_tokz);
     cudaFree(h->d_tokx); cudaFree(h->d_tok); cudaFree(h->d_state); cudaFree(h->d_tmpl);
     cudaFree(h->d_status); cudaFree(h->d_maps); cudaFree(h->d_gwork);
 }
@@ -368,6 +369,7 @@ int vt_create(const VtConfig* cfg, VtHandle* out) {
     auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
     if (fast) {
         A((void**)&h->d_scratch, ch * stem_scratch_floats(kSx) * sizeof(float));
+        A((void**)&h->d_taps, crop_taps_bytes((int)ch));
         if (cfg->blocks_impl == VT_BLOCKS_TCGEN05) {
             const size_t pb = ch * tc_planes_bytes_per_track();
             A((void**)&h->d_planes, pb);
@@ -757,7 +759,7 @@ int vt_tracks_init(VtHandle h, const uint8_t* frames, const int64_t* frame_offse
         VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_tracks_init/crop+stem",
                   launch_crop_stem(frames, frame_offsets + c0, frame_hw + 2 * c0, boxes_xywh + 4 * c0, h->cfg.template_factor, kTz, m,
                                    h->mw, h->d_scratch, h->d_tmpl + (size_t)(first + c0) * kNz * kC, kNz, 0, h->d_status + first + c0,
-                                   h->d_planes, h->chunk, st));
+                                   h->d_planes, h->chunk, h->d_taps, st));
     }
     VT_CUDA(h, cudaMemcpyAsync(h->d_state + (size_t)first * 4, boxes_xywh, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if (out_status) VT_CUDA(h, cudaMemcpyAsync(out_status, h->d_status + first, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
@@ -809,7 +811,7 @@ int vt_tracks_step(VtHandle h, const uint8_t* frames, const int64_t* frame_offse
         VT_LAUNCH(h, VT_STAGE_STEM, m, st, "vt_tracks_step/crop+stem",
                   launch_crop_stem(frames, frame_offsets + c0, frame_hw + 2 * c0, h->d_state + (size_t)t0 * 4, h->cfg.search_factor, kSx, m,
                                    h->mw, h->d_scratch, h->d_tokx + (size_t)c0 * kNx * kC, kNx, 0, h->d_status + t0,
-                                   h->d_planes, h->chunk, st));
+                                   h->d_planes, h->chunk, h->d_taps, st));
     }
     {
         const int m = n;

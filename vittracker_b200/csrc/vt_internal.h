@@ -106,7 +106,8 @@ void stem_tc_pack_weights(int cin, int cch, int cout, int npad, const float* wf,
 // Crop + stem straight from raw uint8 frames (the first conv layer gathers its tile from the frame).
 int launch_crop_stem(const uint8_t* frames, const int64_t* frame_offsets, const int32_t* frame_hw, const double* boxes,
                      double factor, int S, int n, const ModelW& w, float* scratch, float* tokens, int tok_stride_rows,
-                     int tok_off, int32_t* out_status, uint8_t* planes, int plane_tracks, cudaStream_t st);
+                     int tok_off, int32_t* out_status, uint8_t* planes, int plane_tracks, void* tap_tables, cudaStream_t st);
+size_t crop_taps_bytes(int n);      // size of the tap-table buffer launch_crop_stem needs for n tracks
 
 // ViT blocks (fp32 SIMT): tokens_z [n][64][48] (stride z_stride rows per track), tokens_x likewise; in place
 // result written to out [n][320][48]; taps (or null) receives [depth][n][320][48].

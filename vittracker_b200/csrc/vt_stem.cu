@@ -238,12 +238,63 @@ constexpr int kCc1Threads = Conv1Cfg::kThreads;                         // 256
 constexpr int kCc1TileSide = 2 * 32 + 1;                                // 65 resized-crop pixels per side
 constexpr size_t kCc1SmemBytes = Conv1Cfg::kSmemBytes + 64 + 2 * 80 * sizeof(int4);     // 4 CTAs / SM
 
+// Per-track tap tables of the fused gather, computed once per track (float64 geometry + the resize taps) instead of by
+// every tile's CTA: taps[item][0][d + 1] = column record of resized-crop column d, taps[item][1][d + 1] = row record,
+// d = -1 .. S - 1.  Columns: the two horizontal taps of cv::resize are the same or adjacent source pixels, so a column is
+// one PAIR of adjacent pixels (.x = byte offset of the first, .y = weights first | second << 16; a tap that is padding
+// or clamped away has weight 0 - a zero pixel and a zero weight give the same products - and the pair is anchored on a
+// tap that is inside the image, so the six bytes read always are).  Rows: .x/.y = byte offsets of the two tap rows
+// (0 when the row is padding), .z = weights lo | hi << 16.  .w = 1 when the position is outside the resized crop
+// (= the convolution's zero padding, which is 0.0f and not the normalised pixel 0).
+constexpr int kTapPitch = 264;
+template <int S>
+__global__ void __launch_bounds__(288)
+crop_taps_kernel(const int32_t* __restrict__ frame_hw, const double* __restrict__ boxes, double factor, int4* __restrict__ taps,
+                 int32_t* __restrict__ out_status) {
+    __shared__ CropGeom sg;
+    __shared__ double s_scale;
+    const int item = blockIdx.x, tid = threadIdx.x;
+    const int H = frame_hw[2 * item], W = frame_hw[2 * item + 1];
+    if (tid == 0) {
+        const double* bx = boxes + 4 * item;
+        sg = crop_geometry(bx[0], bx[1], bx[2], bx[3], factor, S, H, W);
+        s_scale = resize_scale(S, sg.crop_sz);
+        if (out_status) out_status[item] = sg.status;
+    }
+    __syncthreads();
+    const CropGeom g = sg;
+    const double scale = s_scale;
+    if (tid > S) return;
+    const int d = tid - 1;
+    int4 tc = make_int4(0, 0, 0, 1), tr = make_int4(0, 0, 0, 1);
+    if (d >= 0 && g.status == 0) {
+        {
+            int s0, s1, a0, a1; bool w0, w1;
+            tap_x(d, scale, g.crop_sz, s0, s1, a0, a1, w0, w1);
+            const int ix0 = g.x1 + s0, ix1 = g.x1 + s1;
+            if (!(ix0 >= 0 && ix0 <= W - 2)) a0 = 0;
+            if (!(ix1 >= 0 && ix1 <= W - 2) || ix1 == ix0) a1 = 0;      // s1 == s0 only where cv::resize clamps, and there a1 == 0
+            if (a0 != 0) tc = make_int4(ix0 * 3, a0 | (a1 << 16), 0, 0);
+            else if (a1 != 0) tc = make_int4(ix1 * 3, a1, 0, 0);
+            else tc = make_int4(0, 0, 0, 0);
+        }
+        {
+            int r0, r1, b0, b1; bool w0, w1;
+            tap_y(d, scale, g.crop_sz, r0, r1, b0, b1, w0, w1);
+            const int iy0 = g.y1 + r0, iy1 = g.y1 + r1;
+            const bool v0 = iy0 >= 0 && iy0 <= H - 2, v1 = iy1 >= 0 && iy1 <= H - 2;
+            tr = make_int4(v0 ? iy0 * W * 3 : 0, v1 ? iy1 * W * 3 : 0, (v0 ? b0 : 0) | ((v1 ? b1 : 0) << 16), 0);
+        }
+    }
+    taps[((size_t)item * 2 + 0) * kTapPitch + tid] = tc;
+    taps[((size_t)item * 2 + 1) * kTapPitch + tid] = tr;
+}
+
 template <int S, int TCOUT_CCH>
 __global__ void __launch_bounds__(kCc1Threads)
 crop_conv1_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict__ frame_offsets,
-                  const int32_t* __restrict__ frame_hw, const double* __restrict__ boxes, double factor,
-                  const float* __restrict__ lut, const float* __restrict__ wg, const float* __restrict__ bg,
-                  float* __restrict__ out, int32_t* __restrict__ out_status) {
+                  const int4* __restrict__ taps, const float* __restrict__ lut, const float* __restrict__ wg,
+                  const float* __restrict__ bg, float* __restrict__ out) {
     using K = Conv1Cfg;
     extern __shared__ __align__(16) float smem[];
     float* tile = smem;
@@ -263,44 +314,9 @@ crop_conv1_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict_
     if (tid < 6) cp_async<4>(bs + tid, bg + tid, true);
     asm volatile("cp.async.commit_group;\n" ::: "memory");
 
-    const int H = frame_hw[2 * item], W = frame_hw[2 * item + 1];
-    const double* bx = boxes + 4 * item;
-    const CropGeom g = crop_geometry(bx[0], bx[1], bx[2], bx[3], factor, S, H, W);
-    if (blockIdx.x == 0 && tid == 0 && out_status) out_status[item] = g.status;
-    const double scale = resize_scale(S, g.crop_sz);
-
-    // tap tables.  Columns: the two horizontal taps of cv::resize are the same or adjacent source pixels, so a column is
-    // one PAIR of adjacent pixels (.x = byte offset of the first, .y = weights first | second << 16; a tap that is padding
-    // or clamped away has weight 0 - a zero pixel and a zero weight give the same products - and the pair is anchored on a
-    // tap that is inside the image, so the six bytes read always are).  Rows: .x/.y = byte offsets of the two tap rows
-    // (0 when the row is padding), .z = weights lo | hi << 16.  .w = 1 when the position is outside the resized crop
-    // (= the convolution's zero padding, which is 0.0f and not the normalised pixel 0).
-    if (tid < kCc1TileSide) {
-        const int d = 2 * tx0 - 1 + tid;
-        int4 t = make_int4(0, 0, 0, 1);
-        if (d >= 0 && d < S && g.status == 0) {
-            int s0, s1, a0, a1; bool w0, w1;
-            tap_x(d, scale, g.crop_sz, s0, s1, a0, a1, w0, w1);
-            const int ix0 = g.x1 + s0, ix1 = g.x1 + s1;
-            if (!(ix0 >= 0 && ix0 <= W - 2)) a0 = 0;
-            if (!(ix1 >= 0 && ix1 <= W - 2) || ix1 == ix0) a1 = 0;      // s1 == s0 only where cv::resize clamps, and there a1 == 0
-            if (a0 != 0) t = make_int4(ix0 * 3, a0 | (a1 << 16), 0, 0);
-            else if (a1 != 0) t = make_int4(ix1 * 3, a1, 0, 0);
-            else t = make_int4(0, 0, 0, 0);
-        }
-        s_col[tid] = t;
-    } else if (tid >= 128 && tid < 128 + kCc1TileSide) {
-        const int d = 2 * ty0 - 1 + (tid - 128);
-        int4 t = make_int4(0, 0, 0, 1);
-        if (d >= 0 && d < S && g.status == 0) {
-            int r0, r1, b0, b1; bool w0, w1;
-            tap_y(d, scale, g.crop_sz, r0, r1, b0, b1, w0, w1);
-            const int iy0 = g.y1 + r0, iy1 = g.y1 + r1;
-            const bool v0 = iy0 >= 0 && iy0 <= H - 2, v1 = iy1 >= 0 && iy1 <= H - 2;
-            t = make_int4(v0 ? iy0 * W * 3 : 0, v1 ? iy1 * W * 3 : 0, (v0 ? b0 : 0) | ((v1 ? b1 : 0) << 16), 0);
-        }
-        s_row[tid - 128] = t;
-    }
+    // this tile's 65 column and 65 row records of the per-track tap tables (crop_taps_kernel)
+    if (tid < kCc1TileSide) s_col[tid] = __ldg(taps + ((size_t)item * 2 + 0) * kTapPitch + 2 * tx0 + tid);
+    else if (tid >= 128 && tid < 128 + kCc1TileSide) s_row[tid - 128] = __ldg(taps + ((size_t)item * 2 + 1) * kTapPitch + 2 * ty0 + tid - 128);
     __syncthreads();
 
     const uint8_t* __restrict__ im = frames + frame_offsets[item];
@@ -400,9 +416,11 @@ size_t stem_scratch_floats(int S) {
     return (size_t)6 * (S / 2) * (S / 2) + (size_t)12 * (S / 4) * (S / 4) + (size_t)24 * (S / 8) * (S / 8);
 }
 
+size_t crop_taps_bytes(int n) { return (size_t)n * 2 * kTapPitch * sizeof(int4); }
+
 template <int S, int TCOUT_CCH>
 static int run_crop_conv1(const uint8_t* frames, const int64_t* frame_offsets, const int32_t* frame_hw, const double* boxes,
-                          double factor, int n, const ModelW& w, float* out, int32_t* out_status, cudaStream_t st) {
+                          double factor, int n, const ModelW& w, float* out, int32_t* out_status, int4* taps, cudaStream_t st) {
     auto kern = crop_conv1_kernel<S, TCOUT_CCH>;
     static bool configured = false;
     if (!configured) {
@@ -410,14 +428,14 @@ static int run_crop_conv1(const uint8_t* frames, const int64_t* frame_offsets, c
         configured = true;
     }
     constexpr int tiles = (S / 64) * (S / 64);
-    int launched = 0;
+    crop_taps_kernel<S><<<n, 288, 0, st>>>(frame_hw, boxes, factor, taps, out_status);
+    int launched = 1;
     for (int first = 0; first < n; first += 32768) {
         const int m = min(32768, n - first);
-        kern<<<dim3(tiles, m), kCc1Threads, kCc1SmemBytes, st>>>(frames, frame_offsets + first, frame_hw + 2 * first, boxes + 4 * first, factor,
+        kern<<<dim3(tiles, m), kCc1Threads, kCc1SmemBytes, st>>>(frames, frame_offsets + first, taps + (size_t)first * 2 * kTapPitch,
                                                                  w.lut, w.stem[0].w, w.stem[0].b,
                                                                  TCOUT_CCH > 0 ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(out) + (size_t)first * tc_planes_bytes(TCOUT_CCH, S / 4))
-                                                                               : out + (size_t)first * 6 * (S / 2) * (S / 2),
-                                                                 out_status ? out_status + first : nullptr);
+                                                                               : out + (size_t)first * 6 * (S / 2) * (S / 2));
         ++launched;
     }
     return cudaGetLastError() == cudaSuccess ? launched : -1;
@@ -426,8 +444,9 @@ static int run_crop_conv1(const uint8_t* frames, const int64_t* frame_offsets, c
 // Crop + stem straight from raw frames (fused first layer); same outputs as launch_crop_normalize + launch_stem.
 int launch_crop_stem(const uint8_t* frames, const int64_t* frame_offsets, const int32_t* frame_hw, const double* boxes,
                      double factor, int S, int n, const ModelW& w, float* scratch, float* tokens, int tok_stride_rows,
-                     int tok_off, int32_t* out_status, uint8_t* planes, int plane_tracks, cudaStream_t st) {
+                     int tok_off, int32_t* out_status, uint8_t* planes, int plane_tracks, void* tap_tables, cudaStream_t st) {
     if (n <= 0) return 0;
+    int4* taps = reinterpret_cast<int4*>(tap_tables);
     float* a1 = scratch;
     float* a2 = a1 + (size_t)n * 6 * (S / 2) * (S / 2);
     float* a3 = a2 + (size_t)n * 12 * (S / 4) * (S / 4);
@@ -438,13 +457,13 @@ int launch_crop_stem(const uint8_t* frames, const int64_t* frame_offsets, const 
         uint8_t* planes2 = planes;
         uint8_t* planes3 = planes2 + (size_t)plane_tracks * tc_planes_bytes(kConv2Cch, kConv2Wout);
         uint8_t* planes4 = planes3 + (size_t)plane_tracks * tc_planes_bytes(kConv3Cch, kConv3Wout);
-        if ((r = run_crop_conv1<256, kConv2Cch>(frames, frame_offsets, frame_hw, boxes, factor, n, w, reinterpret_cast<float*>(planes2), out_status, st)) < 0) return r;
+        if ((r = run_crop_conv1<256, kConv2Cch>(frames, frame_offsets, frame_hw, boxes, factor, n, w, reinterpret_cast<float*>(planes2), out_status, taps, st)) < 0) return r;
         total += r;
         if ((r = launch_stem234_tc(planes2, n, w, planes3, planes4, tokens, tok_stride_rows, tok_off, st)) < 0) return r;
         return total + r;
     }
-    if (S == 256) r = run_crop_conv1<256, 0>(frames, frame_offsets, frame_hw, boxes, factor, n, w, a1, out_status, st);
-    else if (S == 128) r = run_crop_conv1<128, 0>(frames, frame_offsets, frame_hw, boxes, factor, n, w, a1, out_status, st);
+    if (S == 256) r = run_crop_conv1<256, 0>(frames, frame_offsets, frame_hw, boxes, factor, n, w, a1, out_status, taps, st);
+    else if (S == 128) r = run_crop_conv1<128, 0>(frames, frame_offsets, frame_hw, boxes, factor, n, w, a1, out_status, taps, st);
     else return -1;
     if (r < 0) return r;
     total += r;
