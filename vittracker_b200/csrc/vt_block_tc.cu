@@ -70,13 +70,16 @@ constexpr int kSmWa = 0;                                  // Wqkv hi|lo, Wproj h
 constexpr int kSmX = kSmWa + kTcWaBytes;                  // attention: K hi|lo, V hi|lo ; MLP: W1 hi|lo, W2 hi|lo
 constexpr int kKBytes = kN * kC * 2;                      // 30720 per precision
 constexpr int kSmKhi = kSmX, kSmKlo = kSmX + kKBytes, kSmVhi = kSmX + 2 * kKBytes, kSmVlo = kSmX + 3 * kKBytes;
-constexpr int kSmW1hi = kSmX, kSmW1lo = kSmX + 18432, kSmW2hi = kSmX + 36864, kSmW2lo = kSmX + 55296;
-constexpr int kSmPar = kSmX + 4 * kKBytes;                // fp32 parameters of all blocks
+constexpr int kSmW2hi = kSmX, kSmW2lo = kSmX + 18432;       // W2 hi|lo overlays K (streamed in once attention is over)
+constexpr int kSmW1 = kSmX + 4 * kKBytes;                 // W1 hi|lo in its own region: prefetched during attention
+constexpr int kSmW1hi = kSmW1, kSmW1lo = kSmW1 + 18432;
+constexpr int kSmPar = kSmW1 + 36864;                     // fp32 parameters of all blocks
 constexpr int kSmRed = kSmPar + kDepth * kTcParFloats * 4;   // 5 arrays x kNS column groups x 128 rows fp32
 constexpr int kSmBar = kSmRed + 5 * kNS * 128 * 4;        // mbarriers
 constexpr int kSmTmem = kSmBar + 12 * 8;
+static_assert(kSmTmem + 16 <= 227 * 1024, "shared memory");
 constexpr int kTcSmemBytes = kSmTmem + 16;
-static_assert(kTcWbBytes <= 4 * kKBytes, "MLP weights overlay the K/V region");
+static_assert(kTcWbBytes == 2 * 36864 && 36864 <= 4 * kKBytes, "W2 overlays the K/V region");
 static_assert(kSmBar % 8 == 0 && kSmX % 128 == 0, "alignment");
 
 // parameter offsets inside one block's fp32 parameter vector
@@ -164,19 +167,20 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// GELU(v) = 0.5 v (1 + erf(v / sqrt 2)) with erf from Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7, about one
-// fp32 ulp of the 1 + erf term): one reciprocal, one exponential and a degree-5 Horner instead of erff's
-// two branch-selected polynomials (erff was ~30 % of this kernel's CUDA-core instructions).
+// GELU(v) = 0.5 v (1 + erf(v / sqrt 2)) with erf from Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7): with x = |v| / sqrt 2,
+// t = 1 / (1 + p x), erf(x) = 1 - P(t) t exp(-x^2), both signs of v collapse to
+//     GELU(v) = max(v, 0) - |v| (P(t) / 2) t exp(-v^2 / 2)
+// - no cancellation against 1, one reciprocal, one exponential, and the 1/2, 1/sqrt 2 and log2(e) folded into constants
+// (erff's two branch-selected polynomials were ~30 % of this kernel's CUDA-core instructions).
 __device__ __forceinline__ float gelu_erf(float v) {
-    const float z = fabsf(v) * 0.70710678118654752f;
-    const float t = rcp_approx(fmaf(0.3275911f, z, 1.f));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    const float e = ex2_approx(-1.4426950408889634f * z * z);
-    const float erf_abs = fmaf(-p * t, e, 1.f);                 // erf(|v| / sqrt 2)
-    return 0.5f * v * (1.f + copysignf(erf_abs, v));
+    const float av = fabsf(v);
+    const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752f, av, 1.f));
+    float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+    p = fmaf(p, t, 0.5f * 1.421413741f);
+    p = fmaf(p, t, 0.5f * -0.284496736f);
+    p = fmaf(p, t, 0.5f * 0.254829592f);
+    const float e = ex2_approx(v * (-0.5f * 1.4426950408889634f * v));
+    return fmaf(-(av * (p * t)), e, fmaxf(v, 0.f));
 }
 
 }  // namespace
@@ -196,6 +200,7 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
     uint64_t* mb_y = mb_go + 6;        // [2] fc2 output ready in Y_A / Y_B          (tcgen05.commit)
     uint64_t* mb_g = mb_go + 8;        // [2] GELU operand written in H_A / H_B      (one arrival per epilogue warp)
     uint64_t* mb_yfree = mb_go + 10;   // Y_A has been read, may be overwritten      (one arrival per epilogue warp)
+    uint64_t* mb_w1 = mb_go + 11;      // W1 landed in shared memory
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kSmTmem);
 
     if (warp == kEpiWarps) tmem_alloc(s_tmem, 512);
@@ -204,6 +209,7 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
         mbar_init(mb_done, 1);
         mbar_init(mb_wa, 1);
         mbar_init(mb_wb, 1);
+        mbar_init(mb_w1, 1);
         mbar_init(mb_h, 1); mbar_init(mb_h + 1, 1);
         mbar_init(mb_y, 1); mbar_init(mb_y + 1, 1);
         mbar_init(mb_g, kEpiWarps); mbar_init(mb_g + 1, kEpiWarps);
@@ -220,13 +226,14 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
     if (warp == kEpiWarps) {
         // =========================== control: weight loads + MMA issue (one thread) ===========================
         {   // the whole warp runs this program convergently; MMA / commit / bulk copy are done by one elected lane
-            uint32_t go_ph = 0, wa_ph = 0, wb_ph = 0;
+            uint32_t go_ph = 0, wa_ph = 0, wb_ph = 0, w1_ph = 0;
             const uint32_t id48 = instr_desc_f16(128, 48, false), id48mn = instr_desc_f16(128, 48, true);
             const uint32_t id144 = instr_desc_f16(128, 144, false), id160 = instr_desc_f16(128, 160, false);
             const uint32_t id192 = instr_desc_f16(128, 192, false);
             auto wait_go = [&]() { TC_TRACE(0); mbar_wait(mb_go, go_ph); go_ph ^= 1; tc_fence_after(); TC_TRACE(0); };
             auto load_wa = [&](int blk) { bulk_g2s_elect(smem + kSmWa, w.tc[blk].wa, kTcWaBytes, mb_wa); };
-            auto load_wb = [&](int blk) { bulk_g2s_elect(smem + kSmX, w.tc[blk].wb, kTcWbBytes, mb_wb); };
+            auto load_w1 = [&](int blk) { bulk_g2s_elect(smem + kSmW1, w.tc[blk].wb, 36864, mb_w1); };
+            auto load_w2 = [&](int blk) { bulk_g2s_elect(smem + kSmX, w.tc[blk].wb + 36864, 36864, mb_wb); };
             // D[d_col] = A(opa slot t, K = 48) x B^T, B K-major [k/8][N][8] at byte offsets b_hi / b_lo
             auto gemm_k48 = [&](int t, uint32_t d_col, uint32_t b_hi, uint32_t b_lo, int N, uint32_t idesc) {
                 const uint32_t a = tbase + kColOpa + 48 * t;
@@ -290,7 +297,7 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
             for (int trk = blockIdx.x; trk < n; trk += gridDim.x) {
                 const bool last_track = trk + (int)gridDim.x >= n;
                 for (int blk = 0; blk < kDepth; ++blk) {
-                    if (first) { load_wa(0); first = false; }
+                    if (first) { load_wa(0); load_w1(0); first = false; }
                     wait_go();                                                   // 1: LN1 operands of all tiles
                     mbar_wait(mb_wa, wa_ph); wa_ph ^= 1;
                     qkv(0, kColBig); qkv(1, kColBig + 160); mma_commit_elect(mb_done);
@@ -299,20 +306,22 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                     wait_go(); pv(0); scores(1); mma_commit_elect(mb_done);            // 4: P(0) written; S(1) reuses the columns in issue order
                     wait_go(); pv(1); scores(2); mma_commit_elect(mb_done);            // 5
                     wait_go(); pv(2); mma_commit_elect(mb_done);                       // 6
-                    wait_go(); load_wb(blk);                                     // 7: attention output + LN2 of every tile done; K/V' dead
+                    wait_go(); load_w2(blk);                                     // 7: attention output + LN2 of every tile done; K/V' dead
                     if (!(last_track && blk == kDepth - 1)) load_wa((blk + 1) % kDepth);
-                    mbar_wait(mb_wb, wb_ph); wb_ph ^= 1;
+                    mbar_wait(mb_w1, w1_ph); w1_ph ^= 1;                         // W1 was prefetched during attention
                     // ---- MLP, pipelined over row tiles (tile 0 -> H_A/Y_A, tile 1 -> H_B/Y_B, tile 2 -> H_A/Y_A) ----
                     fc1(0, kColHA); mma_commit_elect(mb_h);
                     wait_on(mb_h, h_ph[0]);                                      // H_B aliases operand slot 0: fc1(0) must be done
                     fc1(1, kColHB); mma_commit_elect(mb_h + 1);
                     wait_on(mb_g, g_ph[0]);                                      // GELU(0) operand in H_A
                     wait_on(mb_h + 1, h_ph[1]);                                  // Y_A aliases operand slots 0/1: fc1(1) must be done
+                    mbar_wait(mb_wb, wb_ph); wb_ph ^= 1;                         // W2 landed
                     fc2(kColHA, kColYA); mma_commit_elect(mb_y);
                     wait_on(mb_y, y_ph[0]);                                      // fc2(0) has read H_A
                     fc1(2, kColHA); mma_commit_elect(mb_h);
                     wait_on(mb_g + 1, g_ph[1]);                                  // GELU(1) operand in H_B
                     wait_on(mb_h, h_ph[0]);                                      // Y_B aliases operand slot 2: fc1(2) must be done
+                    if (!(last_track && blk == kDepth - 1)) load_w1((blk + 1) % kDepth);   // W1 dead -> the next block's streams in
                     fc2(kColHB, kColYB); mma_commit_elect(mb_y + 1);
                     wait_on(mb_g, g_ph[0]);                                      // GELU(2) operand in H_A
                     wait_on(mb_yfree, yfree_ph);                                 // Y_A (tile 0) has been consumed
