@@ -76,7 +76,7 @@ constexpr int kSmW1hi = kSmW1, kSmW1lo = kSmW1 + 18432;
 constexpr int kSmPar = kSmW1 + 36864;                     // fp32 parameters of all blocks
 constexpr int kSmRed = kSmPar + kDepth * kTcParFloats * 4;   // 5 arrays x kNS column groups x 128 rows fp32
 constexpr int kSmBar = kSmRed + 5 * kNS * 128 * 4;        // mbarriers
-constexpr int kSmTmem = kSmBar + 12 * 8;
+constexpr int kSmTmem = kSmBar + 16 * 8;
 static_assert(kSmTmem + 16 <= 227 * 1024, "shared memory");
 constexpr int kTcSmemBytes = kSmTmem + 16;
 static_assert(kTcWbBytes == 2 * 36864 && 36864 <= 4 * kKBytes, "W2 overlays the K/V region");
@@ -201,6 +201,8 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
     uint64_t* mb_g = mb_go + 8;        // [2] GELU operand written in H_A / H_B      (one arrival per epilogue warp)
     uint64_t* mb_yfree = mb_go + 10;   // Y_A has been read, may be overwritten      (one arrival per epilogue warp)
     uint64_t* mb_w1 = mb_go + 11;      // W1 landed in shared memory
+    uint64_t* mb_qd = mb_go + 12;      // [2] QKV output of a tile ready in buffer 0 / 1     (tcgen05.commit)
+    uint64_t* mb_qf = mb_go + 14;      // QKV buffer 0 has been read (tile 0's epilogue)     (one arrival per epilogue warp)
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kSmTmem);
 
     if (warp == kEpiWarps) tmem_alloc(s_tmem, 512);
@@ -210,6 +212,8 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
         mbar_init(mb_wa, 1);
         mbar_init(mb_wb, 1);
         mbar_init(mb_w1, 1);
+        mbar_init(mb_qd, 1); mbar_init(mb_qd + 1, 1);
+        mbar_init(mb_qf, kEpiWarps);
         mbar_init(mb_h, 1); mbar_init(mb_h + 1, 1);
         mbar_init(mb_y, 1); mbar_init(mb_y + 1, 1);
         mbar_init(mb_g, kEpiWarps); mbar_init(mb_g + 1, kEpiWarps);
@@ -291,17 +295,21 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                     mma_ts_elect(tbase + y_col, a, bl, id48, true);
                 }
             };
-            uint32_t h_ph[2] = {0, 0}, y_ph[2] = {0, 0}, g_ph[2] = {0, 0}, yfree_ph = 0;
+            uint32_t h_ph[2] = {0, 0}, y_ph[2] = {0, 0}, g_ph[2] = {0, 0}, yfree_ph = 0, qf_ph = 0;
             auto wait_on = [&](uint64_t* bar, uint32_t& ph) { TC_TRACE(0); mbar_wait(bar, ph); ph ^= 1; tc_fence_after(); TC_TRACE(0); };
             bool first = true;
             for (int trk = blockIdx.x; trk < n; trk += gridDim.x) {
                 const bool last_track = trk + (int)gridDim.x >= n;
                 for (int blk = 0; blk < kDepth; ++blk) {
                     if (first) { load_wa(0); load_w1(0); first = false; }
-                    wait_go();                                                   // 1: LN1 operands of all tiles
+                    // QKV per tile, overlapped with the LayerNorms / epilogues of the other tiles (two output buffers)
+                    wait_go();                                                   // 1a: LN1 operand of tile 0
                     mbar_wait(mb_wa, wa_ph); wa_ph ^= 1;
-                    qkv(0, kColBig); qkv(1, kColBig + 160); mma_commit_elect(mb_done);
-                    wait_go(); qkv(2, kColBig); mma_commit_elect(mb_done);             // 2
+                    qkv(0, kColBig); mma_commit_elect(mb_qd);
+                    wait_go(); qkv(1, kColBig + 160); mma_commit_elect(mb_qd + 1);     // 1b
+                    wait_go();                                                   // 1c: LN1 operand of tile 2
+                    wait_on(mb_qf, qf_ph);                                       // 2: tile 0's QKV output has been read
+                    qkv(2, kColBig); mma_commit_elect(mb_qd);
                     wait_go(); scores(0); mma_commit_elect(mb_done);                   // 3: K, V' complete
                     wait_go(); pv(0); scores(1); mma_commit_elect(mb_done);            // 4: P(0) written; S(1) reuses the columns in issue order
                     wait_go(); pv(1); scores(2); mma_commit_elect(mb_done);            // 5
@@ -341,7 +349,7 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
         const int s = e.s, row = e.row;
         const float scale = 0.14433756729740643f;                 // 48 ** -0.5
         const float kLog2e = 1.4426950408889634f;
-        uint32_t h_ph[2] = {0, 0}, y_ph[2] = {0, 0};
+        uint32_t h_ph[2] = {0, 0}, y_ph[2] = {0, 0}, qd_ph[2] = {0, 0};
         // softmax: the 20 groups of 16 score columns are dealt to the column groups (7,7,6 or 4,4,3,3,3,3)
         constexpr int kSmBase = 20 / kNS, kSmRem = 20 % kNS;
         const int sm_groups = kSmBase + (s < kSmRem ? 1 : 0);
@@ -376,12 +384,12 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                 const float* par = s_par + blk * kTcParFloats;
 
 #pragma unroll
-                for (int t = 0; t < 3; ++t) {      // LayerNorm 1 -> the tiles' A-operand slots
+                for (int t = 0; t < 3; ++t) {      // LayerNorm 1 -> the tiles' A-operand slots; each tile's QKV GEMM starts at once
                     float y[kCW];
                     e.ln(x[t], par + kPLn1g, par + kPLn1b, y);
                     if (e.active(t)) e.store_opa(t, y);
+                    e.signal_go(false);         // -> 1a, 1b, 1c  (the LayerNorm barriers keep the three phases apart)
                 }
-                e.signal_go(false);             // -> 1
 
                 // ---- QKV epilogue: a column group handles kQW of the 144 output columns: part 0 -> q (scaled) into the
                 //      tile's A slot, part 1 -> K rows, part 2 -> V rows (shared memory, UMMA layouts)
@@ -422,13 +430,9 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                         }
                     }
                 };
-                e.wait_done();
-                epi_qkv(0, kColBig);
-                epi_qkv(1, kColBig + 160);
-                e.signal_go(true);              // -> 2
-                e.wait_done();
-                epi_qkv(2, kColBig);
-                e.signal_go(true);              // -> 3
+                e.wait_bar(mb_qd, qd_ph[0]);      epi_qkv(0, kColBig);        e.signal(mb_qf, true);     // -> 2 (buffer 0 free)
+                e.wait_bar(mb_qd + 1, qd_ph[1]);  epi_qkv(1, kColBig + 160);
+                e.wait_bar(mb_qd, qd_ph[0]);      epi_qkv(2, kColBig);        e.signal_go(true);         // -> 3
 
                 // ---- attention per tile -------------------------------------------------------------------
                 auto softmax = [&](int t) {
