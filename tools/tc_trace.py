@@ -23,7 +23,7 @@ print("control events", n[0], "epilogue events", n[1])
 # control: pairs (before wait_go, after wait_go); epilogue: pairs (before wait_done, after wait_done)
 cw = ctl.reshape(-1, 2); ew = epi.reshape(-1, 2)
 t0 = min(cw[0, 0], ew[0, 0])
-names = ["qkv01", "qkv2", "S0", "PV0+S1", "PV1+S2", "PV2", "h_A(fc1_0)", "h_B(fc1_1)", "y_A(fc2_0)", "h_A(fc1_2)", "y_B(fc2_1)", "y_A(fc2_2)"]
+names = ["qkv0", "qkv1", "qkv2", "S0", "PV0+S1", "PV1+S2", "PV2", "h_A(fc1_0)", "h_B(fc1_1)", "y_A(fc2_0)", "h_A(fc1_2)", "y_B(fc2_1)", "y_A(fc2_2)"]
 print("epilogue-side view (control-side columns are not aligned with these rows in the MLP phase)")
 print(f"{'step':10s} {'ctl_wait_go':>11s} {'issue':>7s} {'epi_wait_done':>13s} {'epilogue':>9s}")
 tot = dict(wg=0, iss=0, wd=0, ep=0)

@@ -202,6 +202,7 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
     uint64_t* mb_yfree = mb_go + 10;   // Y_A has been read, may be overwritten      (one arrival per epilogue warp)
     uint64_t* mb_w1 = mb_go + 11;      // W1 landed in shared memory
     uint64_t* mb_qd = mb_go + 12;      // [2] QKV output of a tile ready in buffer 0 / 1     (tcgen05.commit)
+    uint64_t* mb_pa = mb_go + 15;      // first part of P (keys 0..159) written            (one arrival per epilogue warp)
     uint64_t* mb_qf = mb_go + 14;      // QKV buffer 0 has been read (tile 0's epilogue)     (one arrival per epilogue warp)
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kSmTmem);
 
@@ -214,6 +215,7 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
         mbar_init(mb_w1, 1);
         mbar_init(mb_qd, 1); mbar_init(mb_qd + 1, 1);
         mbar_init(mb_qf, kEpiWarps);
+        mbar_init(mb_pa, kEpiWarps);
         mbar_init(mb_h, 1); mbar_init(mb_h + 1, 1);
         mbar_init(mb_y, 1); mbar_init(mb_y + 1, 1);
         mbar_init(mb_g, kEpiWarps); mbar_init(mb_g + 1, kEpiWarps);
@@ -253,28 +255,25 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
             auto qkv = [&](int t, uint32_t d_col) { gemm_k48(t, d_col, kSmWa, kSmWa + 13824, 144, id144); };
             auto fc1 = [&](int t, uint32_t h_col) { gemm_k48(t, h_col, kSmW1hi, kSmW1lo, 192, id192); };
             // S = q k^T over 320 keys as two N = 160 halves; K operand K-major [k/8][320][8]
-            auto scores = [&](int t) {
+            auto scores_half = [&](int t, int half) {
                 const uint32_t a = tbase + kColOpa + 48 * t;
+                const uint32_t d = tbase + kColBig + 160 * half;
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const uint32_t d = tbase + kColBig + 160 * half;
-#pragma unroll
-                    for (int ks = 0; ks < 3; ++ks) {
-                        const uint32_t off = ks * 2 * (kN * 16) + half * 160 * 16;
-                        const uint64_t bh = smem_desc(sbase + kSmKhi + off, kN * 16, 128);
-                        const uint64_t bl = smem_desc(sbase + kSmKlo + off, kN * 16, 128);
-                        mma_ts_elect(d, a + 8 * ks, bh, id160, ks > 0);
-                        mma_ts_elect(d, a + 24 + 8 * ks, bh, id160, true);
-                        mma_ts_elect(d, a + 8 * ks, bl, id160, true);
-                    }
+                for (int ks = 0; ks < 3; ++ks) {
+                    const uint32_t off = ks * 2 * (kN * 16) + half * 160 * 16;
+                    const uint64_t bh = smem_desc(sbase + kSmKhi + off, kN * 16, 128);
+                    const uint64_t bl = smem_desc(sbase + kSmKlo + off, kN * 16, 128);
+                    mma_ts_elect(d, a + 8 * ks, bh, id160, ks > 0);
+                    mma_ts_elect(d, a + 24 + 8 * ks, bh, id160, true);
+                    mma_ts_elect(d, a + 8 * ks, bl, id160, true);
                 }
             };
             // O' = P V' accumulated in the tile's (now dead) q slot: P in TMEM (16-key group g: hi cols 16g.., lo cols 16g+8..),
-            // V' = V Wproj^T MN-major [f/8][key/8][key%8][f%8]
-            auto pv = [&](int t) {
+            // V' = V Wproj^T MN-major [f/8][key/8][key%8][f%8]; key groups [g0, g1)
+            auto pv = [&](int t, int g0, int g1) {
                 const uint32_t d = tbase + kColOpa + 48 * t;
-#pragma unroll 4
-                for (int g = 0; g < kN / 16; ++g) {
+#pragma unroll 5
+                for (int g = g0; g < g1; ++g) {
                     const uint32_t a = tbase + kColBig + 16 * g;
                     const uint64_t bh = smem_desc(sbase + kSmVhi + g * 256, 128, (kN / 8) * 128);
                     const uint64_t bl = smem_desc(sbase + kSmVlo + g * 256, 128, (kN / 8) * 128);
@@ -295,7 +294,7 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                     mma_ts_elect(tbase + y_col, a, bl, id48, true);
                 }
             };
-            uint32_t h_ph[2] = {0, 0}, y_ph[2] = {0, 0}, g_ph[2] = {0, 0}, yfree_ph = 0, qf_ph = 0;
+            uint32_t h_ph[2] = {0, 0}, y_ph[2] = {0, 0}, g_ph[2] = {0, 0}, yfree_ph = 0, qf_ph = 0, pa_ph = 0;
             auto wait_on = [&](uint64_t* bar, uint32_t& ph) { TC_TRACE(0); mbar_wait(bar, ph); ph ^= 1; tc_fence_after(); TC_TRACE(0); };
             bool first = true;
             for (int trk = blockIdx.x; trk < n; trk += gridDim.x) {
@@ -310,10 +309,25 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                     wait_go();                                                   // 1c: LN1 operand of tile 2
                     wait_on(mb_qf, qf_ph);                                       // 2: tile 0's QKV output has been read
                     qkv(2, kColBig); mma_commit_elect(mb_qd);
-                    wait_go(); scores(0); mma_commit_elect(mb_done);                   // 3: K, V' complete
-                    wait_go(); pv(0); scores(1); mma_commit_elect(mb_done);            // 4: P(0) written; S(1) reuses the columns in issue order
-                    wait_go(); pv(1); scores(2); mma_commit_elect(mb_done);            // 5
-                    wait_go(); pv(2); mma_commit_elect(mb_done);                       // 6
+                    wait_go(); scores_half(0, 0); scores_half(0, 1); mma_commit_elect(mb_done);     // 3: K, V' complete
+                    // per tile: the softmax publishes P in two parts (keys 0..159 first); P V' of a part and the next tile's scores
+                    // over the same columns are issued behind it, in that order, while the epilogue warps go on with the other part
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        wait_on(mb_pa, pa_ph);                                   // 4a: P(t), key groups 0..9 (at least)
+#ifdef VT_TC_LATE_ISSUE
+                        wait_go();
+                        pv(t, 0, 10);
+                        if (t < 2) scores_half(t + 1, 0);
+#else
+                        pv(t, 0, 10);
+                        if (t < 2) scores_half(t + 1, 0);
+                        wait_go();                                               // 4b: all of P(t)
+#endif
+                        pv(t, 10, 20);
+                        if (t < 2) scores_half(t + 1, 1);
+                        mma_commit_elect(mb_done);
+                    }
                     wait_go(); load_w2(blk);                                     // 7: attention output + LN2 of every tile done; K/V' dead
                     if (!(last_track && blk == kDepth - 1)) load_wa((blk + 1) % kDepth);
                     mbar_wait(mb_w1, w1_ph); w1_ph ^= 1;                         // W1 was prefetched during attention
@@ -350,10 +364,6 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
         const float scale = 0.14433756729740643f;                 // 48 ** -0.5
         const float kLog2e = 1.4426950408889634f;
         uint32_t h_ph[2] = {0, 0}, y_ph[2] = {0, 0}, qd_ph[2] = {0, 0};
-        // softmax: the 20 groups of 16 score columns are dealt to the column groups (7,7,6 or 4,4,3,3,3,3)
-        constexpr int kSmBase = 20 / kNS, kSmRem = 20 % kNS;
-        const int sm_groups = kSmBase + (s < kSmRem ? 1 : 0);
-        const int sm_begin = 16 * (s * kSmBase + (s < kSmRem ? s : kSmRem));
         // QKV epilogue: which of q / K / V this column group handles, and where inside its 48 columns
         const int qkv_part = (s * kQW) / 48, qkv_off = (s * kQW) % 48;
 
@@ -436,20 +446,24 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
 
                 // ---- attention per tile -------------------------------------------------------------------
                 auto softmax = [&](int t) {
-                    // TMEM loads are software pipelined (group g+1 is in flight while group g is processed)
-                    constexpr int kMaxGroups = kSmBase + (kSmRem ? 1 : 0);
-                    const uint32_t a0 = e.taddr(kColBig + sm_begin);
+                    // the 20 groups of 16 score columns are dealt round-robin: column group s owns groups s, s + kNS, ...  After
+                    // kRoundsA rounds every group of keys 0..159 is done and is published on its own barrier, so that the tensor
+                    // pipe starts P V' (and the next tile's scores over those columns) while the remaining rounds are computed.
+                    // TMEM loads are software pipelined (the next group is in flight while one is processed).
+                    constexpr int kRounds = (20 + kNS - 1) / kNS;          // 4 (kNS = 6) or 7 (kNS = 3)
+                    constexpr int kRoundsA = (10 + kNS - 1) / kNS;         // 2 or 4: rounds that cover key groups 0..9
+                    const int my_groups = (20 - s + kNS - 1) / kNS;
+                    const uint32_t a0 = e.taddr(kColBig + 16 * s);
                     float m = -INFINITY;
                     if (e.active(t)) {
-                        uint32_t r[2][16];
-                        tmem_ld16(a0, r[0]);
 #pragma unroll
-                        for (int g = 0; g < kMaxGroups; ++g) {
-                            if (g < sm_groups) {
+                        for (int k = 0; k < kRounds; ++k) {
+                            if (k < my_groups) {
+                                uint32_t r[16];
+                                tmem_ld16(a0 + 16 * kNS * k, r);
                                 tc_wait_ld();
-                                if (g + 1 < sm_groups) tmem_ld16(a0 + 16 * (g + 1), r[(g + 1) & 1]);
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(r[g & 1][j]));
+                                for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(r[j]));
                             }
                         }
                     }
@@ -460,31 +474,30 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
 #pragma unroll
                     for (int g = 1; g < kNS; ++g) m = fmaxf(m, rm[g * 128 + row]);
                     float l = 0.f;
-                    if (e.active(t)) {
-                        const float mb = m * kLog2e;
-                        uint32_t r[2][16];
-                        tmem_ld16(a0, r[0]);
+                    const float mb = m * kLog2e;
 #pragma unroll
-                        for (int g = 0; g < kMaxGroups; ++g) {
-                            if (g < sm_groups) {
-                                tc_wait_ld();
-                                if (g + 1 < sm_groups) tmem_ld16(a0 + 16 * (g + 1), r[(g + 1) & 1]);
-                                uint32_t hi[8], lo[8];
-                                float l0 = 0.f, l1 = 0.f;
+                    for (int k = 0; k < kRounds; ++k) {
+                        if (e.active(t) && k < my_groups) {
+                            uint32_t r[16];
+                            tmem_ld16(a0 + 16 * kNS * k, r);
+                            tc_wait_ld();
+                            uint32_t hi[8], lo[8];
+                            float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const float p0 = ex2_approx(fmaf(__uint_as_float(r[g & 1][2 * j]), kLog2e, -mb));
-                                    const float p1 = ex2_approx(fmaf(__uint_as_float(r[g & 1][2 * j + 1]), kLog2e, -mb));
-                                    l0 += p0; l1 += p1;
-                                    split_pack2(p0, p1, hi[j], lo[j]);
-                                }
-                                l += l0 + l1;
-                                tmem_st8(a0 + 16 * g, hi);       // P overwrites S in place: [hi x8 | lo x8] per 16 keys
-                                tmem_st8(a0 + 16 * g + 8, lo);
+                            for (int j = 0; j < 8; ++j) {
+                                const float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), kLog2e, -mb));
+                                const float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), kLog2e, -mb));
+                                l0 += p0; l1 += p1;
+                                split_pack2(p0, p1, hi[j], lo[j]);
                             }
+                            l += l0 + l1;
+                            tmem_st8(a0 + 16 * kNS * k, hi);       // P overwrites S in place: [hi x8 | lo x8] per 16 keys
+                            tmem_st8(a0 + 16 * kNS * k + 8, lo);
                         }
+                        if (k == kRoundsA - 1) e.signal(mb_pa, false);           // -> 4a
                     }
                     e.red[(3 + (t & 1)) * (kNS * 128) + s * 128 + row] = l;     // summed in epi_out(t)
+                    e.signal_go(false);                                          // -> 4b
                 };
                 // attention output of tile t: x += (P V')/l + bproj (V' carries the output projection), then LayerNorm 2 -> A slot.
                 // O' sits in the tile's own slot: every thread reads its columns before the LayerNorm barriers, writes after.
@@ -506,26 +519,25 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                     e.ln(x[t], par + kPLn2g, par + kPLn2b, y);
                     if (e.active(t)) e.store_opa(t, y);
                 };
-                e.wait_done(); softmax(0); e.signal_go(false);                    // -> 4
-                e.wait_done(); softmax(1); e.signal_go(false); epi_out(0);        // -> 5   (epi_out overlaps P V' (1) and S(2))
-                e.wait_done(); softmax(2); e.signal_go(false); epi_out(1);        // -> 6
+                e.wait_done(); softmax(0);
+                e.wait_done(); softmax(1); epi_out(0);        // epi_out overlaps P V' (1) and S(2)
+                e.wait_done(); softmax(2); epi_out(1);
                 e.wait_done(); epi_out(2); e.signal_go(false);                    // -> 7
 
                 // ---- MLP per tile -------------------------------------------------------------------------
                 auto gelu = [&](int t, uint32_t h_col) {
                     if (!e.active(t)) return;
                     const uint32_t a0 = e.taddr(h_col + kHW * s);                 // group s owns hidden columns [kHW s, kHW s + kHW)
-                    uint32_t r[2][16];
-                    tmem_ld16(a0, r[0]);
 #pragma unroll
                     for (int g = 0; g < kHW / 16; ++g) {
+                        uint32_t r[16];
+                        tmem_ld16(a0 + 16 * g, r);
                         tc_wait_ld();
-                        if (g + 1 < kHW / 16) tmem_ld16(a0 + 16 * (g + 1), r[(g + 1) & 1]);
                         uint32_t hi[8], lo[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float h0 = gelu_erf(__uint_as_float(r[g & 1][2 * j]) + par[kPBfc1 + kHW * s + 16 * g + 2 * j]);
-                            const float h1 = gelu_erf(__uint_as_float(r[g & 1][2 * j + 1]) + par[kPBfc1 + kHW * s + 16 * g + 2 * j + 1]);
+                            const float h0 = gelu_erf(__uint_as_float(r[2 * j]) + par[kPBfc1 + kHW * s + 16 * g + 2 * j]);
+                            const float h1 = gelu_erf(__uint_as_float(r[2 * j + 1]) + par[kPBfc1 + kHW * s + 16 * g + 2 * j + 1]);
                             split_pack2(h0, h1, hi[j], lo[j]);
                         }
                         tmem_st8(a0 + 16 * g, hi);
