@@ -27,6 +27,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+_JSON_OUT = sys.stdout
 METRIC = "tracked frames/sec over B concurrent tracks"
 UNIT = "frames/s"
 FLOP_BLOCKS = 112.07e6        # algorithmic FLOP per tracked frame in the 3 ViT blocks
@@ -190,7 +191,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                              "sample": f"{tracks} tracks x {args.steps} steps, cv2 crop + torch fp32 forward batched by 16 + decode"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 def workload_config(args, world, note=None):
@@ -224,6 +225,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries the one JSON line and nothing else: library chatter (e.g. NCCL's version banner) goes to stderr
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -238,7 +244,6 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = load_cfg()
@@ -260,11 +265,20 @@ def main():
     fidx_host = np.arange(n, dtype=np.int64) % F
     step_offsets = [torch.from_numpy(((fidx_host + t) % F) * pool.frame_bytes).to(dev) for t in range(F)]
 
+    pending = [None]
+
+    def finish_gather():
+        if pending[0] is not None:
+            pending[0].wait()                 # current stream waits for the gather of the previous step
+            pending[0] = None
+
     def step(t):
         bt.engine.tracks_set_state(step_boxes[t % nsets], first=0)
         out = bt.track_offsets(pool.data, step_offsets[t % F], update_state=True)
         if sharded is not None:
-            out = sharded.gather(out)
+            # the only exchange step: all-gather of (x, y, w, h, conf); it overlaps the next step's kernels
+            finish_gather()
+            pending[0], out = sharded.gather_async(out)
         return out
 
     def barrier():
@@ -275,6 +289,7 @@ def main():
 
     for t in range(W):
         step(t)
+    finish_gather()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -286,6 +301,7 @@ def main():
     e0.record()
     for t in range(K):
         step(W + t)
+    finish_gather()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -308,6 +324,8 @@ def main():
     host_out = torch.empty((n * world if world > 1 else n, 5), dtype=torch.float64).pin_memory()
     feeder = PipelinedFrameFeeder(F, FRAME_H, FRAME_W, dev, max_tracks=n)
 
+    prev = [None]
+
     def e2e_run(steps):
         feeder.upload(host_pools[0], host_boxes[0])
         for t in range(steps):
@@ -316,10 +334,18 @@ def main():
                 feeder.upload(host_pools[(t + 1) % 2], host_boxes[(t + 1) % nsets])
             bt.engine.tracks_set_state(fp.boxes, first=0)
             out = bt.track_offsets(fp.data, step_offsets[t % F], update_state=True)
-            if sharded is not None:
-                out = sharded.gather(out)
-            host_out.copy_(out, non_blocking=True)
             feeder.release(fp)
+            if sharded is not None:
+                # read back the PREVIOUS step's gathered boxes (its gather overlapped this step), then start this step's
+                if pending[0] is not None:
+                    finish_gather()
+                    host_out.copy_(prev[0], non_blocking=True)
+                pending[0], prev[0] = sharded.gather_async(out)
+            else:
+                host_out.copy_(out, non_blocking=True)
+        if sharded is not None:
+            finish_gather()
+            host_out.copy_(prev[0], non_blocking=True)
 
     e2e_run(3)
     barrier()
@@ -374,7 +400,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         v, cores, sample = cpu_sample(sd)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

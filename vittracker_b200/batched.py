@@ -159,20 +159,38 @@ class ShardedTracker:
     def n_local(self) -> int:
         return self.hi - self.lo
 
+    def _buffers(self, k: int, dev, dt):
+        if self._gather_buf is None or self._gather_buf[0].device != dev or self._gather_buf[0].dtype != dt:
+            self._gather_buf = [torch.zeros((self.world, self.max_local, 5), dtype=dt, device=dev) for _ in range(2)]
+            self._send_buf = [torch.zeros((self.max_local, 5), dtype=dt, device=dev) for _ in range(2)]
+        return self._gather_buf[k], self._send_buf[k]
+
+    def _ordered(self, buf: torch.Tensor) -> torch.Tensor:
+        if self.total % self.world == 0:
+            return buf.view(-1, 5)
+        parts = []
+        for r in range(self.world):
+            lo, hi = shard_range(self.total, r, self.world)
+            parts.append(buf[r, : hi - lo])
+        return torch.cat(parts, 0)
+
     def gather(self, local_boxes: torch.Tensor) -> torch.Tensor:
         """[n_local, 5] per rank -> [total, 5] on every rank, ordered by global track id."""
         if self.world == 1:
             return local_boxes
-        dev, dt = local_boxes.device, local_boxes.dtype
-        if self._gather_buf is None or self._gather_buf.device != dev or self._gather_buf.dtype != dt:
-            self._gather_buf = torch.zeros((self.world, self.max_local, 5), dtype=dt, device=dev)
-            self._send_buf = torch.zeros((self.max_local, 5), dtype=dt, device=dev)
-        self._send_buf[: self.n_local].copy_(local_boxes)
-        self.dist.all_gather_into_tensor(self._gather_buf.view(-1, 5), self._send_buf, group=self.group)
-        if self.total % self.world == 0:
-            return self._gather_buf.view(-1, 5)
-        parts = []
-        for r in range(self.world):
-            lo, hi = shard_range(self.total, r, self.world)
-            parts.append(self._gather_buf[r, : hi - lo])
-        return torch.cat(parts, 0)
+        buf, send = self._buffers(0, local_boxes.device, local_boxes.dtype)
+        send[: self.n_local].copy_(local_boxes)
+        self.dist.all_gather_into_tensor(buf.view(-1, 5), send, group=self.group)
+        return self._ordered(buf)
+
+    def gather_async(self, local_boxes: torch.Tensor):
+        """Start the gather of this step's boxes and return ``(work, result)``: the collective runs on NCCL's stream, so the
+        next step's kernels are not ordered behind it (nor behind the slowest rank); call ``work.wait()`` before reading
+        ``result`` ([total, 5], valid for two calls - the buffers alternate).  At most one gather may be outstanding."""
+        if self.world == 1:
+            return None, local_boxes
+        self._flip = getattr(self, "_flip", 0) ^ 1
+        buf, send = self._buffers(self._flip, local_boxes.device, local_boxes.dtype)
+        send[: self.n_local].copy_(local_boxes)
+        work = self.dist.all_gather_into_tensor(buf.view(-1, 5), send, group=self.group, async_op=True)
+        return work, (buf.view(-1, 5) if self.total % self.world == 0 else buf)
