@@ -1,0 +1,101 @@
+"""Batched multi-sequence driver (SURVEY 8f rank 1 + rank 4): scheduling over ragged sequences and the reference's result
+files, on a fake backend (no GPU); and on the GPU, equality with the drop-in tracker run sequence by sequence."""
+import os
+
+import numpy as np
+import pytest
+
+from vittracker_b200.sequences import MultiSequenceRunner, Sequence, results_path, run_sequences, save_tracker_output
+
+
+class FakeBackend:
+    """Box of a slot after k steps = init box + k in x; remembers which slot served which frame."""
+
+    def __init__(self, slots):
+        self.state = [None] * slots
+        self.log = []
+
+    def initialize(self, slot, image, box):
+        if box[2] <= 0:
+            raise Exception("Too small bounding box.")
+        self.state[slot] = [float(v) for v in box]
+
+    def park(self, slot):
+        self.state[slot] = [0.0, 0.0, 1.0, 1.0]
+
+    def step(self, images):
+        out = np.zeros((len(images), 5))
+        for i, im in enumerate(images):
+            if im is not None:
+                assert self.state[i] is not None
+                self.state[i][0] += 1.0
+                self.log.append((i, int(im[0, 0, 0])))
+            out[i, :4] = self.state[i]
+            out[i, 4] = 0.5
+        return out
+
+
+def _frames(n, tag):
+    return [np.full((4, 4, 3), tag, dtype=np.uint8) for _ in range(n)]
+
+
+def test_scheduler_ragged_sequences_and_result_files(tmp_path):
+    lengths = [5, 1, 3, 7, 2, 4]
+    seqs = [Sequence(f"s{i}", _frames(n, i), [10.0 * i + 0.7, 5.9, 20.5, 30.2], dataset="got10k" if i == 2 else "") for i, n in enumerate(lengths)]
+    seqs.append(Sequence("bad", _frames(3, 9), [1.0, 1.0, 0.0, 5.0]))          # init fails: reported and skipped
+    be = FakeBackend(3)
+    res = MultiSequenceRunner(be, 3, results_dir=str(tmp_path)).run(seqs)
+    assert set(res) == {f"s{i}" for i in range(len(lengths))}
+    for i, n in enumerate(lengths):
+        out = res[f"s{i}"]
+        if n == 1:
+            assert "target_bbox" not in out and len(out["time"]) == 1       # tracker.py:148-150
+            continue
+        assert len(out["target_bbox"]) == n and len(out["time"]) == n
+        assert out["target_bbox"][0] == seqs[i].init_bbox
+        assert [b[0] for b in out["target_bbox"]] == [seqs[i].init_bbox[0] + k for k in range(n)]
+        # every frame of the sequence was served by one slot, in order
+        assert [t for (_, t) in be.log if t == i] == [i] * (n - 1)
+    # the reference's file format: ints, tab separated; got10k goes into its own folder
+    got = np.loadtxt(results_path(str(tmp_path), seqs[0]) + ".txt", delimiter="\t")
+    assert got.shape == (5, 4) and got[0].tolist() == [0, 5, 20, 30] and got[3].tolist() == [3, 5, 20, 30]
+    assert os.path.isfile(os.path.join(str(tmp_path), "got10k", "s2.txt"))
+    assert np.loadtxt(results_path(str(tmp_path), seqs[0]) + "_time.txt").shape == (5,)
+    # resumable: sequences whose results exist are skipped (running.py:116-131)
+    be2 = FakeBackend(3)
+    res2 = MultiSequenceRunner(be2, 3, results_dir=str(tmp_path)).run(seqs[:5])
+    assert set(res2) == {"s1"} and not be2.log            # s1 has a single frame: no box file is ever written for it
+
+
+def test_save_tracker_output_truncates_like_astype_int(tmp_path):
+    s = Sequence("q", _frames(2, 0), [1, 2, 3, 4])
+    save_tracker_output(str(tmp_path), s, {"target_bbox": [[1.9, 2.1, 3.999, 4.5], [10.2, -0.5, 7.7, 8.0]], "time": [0.25, 0.5]})
+    assert open(os.path.join(str(tmp_path), "q.txt")).read() == "1\t2\t3\t4\n10\t0\t7\t8\n"
+    assert open(os.path.join(str(tmp_path), "q_time.txt")).read() == "0.250000\n0.500000\n"
+
+
+@pytest.mark.gpu
+def test_batched_sequences_match_the_dropin_tracker(tmp_path):
+    from oracle import vt_oracle as O
+    from vittracker_b200 import get_tracker_class, load_cfg, parameters
+    sd = O.make_state_dict(seed=31, stress=True, stable_size=True)
+    rng = np.random.default_rng(5)
+    seqs = []
+    for i, (n, (H, W)) in enumerate(zip([4, 1, 6, 3, 5], [(360, 640), (240, 320), (360, 640), (300, 500), (240, 320)])):
+        frames = O.synth_frames(n, H, W, seed=40 + i, smooth=True)
+        box = [float(rng.uniform(40, W - 140)), float(rng.uniform(40, H - 120)), float(rng.uniform(30, 90)), float(rng.uniform(30, 70))]
+        seqs.append(Sequence(f"seq{i}", list(frames), box))
+    res = run_sequences(seqs, load_cfg(), sd, slots=3, results_dir=str(tmp_path))
+    params = parameters("vit_48_h32_noKD")
+    params.state_dict = sd
+    for s in seqs:
+        trk = get_tracker_class()(params, "synthetic")
+        trk.initialize(s.frames[0], s.init_info())
+        want = [list(s.init_bbox)] + [list(trk.track(f, {})["target_bbox"]) for f in s.frames[1:]]
+        if len(s.frames) == 1:
+            assert "target_bbox" not in res[s.name]
+            continue
+        got = res[s.name]["target_bbox"]
+        assert len(got) == len(want)
+        assert np.allclose(np.array(got), np.array(want, dtype=np.float64), rtol=1e-6, atol=1e-6), (s.name, got, want)
+        assert os.path.isfile(os.path.join(str(tmp_path), s.name + ".txt"))

@@ -1,0 +1,226 @@
+"""Batched multi-sequence driver: many ``Sequence``s advanced concurrently on one GPU.
+
+The reference evaluates a dataset with ``multiprocessing.Pool`` - one process, one tracker, one sequence at a time per
+worker, ``worker_id % num_gpu`` picks the GPU (lib/test/evaluation/running.py:105-113,159-187) - and
+``Tracker._track_sequence`` (lib/test/evaluation/tracker.py:90-152) walks the frames.  Here ``slots`` sequences share one
+``BatchedTracker``: every step uploads the next frame of each running sequence, advances all of them with one
+``vt_tracks_step``, and a slot whose sequence ended is re-initialised with the next pending one (ragged lengths, mixed
+frame sizes).  Outputs keep the reference's shape - per sequence ``{'target_bbox': [[x, y, w, h], ...], 'time': [...]}``
+with the init box as entry 0 - and ``save_tracker_output`` writes the same ``<seq>.txt`` / ``<seq>_time.txt`` files
+(running.py:14-102), so the analysis tooling reads them unchanged."""
+from __future__ import annotations
+
+import os
+import time
+from typing import Callable, Dict, List, Optional, Sequence as Seq, Union
+
+import numpy as np
+
+Frame = Union[np.ndarray, str, Callable[[], np.ndarray]]
+
+
+class Sequence:
+    """What the driver needs of lib/test/evaluation/data.py:Sequence: a name, the frames (arrays, image paths or
+    zero-argument loaders) and the initial box [x, y, w, h]."""
+
+    def __init__(self, name: str, frames: Seq[Frame], init_bbox, dataset: str = ""):
+        self.name = name
+        self.frames = list(frames)
+        self.init_bbox = [float(v) for v in init_bbox]
+        self.dataset = dataset
+
+    def init_info(self) -> dict:
+        return {"init_bbox": list(self.init_bbox)}
+
+
+def read_image(frame: Frame) -> np.ndarray:
+    """HxWx3 uint8 RGB, as Tracker._read_image delivers it (tracker.py:282-289: cv.imread + BGR2RGB)."""
+    if isinstance(frame, np.ndarray):
+        return frame
+    if callable(frame):
+        return frame()
+    import cv2 as cv
+    im = cv.imread(frame)
+    if im is None:
+        raise FileNotFoundError(frame)
+    return cv.cvtColor(im, cv.COLOR_BGR2RGB)
+
+
+def results_path(results_dir: str, seq: Sequence) -> str:
+    """running.py:20-27: trackingnet / got10k results go into a folder named after the dataset."""
+    if seq.dataset in ("trackingnet", "got10k"):
+        return os.path.join(results_dir, seq.dataset, seq.name)
+    return os.path.join(results_dir, seq.name)
+
+
+def save_tracker_output(results_dir: str, seq: Sequence, output: dict) -> None:
+    """Same files as running.py:_save_tracker_output: boxes truncated to int, tab separated, '%d'; times '%f'."""
+    base = results_path(results_dir, seq)
+    os.makedirs(os.path.dirname(base), exist_ok=True)
+    if output.get("target_bbox"):
+        np.savetxt(base + ".txt", np.array(output["target_bbox"]).astype(int), delimiter="\t", fmt="%d")
+    if output.get("time"):
+        np.savetxt(base + "_time.txt", np.array(output["time"]).astype(float), delimiter="\t", fmt="%f")
+
+
+class _Slot:
+    __slots__ = ("seq", "next_frame", "output")
+
+    def __init__(self):
+        self.seq: Optional[Sequence] = None
+        self.next_frame = 0
+        self.output: Optional[dict] = None
+
+
+class BatchedBackend:
+    """The device side of the driver: per-slot initialise, one step for a prefix of slots.  Split from the scheduler so
+    that the scheduling logic is testable without a GPU."""
+
+    def __init__(self, cfg, state_dict, slots: int, device: Optional[int] = None, blocks_impl: str = "tcgen05"):
+        import torch
+        from .batched import BatchedTracker
+        self.torch = torch
+        self.bt = BatchedTracker(cfg, state_dict, max_tracks=slots, device=device, blocks_impl=blocks_impl)
+        self.dev = self.bt.device
+        self.slots = slots
+        self._cap = 0
+        self._pin = None
+        self._devbuf = None
+        self._hw = torch.zeros((slots, 2), dtype=torch.int32)
+        self._off = torch.zeros((slots,), dtype=torch.int64)
+        self._out_pin = torch.zeros((slots, 5), dtype=torch.float64).pin_memory()
+        # idle slots keep tracking a small black frame so that a step can always cover a contiguous slot range
+        self._dummy = np.zeros((64, 64, 3), dtype=np.uint8)
+        self._dummy_box = [24.0, 24.0, 16.0, 16.0]
+
+    def _stage(self, frames: List[np.ndarray]):
+        """Pack the frames into one pinned buffer, upload with one copy; returns per-frame byte offsets."""
+        torch = self.torch
+        sizes = [f.size for f in frames]
+        total = int(sum(sizes))
+        if total > self._cap:
+            self._cap = int(total * 1.25) + 1024
+            self._pin = torch.empty((self._cap,), dtype=torch.uint8).pin_memory()
+            self._devbuf = torch.empty((self._cap,), dtype=torch.uint8, device=self.dev)
+        offs, o = [], 0
+        pin = self._pin.numpy()
+        for f, n in zip(frames, sizes):
+            pin[o:o + n] = np.ascontiguousarray(f).reshape(-1)
+            offs.append(o)
+            o += n
+        self._devbuf[:total].copy_(self._pin[:total], non_blocking=True)
+        return offs
+
+    def initialize(self, slot: int, image: np.ndarray, box) -> None:
+        torch = self.torch
+        if image.dtype != np.uint8 or image.ndim != 3 or image.shape[2] != 3:
+            raise ValueError("image must be HxWx3 uint8")
+        offs = self._stage([image])
+        hw = torch.tensor([[image.shape[0], image.shape[1]]], dtype=torch.int32, device=self.dev)
+        off = torch.tensor(offs, dtype=torch.int64, device=self.dev)
+        b = torch.tensor([list(box)], dtype=torch.float64, device=self.dev)
+        status = self.bt.engine.tracks_init(self._devbuf, off, hw, b, first=slot)
+        code = int(status.cpu()[0])
+        if code == 1:
+            raise Exception("Too small bounding box.")                 # processing_utils.py:32-33
+        if code != 0:
+            raise ValueError("crop lies outside the image (undefined in the reference)")
+
+    def park(self, slot: int) -> None:
+        """Give an idle slot a valid template / state on the dummy frame."""
+        self.initialize(slot, self._dummy, self._dummy_box)
+
+    def step(self, images: List[Optional[np.ndarray]]) -> np.ndarray:
+        """images[i] = next frame of slot i (None = idle); returns [len(images), 5] boxes + confidence."""
+        torch = self.torch
+        n = len(images)
+        frames = [self._dummy if im is None else im for im in images]
+        offs = self._stage(frames)
+        for i, f in enumerate(frames):
+            self._hw[i, 0], self._hw[i, 1] = f.shape[0], f.shape[1]
+            self._off[i] = offs[i]
+        hw = self._hw[:n].to(self.dev, non_blocking=True)
+        off = self._off[:n].to(self.dev, non_blocking=True)
+        out = self.bt.engine.tracks_step(self._devbuf, off, hw, first=0, n=n, update_state=True)
+        self._out_pin[:n].copy_(out, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        return self._out_pin[:n].numpy().copy()
+
+
+class MultiSequenceRunner:
+    """``run(sequences)``: the batched counterpart of run_dataset + Tracker.run_sequence for one GPU."""
+
+    def __init__(self, backend, slots: int, results_dir: Optional[str] = None, skip_existing: bool = True, verbose: bool = False):
+        self.backend = backend
+        self.slots = [_Slot() for _ in range(slots)]
+        self.results_dir = results_dir
+        self.skip_existing = skip_existing
+        self.verbose = verbose
+        self._parked = [False] * slots
+
+    def _finish(self, slot: _Slot, results: Dict[str, dict]) -> None:
+        seq, out = slot.seq, slot.output
+        if len(out["target_bbox"]) <= 1:                               # tracker.py:148-150
+            out.pop("target_bbox")
+        results[seq.name] = out
+        if self.results_dir is not None:
+            save_tracker_output(self.results_dir, seq, out)
+        if self.verbose:
+            t = float(np.sum(out["time"]))
+            print("FPS: {}".format(len(out["time"]) / t if t > 0 else float("inf")))          # running.py:146-150
+        slot.seq, slot.output = None, None
+
+    def run(self, sequences: Seq[Sequence]) -> Dict[str, dict]:
+        pending = []
+        for s in sequences:
+            if self.results_dir is not None and self.skip_existing and os.path.isfile(results_path(self.results_dir, s) + ".txt"):
+                if self.verbose:
+                    print("FPS: {}".format(-1))                        # running.py:116-131: results exist, skip
+                continue
+            pending.append(s)
+        pending.reverse()
+        results: Dict[str, dict] = {}
+        while True:
+            # (re)fill free slots; a sequence whose initialisation fails is reported and skipped (running.py:135-142)
+            for i, slot in enumerate(self.slots):
+                while slot.seq is None and pending:
+                    seq = pending.pop()
+                    t0 = time.time()
+                    try:
+                        self.backend.initialize(i, read_image(seq.frames[0]), seq.init_bbox)
+                    except Exception as e:
+                        print(e)
+                        continue
+                    slot.seq, slot.next_frame = seq, 1
+                    slot.output = {"target_bbox": [list(seq.init_bbox)], "time": [time.time() - t0]}
+                    self._parked[i] = False
+                    if len(seq.frames) == 1:
+                        self._finish(slot, results)
+            active = [i for i, s in enumerate(self.slots) if s.seq is not None]
+            if not active:
+                break
+            high = max(active) + 1
+            for i in range(high):
+                if self.slots[i].seq is None and not self._parked[i]:
+                    self.backend.park(i)
+                    self._parked[i] = True
+            t0 = time.time()
+            images = [read_image(s.seq.frames[s.next_frame]) if s.seq is not None else None for s in self.slots[:high]]
+            boxes = self.backend.step(images)
+            dt = time.time() - t0
+            for i in active:
+                slot = self.slots[i]
+                slot.output["target_bbox"].append([float(v) for v in boxes[i, :4]])
+                slot.output["time"].append(dt)
+                slot.next_frame += 1
+                if slot.next_frame >= len(slot.seq.frames):
+                    self._finish(slot, results)
+        return results
+
+
+def run_sequences(sequences: Seq[Sequence], cfg, state_dict, slots: int = 64, results_dir: Optional[str] = None,
+                  device: Optional[int] = None, blocks_impl: str = "tcgen05", **kw) -> Dict[str, dict]:
+    """Track every sequence; ``slots`` run concurrently on one GPU."""
+    slots = max(1, min(slots, len(sequences)))
+    backend = BatchedBackend(cfg, state_dict, slots, device=device, blocks_impl=blocks_impl)
+    return MultiSequenceRunner(backend, slots, results_dir=results_dir, **kw).run(sequences)
