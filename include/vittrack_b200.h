@@ -15,6 +15,7 @@
  *   - No exceptions and no caller-visible allocation cross the ABI; the handle owns its
  *     workspace (allocated in vt_create / grown in vt_reserve).
  *   - There is no CPU fallback: without a CUDA device every compute entry point fails.
+ *   - An empty batch (n == 0) is a successful no-op; its data pointers may be null.
  */
 #ifndef VITTRACK_B200_H
 #define VITTRACK_B200_H

@@ -404,3 +404,65 @@ def test_sharded_tracks_nccl_gather_matches_single_gpu(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=600)
         assert p.returncode == 0 and "OK" in out, out[-3000:]
+
+
+# ------------------------------------------------------------------------------------------------
+# edge cases of the batched path: empty / ragged batches, extreme frame sizes, flagged tracks, odd row pitch
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("blocks", BLOCKS)
+def test_batched_edge_cases_against_oracle(cfg, blocks):
+    from vittracker_b200 import BatchedTracker
+    sd = O.make_state_dict(seed=12, stress=True)
+    model = O.OracleModel(sd)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    # frames of very different sizes in one buffer: tiny, odd width (row pitch not a multiple of 4), 4K
+    shapes = [(48, 64), (241, 321), (2160, 3840)]
+    frames = [O.synth_frames(2, H, W, seed=70 + i, smooth=(i != 1)) for i, (H, W) in enumerate(shapes)]
+    flat = np.concatenate([f.reshape(-1) for f in frames])
+    base = np.cumsum([0] + [f.size for f in frames])[:-1]
+    buf = torch.from_numpy(flat).to(dev)
+    #          frame set, init box                       (tracks 0-1 tiny, 2-4 odd pitch incl. a border-touching one, 5-6 4K)
+    tracks = [(0, [12.0, 10.0, 20.0, 16.0]), (0, [30.0, 20.0, 9.0, 11.0]),
+              (1, [100.5, 80.25, 40.0, 30.0]), (1, [0.0, 200.0, 25.0, 37.0]), (1, [290.0, 10.0, 30.0, 50.0]),
+              (2, [1800.0, 900.0, 400.0, 300.0]), (2, [3700.0, 2000.0, 90.0, 120.0])]
+    n = len(tracks)
+    bt = BatchedTracker(cfg, sd, max_tracks=n + 2, chunk_tracks=3, blocks_impl=blocks)          # ragged chunks: 3 + 3 + 1
+    hw = torch.tensor([list(shapes[s]) for s, _ in tracks], dtype=torch.int32, device=dev)
+    boxes = torch.tensor([b for _, b in tracks], dtype=torch.float64, device=dev)
+
+    def offsets(t):
+        return torch.tensor([int(base[s]) + t * int(np.prod(shapes[s])) * 3 for s, _ in tracks], dtype=torch.int64, device=dev)
+
+    # an empty batch is a no-op
+    empty = bt.engine.tracks_init(buf, offsets(0)[:0], hw[:0], boxes[:0], first=0)
+    assert empty.numel() == 0
+    st = bt.engine.tracks_init(buf, offsets(0), hw, boxes, first=0)
+    assert st.cpu().tolist() == [0] * n
+    out, det = bt.engine.tracks_step(buf, offsets(1), hw, first=0, n=n, update_state=True, detail=True)
+    out, det = out.cpu().numpy(), det.cpu().numpy()
+    for i, (s, b) in enumerate(tracks):
+        trk = O.OracleTracker(model)
+        trk.initialize(frames[s][0], {"init_bbox": list(b)})
+        want = trk.track(frames[s][1], {})
+        resp = trk.last["response"].flatten()
+        top = torch.topk(resp, 2).values
+        if float(top[0] - top[1]) < TIE_GAP:
+            continue
+        assert int(det[i, 5]) == int(resp.argmax()), (i, shapes[s])
+        assert close(out[i, :4], want["target_bbox"]), (i, out[i], want["target_bbox"])
+    # a track whose state was forced out of the image is flagged (confidence -1, state kept), its neighbours are unaffected
+    state = bt.engine.tracks_get_state(0, n).clone()
+    bad = state.clone()
+    bad[2] = torch.tensor([5000.0, 5000.0, 20.0, 20.0], dtype=torch.float64)
+    bad[5] = torch.tensor([10.0, 10.0, 0.0, 0.0], dtype=torch.float64)
+    bt.engine.tracks_set_state(bad.contiguous(), first=0)
+    out2 = bt.engine.tracks_step(buf, offsets(0), hw, first=0, n=n, update_state=True).cpu().numpy()
+    assert out2[2, 4] == -1.0 and out2[5, 4] == -1.0
+    assert np.array_equal(out2[2, :4], [5000.0, 5000.0, 20.0, 20.0])
+    bt.engine.tracks_set_state(state.contiguous(), first=0)
+    ref = bt.engine.tracks_step(buf, offsets(0), hw, first=0, n=n, update_state=False).cpu().numpy()
+    for i in (0, 1, 3, 4, 6):
+        assert np.array_equal(out2[i], ref[i]), i
+    # sub-range step: tracks [3, 6) only, results land at the front of the output
+    part = bt.engine.tracks_step(buf, offsets(0)[3:6].contiguous(), hw[3:6].contiguous(), first=3, n=3, update_state=False).cpu().numpy()
+    assert np.array_equal(part, ref[3:6])

@@ -671,6 +671,7 @@ int vt_crop_normalize(VtHandle h, const uint8_t* frames, const int64_t* frame_of
                       void* stream) {
     int rc = check_ready(h, false);
     if (rc) return rc;
+    if (n == 0) return VT_OK;                      // an empty batch is a no-op (its pointers may be null)
     if (!frames || !frame_offsets || !frame_hw || !boxes_xywh || !out_nchw || n < 0) return fail(h, VT_ERR_INVALID_ARG, "vt_crop_normalize: null pointer or negative n");
     if (out_size != 128 && out_size != 256) return fail(h, VT_ERR_UNSUPPORTED, "vt_crop_normalize: out_size must be 128 or 256");
     if (!(factor > 0)) return fail(h, VT_ERR_INVALID_ARG, "vt_crop_normalize: factor must be positive");
@@ -686,6 +687,7 @@ int vt_forward(VtHandle h, const float* z, const float* x, int32_t n, float* pre
                float* size_map, float* offset_map, float* taps, void* stream) {
     int rc = check_ready(h, false);
     if (rc) return rc;
+    if (n == 0) return VT_OK;
     if (!z || !x || n < 0) return fail(h, VT_ERR_INVALID_ARG, "vt_forward: null input or negative n");
     cudaStream_t st = (cudaStream_t)stream;
     VT_CUDA(h, cudaSetDevice(h->cfg.device));
@@ -742,6 +744,7 @@ int vt_tracks_init(VtHandle h, const uint8_t* frames, const int64_t* frame_offse
                    const double* boxes_xywh, int32_t first, int32_t n, int32_t* out_status, void* stream) {
     int rc = check_ready(h, false);
     if (rc) return rc;
+    if (n == 0) { h->tracks_ready = true; return VT_OK; }
     if (!frames || !frame_offsets || !frame_hw || !boxes_xywh) return fail(h, VT_ERR_INVALID_ARG, "vt_tracks_init: null pointer");
     if (first < 0 || n < 0 || first + n > h->cfg.max_tracks) return fail(h, VT_ERR_INVALID_ARG, "vt_tracks_init: tracks [%d, %d) exceed max_tracks %d", first, first + n, h->cfg.max_tracks);
     cudaStream_t st = (cudaStream_t)stream;
@@ -771,6 +774,7 @@ int vt_tracks_step(VtHandle h, const uint8_t* frames, const int64_t* frame_offse
                    int32_t first, int32_t n, double* out_boxes, double* out_detail, int32_t update_state, void* stream) {
     int rc = check_ready(h, true);
     if (rc) return rc;
+    if (n == 0) return VT_OK;
     if (!frames || !frame_offsets || !frame_hw || !out_boxes) return fail(h, VT_ERR_INVALID_ARG, "vt_tracks_step: null pointer");
     if (first < 0 || n < 0 || first + n > h->cfg.max_tracks) return fail(h, VT_ERR_INVALID_ARG, "vt_tracks_step: tracks [%d, %d) exceed max_tracks %d", first, first + n, h->cfg.max_tracks);
     cudaStream_t st = (cudaStream_t)stream;
