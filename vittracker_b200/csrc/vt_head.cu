@@ -51,15 +51,16 @@ static_assert(kHeadSmemBytes <= 227 * 1024, "head smem");
 constexpr int kTcAChunk = 18 * 16 * 16;                 // bytes of one 8-channel chunk image: 18 rows x 16 px x 16 B
 constexpr int kT_R0 = 0, kT_R0Bytes = 2 * 6 * kTcAChunk;                   // 55296
 constexpr int kT_Ring = kT_R0 + kT_R0Bytes, kT_PieceBytes = 2 * 6 * 48 * 16;   // piece (h, kx, ky): hi | lo, N = 48, K = 48 -> 9216
-constexpr int kT_R1 = kT_Ring + 3 * kT_PieceBytes, kT_R1Half = 12 * kTcAChunk; // 55296 per precision
+constexpr int kT_RingSlots = 5;                          // conv1 weight pieces in flight: 4 x 432 cycles of MMA cover an L2 round trip
+constexpr int kT_R1 = kT_Ring + kT_RingSlots * kT_PieceBytes, kT_R1Half = 12 * kTcAChunk; // 55296 per precision
 constexpr int kT_Out2 = kT_R1, kT_Out3 = kT_Out2 + 48 * kPlane * 4, kT_Out4 = kT_Out3 + 24 * kPlane * 4;
 constexpr int kT_Bias = kT_R1 + 2 * kT_R1Half;
 constexpr int kT_Maps = kT_Bias + 256 * 4;
 constexpr int kT_Red = kT_Maps + 6 * 256 * 4;
-constexpr int kT_Bar = kT_Red + 32 * 4;                 // loaded[3], consumed[3], acc_ready, w2_loaded, tmem base
-constexpr size_t kHeadTcSmemBytes = kT_Bar + 9 * 8;
+constexpr int kT_Bar = kT_Red + 32 * 4;                 // loaded[slots], consumed[slots], acc_ready, w2_loaded, tmem base
+constexpr size_t kHeadTcSmemBytes = kT_Bar + (2 * kT_RingSlots + 3) * 8;
 constexpr int kT_W2Bytes = 9 * 2 * 12 * 16 * 16;        // conv2 weights: (tower, kx) x [hi | lo] x K-major [12 chunks][16][8] = 55296
-static_assert(kT_W2Bytes <= kT_R0Bytes && kT_Out4 + 12 * kPlane * 4 <= kT_Bias && 3 * kT_PieceBytes >= 2 * kWChunk * 4, "head tc smem plan");
+static_assert(kT_W2Bytes <= kT_R0Bytes && kT_Out4 + 12 * kPlane * 4 <= kT_Bias && kT_RingSlots * kT_PieceBytes >= 2 * kWChunk * 4, "head tc smem plan");
 static_assert(kHeadTcSmemBytes <= 227 * 1024 && kT_Bar % 8 == 0 && kT_R1 % 128 == 0, "head smem (tc)");
 
 __device__ __forceinline__ void cp_async16(float* dst_smem, const float* src_gmem) {
@@ -270,11 +271,11 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
     float* maps = reinterpret_cast<float*>(sm8 + kT_Maps);
     float* red = reinterpret_cast<float*>(sm8 + kT_Red);
     float* wbuf = reinterpret_cast<float*>(sm8 + kT_Ring);
-    uint64_t* bar_loaded = reinterpret_cast<uint64_t*>(sm8 + kT_Bar);      // [3]
-    uint64_t* bar_consumed = bar_loaded + 3;                               // [3]
-    uint64_t* bar_acc = bar_loaded + 6;
-    uint64_t* bar_w2 = bar_loaded + 7;
-    uint32_t* tc_tmem = reinterpret_cast<uint32_t*>(bar_loaded + 8);
+    uint64_t* bar_loaded = reinterpret_cast<uint64_t*>(sm8 + kT_Bar);      // [kT_RingSlots]
+    uint64_t* bar_consumed = bar_loaded + kT_RingSlots;                    // [kT_RingSlots]
+    uint64_t* bar_acc = bar_loaded + 2 * kT_RingSlots;
+    uint64_t* bar_w2 = bar_acc + 1;
+    uint32_t* tc_tmem = reinterpret_cast<uint32_t*>(bar_acc + 2);
     const int trk = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int py = tid >> 4, px = tid & 15;
@@ -294,8 +295,15 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
     if (tid < 6) sb[204 + tid] = w.head.b5[tid];
     if (warp == 0) tc::tmem_alloc(tc_tmem, 512);
     if (tid == 32) {
-        for (int i = 0; i < 8; ++i) tc::mbar_init(bar_loaded + i, 1);
+        for (int i = 0; i < 2 * kT_RingSlots + 2; ++i) tc::mbar_init(bar_loaded + i, 1);
         tc::mbar_fence_init();
+    }
+    __syncthreads();
+    // the first conv1 weight pieces stream in underneath the LayerNorm
+    if (warp == 0) {
+#pragma unroll
+        for (int p = 0; p < kT_RingSlots - 1; ++p)
+            tc::bulk_g2s_elect(sm8 + kT_Ring + p * kT_PieceBytes, w.head_tc_w1 + (size_t)p * kT_PieceBytes, kT_PieceBytes, bar_loaded + p);
     }
     // ---- final LayerNorm -> conv1's operand image (fp16 hi | lo, 8-channel chunks) ----------------------------------
     {
@@ -327,22 +335,22 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
     {
         const uint32_t id48 = tc::instr_desc_f16(128, 48, false);
         auto load_piece = [&](int p) {
-            tc::bulk_g2s_elect(sm8 + kT_Ring + (p % 3) * kT_PieceBytes, w.head_tc_w1 + (size_t)p * kT_PieceBytes, kT_PieceBytes, bar_loaded + p % 3);
+            tc::bulk_g2s_elect(sm8 + kT_Ring + (p % kT_RingSlots) * kT_PieceBytes, w.head_tc_w1 + (size_t)p * kT_PieceBytes, kT_PieceBytes,
+                               bar_loaded + p % kT_RingSlots);
         };
-        if (warp == 0) { load_piece(0); load_piece(1); }
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
             if (warp == 0) {                     // convergent: every lane runs the program, one elected lane issues
 #pragma unroll 1
                 for (int q = 0; q < 9; ++q) {
                     const int p = 9 * h + q, kx = q / 3, ky = q % 3;
-                    if (p + 2 < 18) {
-                        if (p >= 1) tc::mbar_wait(bar_consumed + (p - 1) % 3, ((p - 1) / 3) & 1);    // ring slot of piece p-1 is free
-                        load_piece(p + 2);
+                    if (p + kT_RingSlots - 1 < 18) {
+                        if (p >= 1) tc::mbar_wait(bar_consumed + (p - 1) % kT_RingSlots, ((p - 1) / kT_RingSlots) & 1);    // ring slot of piece p-1 is free
+                        load_piece(p + kT_RingSlots - 1);
                     }
-                    tc::mbar_wait(bar_loaded + p % 3, (p / 3) & 1);
+                    tc::mbar_wait(bar_loaded + p % kT_RingSlots, (p / kT_RingSlots) & 1);
                     tc::tc_fence_after();
-                    const uint32_t wb = sbase + kT_Ring + (p % 3) * kT_PieceBytes;
+                    const uint32_t wb = sbase + kT_Ring + (p % kT_RingSlots) * kT_PieceBytes;
 #pragma unroll
                     for (int tl = 0; tl < 2; ++tl) {
                         const uint32_t d = tbase + (tl * 3 + kx) * 48;
@@ -358,7 +366,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
                             tc::mma_ss_elect(d, ah, bl, id48, 1);
                         }
                     }
-                    tc::mma_commit_elect(bar_consumed + p % 3);
+                    tc::mma_commit_elect(bar_consumed + p % kT_RingSlots);
                 }
                 tc::mma_commit_elect(bar_acc);
             }
