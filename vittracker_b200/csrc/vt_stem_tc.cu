@@ -75,183 +75,226 @@ struct TcConv {
     static constexpr int kStepsA = 6 * (CCH / 2) + ((CCH & 1) ? 3 : 0), kStepsB = 3 * (CCH / 2) + ((CCH & 1) ? 2 : 0);
     static constexpr int kWPrecBytes = (kStepsA + kStepsB) * 2 * NPAD * 16;   // one precision, two 8-wide chunks per K step
     static constexpr int kWBytes = 2 * kWPrecBytes;
+    static constexpr int kStages = 2;                            // A operand stages (bulk copies of item i+1 overlap MMA + epilogue of item i)
+    static constexpr int kStageBytes = 2 * kABytes;              // hi | lo
     static constexpr int kOffA = 0;
-    static constexpr int kOffW = 2 * kABytes;
+    static constexpr int kOffW = kStages * kStageBytes;
     static constexpr int kOffBias = kOffW + kWBytes;
-    static constexpr int kOffBar = kOffBias + NPAD * 4;
-    static constexpr int kSmemBytes = kOffBar + 32;
+    static constexpr int kOffXchg = kOffBias + NPAD * 4;         // row-split exchange (WOUT = 64 only): [tile pair or chunk][2][2][8] floats
+    static constexpr int kXchgFloats = 2 * 4 * 2 * 2 * 8;         // per epilogue group
+    static constexpr int kOffBar = kOffXchg + kXchgFloats * 4;   // w, full[2], afree[2], tfull[2], tfree[2], tmem base
+    static constexpr int kSmemBytes = kOffBar + 10 * 8;
     static constexpr int kCopies = 2 * 4 * CCH;                  // bulk copies per band: (precision, plane, chunk)
-    static constexpr int kTmemCols = (kTiles * 2 * NPAD <= 32) ? 32 : (kTiles * 2 * NPAD <= 64) ? 64 : (kTiles * 2 * NPAD <= 128) ? 128 : 256;
-    static constexpr int kThreads = 256;
+    static constexpr int kAccCols = kTiles * 2 * NPAD;           // TMEM columns of one item's accumulators (T_A | T_B per tile)
+    static constexpr int kTmemCols = (2 * kAccCols <= 32) ? 32 : (2 * kAccCols <= 64) ? 64 : (2 * kAccCols <= 128) ? 128 : (2 * kAccCols <= 256) ? 256 : 512;
+    static constexpr int kThreads = 544;                         // 2 x 8 epilogue warps (one group per accumulator set) + 1 control warp
     static_assert(NPAD % 16 == 0 && NPAD >= COUT && 128 % WOUT == 0 && kBR % kRowsPerTile == 0, "shape");
-    static_assert(kOffBar % 8 == 0 && kOffW % 128 == 0, "alignment");
+    static_assert(kOffBar % 8 == 0 && kOffW % 128 == 0 && kStageBytes % 128 == 0 && 2 * kAccCols <= 512, "alignment");
 };
 
 }  // namespace
 
-// grid: (Hout / 8 bands, n tracks).  in: plane images [n][tc_planes_bytes(CCH, WOUT)]; wt: packed fp16 hi|lo weight blob
-// in K-step order; bias fp32 [COUT].  OUT_PLANES: write the next layer's plane image (NEXT_CCH chunks, WOUT/2 wide),
-// else tokens [n][tok_stride_rows][COUT] + positional embedding.
+// Persistent: a CTA walks over work items (track, band of BR output rows).  in: plane images [n][tc_planes_bytes(CCH, WOUT)];
+// wt: packed fp16 hi|lo weight blob in K-step order (loaded once per CTA); bias fp32 [COUT].  OUT_PLANES: write the next
+// layer's plane image (NEXT_CCH chunks, WOUT/2 wide), else tokens [n][tok_stride_rows][COUT] + positional embedding.
+// Warp 16 = control (bulk copies of item i+1 while item i computes; single-thread MMA issue), warps 0-7 / 8-15 = the
+// epilogue groups of accumulator set 0 / 1; two A stages in shared memory and two accumulator sets in TMEM, handed over
+// through mbarriers.
 template <int CCH, int COUT, int NPAD, int WOUT, int BR, bool HSWISH, bool OUT_PLANES, int NEXT_CCH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(544)
 conv_s2_tc_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wt, const float* __restrict__ bias,
-                  void* __restrict__ outp, const float* __restrict__ pos, int tok_stride_rows, int tok_off) {
+                  void* __restrict__ outp, const float* __restrict__ pos, int tok_stride_rows, int tok_off, int n_items) {
     using K = TcConv<CCH, COUT, NPAD, WOUT, BR>;
+    constexpr int kBands = WOUT / BR;
     extern __shared__ __align__(128) uint8_t smem_tc[];
-    uint8_t* sA = smem_tc + K::kOffA;
     uint8_t* sW = smem_tc + K::kOffW;
     float* sBias = reinterpret_cast<float*>(smem_tc + K::kOffBias);
+    float* sXchg = reinterpret_cast<float*>(smem_tc + K::kOffXchg);
     uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem_tc + K::kOffBar);
-    uint64_t* bar_a = bar_w + 1;
-    uint64_t* bar_d = bar_w + 2;
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_w + 3);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int oy0 = blockIdx.x * K::kBR;
-    const int b = blockIdx.y;
+    uint64_t* bar_full = bar_w + 1;      // [2] A stage landed                    (kCopies expect_tx arrivals)
+    uint64_t* bar_afree = bar_w + 3;     // [2] A stage consumed by the MMAs      (tcgen05.commit)
+    uint64_t* bar_tfull = bar_w + 5;     // [2] accumulators complete             (tcgen05.commit)
+    uint64_t* bar_tfree = bar_w + 7;     // [2] accumulators read by the epilogue (8 warp arrivals)
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_w + 9);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int wid = tid >> 5;                    // 0-15 epilogue, 16 control
+    const int warp = wid & 7, group = wid >> 3;  // epilogue warp within its group; group = accumulator set it serves
 
-    if (warp == 0) tmem_alloc(s_tmem, K::kTmemCols);
-    if (tid == 32) { mbar_init(bar_w, 1); mbar_init(bar_a, K::kCopies); mbar_init(bar_d, 1); mbar_fence_init(); }
+    if (wid == 16) tmem_alloc(s_tmem, K::kTmemCols);
+    if (tid == 0) {
+        mbar_init(bar_w, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_full + i, K::kCopies); mbar_init(bar_afree + i, 1); mbar_init(bar_tfull + i, 1); mbar_init(bar_tfree + i, 8); }
+        mbar_fence_init();
+    }
     if (tid < NPAD) sBias[tid] = tid < COUT ? __ldg(bias + tid) : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = __shfl_sync(0xffffffffu, *s_tmem, 0);
 
-    if (warp == 0) {                 // convergent; the elected lane performs copies, MMAs and commits
-        // ---- stage weights and the band's plane rows [oy0, oy0 + 9) of every (precision, plane, chunk) ----
-        bulk_g2s_elect(sW, wt, K::kWBytes, bar_w);
-        const uint8_t* inb = in + (size_t)b * tc_planes_bytes(CCH, WOUT);
+    if (wid == 16) {                 // convergent; the elected lane performs copies, MMAs and commits
+        auto stage_item = [&](int item, int st) {     // plane rows [oy0, oy0 + BR + 1) of every (precision, plane, chunk)
+            const int b = item / kBands, oy0 = (item % kBands) * K::kBR;
+            const uint8_t* inb = in + (size_t)b * tc_planes_bytes(CCH, WOUT);
+            uint8_t* sA = smem_tc + K::kOffA + st * K::kStageBytes;
 #pragma unroll 1
-        for (int i = 0; i < K::kCopies; ++i) {
-            const int chunk = i % CCH, plane = (i / CCH) & 3, prec = i / (4 * CCH);
-            const size_t src = (((size_t)(prec * 4 + plane) * CCH + chunk) * (WOUT + 1) + oy0) * WOUT * 16;
-            bulk_g2s_elect(sA + prec * K::kABytes + (plane * CCH + chunk) * K::kChunkBytes, inb + src, K::kChunkBytes, bar_a);
-        }
+            for (int i = 0; i < K::kCopies; ++i) {
+                const int chunk = i % CCH, plane = (i / CCH) & 3, prec = i / (4 * CCH);
+                const size_t src = (((size_t)(prec * 4 + plane) * CCH + chunk) * (WOUT + 1) + oy0) * WOUT * 16;
+                bulk_g2s_elect(sA + prec * K::kABytes + (plane * CCH + chunk) * K::kChunkBytes, inb + src, K::kChunkBytes, bar_full + st);
+            }
+        };
+        bulk_g2s_elect(sW, wt, K::kWBytes, bar_w);
+        if ((int)blockIdx.x < n_items) stage_item(blockIdx.x, 0);
         const uint32_t sbase = smem_u32(smem_tc);
         const uint32_t idesc = instr_desc_f16(128, NPAD, false);
         mbar_wait(bar_w, 0);
-        mbar_wait(bar_a, 0);
-        tc_fence_after();
+        int it = 0;
 #pragma unroll 1
-        for (int tile = 0; tile < K::kTiles; ++tile) {          // rolled: the descriptors are affine in `tile`
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const int st = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            const int next = item + gridDim.x;
+            if (next < n_items) {                                   // prefetch the next item into the other stage
+                if (it >= 1) mbar_wait(bar_afree + (st ^ 1), ((it - 1) >> 1) & 1);      // its previous user's MMAs are done
+                stage_item(next, st ^ 1);
+            }
+            mbar_wait(bar_full + st, ph);
+            if (it >= 2) mbar_wait(bar_tfree + st, ((it - 2) >> 1) & 1);                // accumulator set st has been read
+            tc_fence_after();
+            const uint32_t abase = sbase + K::kOffA + st * K::kStageBytes;
+#pragma unroll 1
+            for (int tile = 0; tile < K::kTiles; ++tile) {          // rolled: the descriptors are affine in `tile`
 #pragma unroll
-            for (int acc = 0; acc < 2; ++acc) {                             // 0: T_A (kx = 1, 2)   1: T_B (kx = 0, shifted later)
-                const uint32_t d = tbase + (tile * 2 + acc) * NPAD;
-                const int nsteps = acc == 0 ? K::kStepsA : K::kStepsB;
+                for (int acc = 0; acc < 2; ++acc) {                             // 0: T_A (kx = 1, 2)   1: T_B (kx = 0, shifted later)
+                    const uint32_t d = tbase + st * K::kAccCols + (tile * 2 + acc) * NPAD;
+                    const int nsteps = acc == 0 ? K::kStepsA : K::kStepsB;
 #pragma unroll
-                for (int s = 0; s < nsteps; ++s) {
-                    int tap0, ch0, tap1, ch1; bool zero1;
-                    tcs_step(CCH, acc, s, tap0, ch0, tap1, ch1, zero1);
-                    int ky, kx, p0, r0, p1, r1;
-                    tcs_tap(acc, tap0, ky, kx); tcs_tap_pos(ky, kx, p0, r0);
-                    tcs_tap(acc, tap1, ky, kx); tcs_tap_pos(ky, kx, p1, r1);
-                    const uint32_t a0 = (p0 * CCH + ch0) * K::kChunkBytes + (tile * K::kRowsPerTile + r0) * WOUT * 16;
-                    const uint32_t a1 = (p1 * CCH + ch1) * K::kChunkBytes + (tile * K::kRowsPerTile + r1) * WOUT * 16;
-                    const uint32_t lbo = zero1 ? 16 : a1 - a0;              // > 0 by construction of the schedule; zero weights: any finite data
-                                                                            // inside the CTA's shared memory (one pixel further: at most 16 bytes into the next region)
-                    const uint64_t ah = smem_desc(sbase + K::kOffA + a0, lbo, 128);
-                    const uint64_t al = smem_desc(sbase + K::kOffA + K::kABytes + a0, lbo, 128);
-                    const uint32_t boff = ((acc == 0 ? 0 : K::kStepsA) + s) * 2 * NPAD * 16;
-                    const uint64_t bh = smem_desc(sbase + K::kOffW + boff, NPAD * 16, 128);
-                    const uint64_t bl = smem_desc(sbase + K::kOffW + K::kWPrecBytes + boff, NPAD * 16, 128);
-                    mma_ss_elect(d, ah, bh, idesc, s > 0 ? 1u : 0u);
-                    mma_ss_elect(d, al, bh, idesc, 1u);
-                    mma_ss_elect(d, ah, bl, idesc, 1u);
+                    for (int s2 = 0; s2 < nsteps; ++s2) {
+                        int tap0, ch0, tap1, ch1; bool zero1;
+                        tcs_step(CCH, acc, s2, tap0, ch0, tap1, ch1, zero1);
+                        int ky, kx, p0, r0, p1, r1;
+                        tcs_tap(acc, tap0, ky, kx); tcs_tap_pos(ky, kx, p0, r0);
+                        tcs_tap(acc, tap1, ky, kx); tcs_tap_pos(ky, kx, p1, r1);
+                        const uint32_t a0 = (p0 * CCH + ch0) * K::kChunkBytes + (tile * K::kRowsPerTile + r0) * WOUT * 16;
+                        const uint32_t a1 = (p1 * CCH + ch1) * K::kChunkBytes + (tile * K::kRowsPerTile + r1) * WOUT * 16;
+                        const uint32_t lbo = zero1 ? 16 : a1 - a0;              // > 0 by construction of the schedule; zero weights: any finite data
+                                                                                // inside the CTA's shared memory (one pixel further: at most 16 bytes into the next region)
+                        const uint64_t ah = smem_desc(abase + a0, lbo, 128);
+                        const uint64_t al = smem_desc(abase + K::kABytes + a0, lbo, 128);
+                        const uint32_t boff = ((acc == 0 ? 0 : K::kStepsA) + s2) * 2 * NPAD * 16;
+                        const uint64_t bh = smem_desc(sbase + K::kOffW + boff, NPAD * 16, 128);
+                        const uint64_t bl = smem_desc(sbase + K::kOffW + K::kWPrecBytes + boff, NPAD * 16, 128);
+                        mma_ss_elect(d, ah, bh, idesc, s2 > 0 ? 1u : 0u);
+                        mma_ss_elect(d, al, bh, idesc, 1u);
+                        mma_ss_elect(d, ah, bl, idesc, 1u);
+                    }
                 }
             }
+            mma_commit_elect(bar_afree + st);
+            mma_commit_elect(bar_tfull + st);
         }
-        mma_commit_elect(bar_d);
-    }
-    mbar_wait(bar_d, 0);
-    tc_fence_after();
-
-    // ---- epilogue: 8 warps = 2 (tile or channel half) x 4 TMEM lane quarters; thread -> one output pixel ------------------
-    {
+        __syncwarp();
+    } else {
+        // ---- epilogue: 8 warps = 2 (tile or channel half) x 4 TMEM lane quarters; thread -> one output pixel ------------------
         constexpr int kPasses = (K::kTiles >= 2) ? K::kTiles / 2 : 1;           // two tiles per pass, or one tile split by channels
         constexpr int kChPerThread = (K::kTiles >= 2) ? NPAD : NPAD / 2;
         static_assert(kChPerThread % 8 == 0 && (K::kTiles == 1 || K::kTiles % 2 == 0), "epilogue split");
         constexpr bool kSplitRows = WOUT > 32;                                  // TMEM lane quarter (= warp) shorter than an image row
-        static_assert(!kSplitRows || (WOUT == 64 && K::kTiles >= 2), "row split");
-        __shared__ float s_xchg[kSplitRows ? kPasses * (kChPerThread / 8) : 1][2][2][8];
+        static_assert(!kSplitRows || (WOUT == 64 && K::kTiles >= 2 && kPasses * (kChPerThread / 8) <= 4), "row split");
         const int chb = (K::kTiles >= 2) ? 0 : (warp >> 2) * kChPerThread;
         const int r = 32 * (warp & 3) + lane;                                   // row of the M tile = TMEM lane
+        int it = 0;
 #pragma unroll 1
-        for (int pass = 0; pass < kPasses; ++pass) {
-            const int tile = (K::kTiles >= 2) ? 2 * pass + (warp >> 2) : 0;
-            const int oy = oy0 + tile * K::kRowsPerTile + r / WOUT, ox = r % WOUT;
-            const uint32_t ta = tbase + ((uint32_t)(32 * (warp & 3)) << 16) + tile * 2 * NPAD + chb;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const int st = it & 1;
+            if (st != group) continue;                                          // the other group's accumulator set
+            const int b = item / kBands, oy0 = (item % kBands) * K::kBR;
+            mbar_wait(bar_tfull + st, (it >> 1) & 1);
+            tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 < kChPerThread; c0 += 8) {
-                uint32_t ra[8], rb[8];
-                tmem_ld8(ta + c0, ra);
-                tmem_ld8(ta + NPAD + c0, rb);
-                tc_wait_ld();
-                if constexpr (kSplitRows) {
-                    // an image row spans two warps: column 31's T_B crosses to column 32 through shared memory
-                    float* xs = s_xchg[pass * (kChPerThread / 8) + c0 / 8][warp >> 2][(warp & 3) >> 1];
-                    if (lane == 31 && !(warp & 1)) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) xs[j] = __uint_as_float(rb[j]);
-                    }
-                    __syncthreads();
-                }
-                float v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float tb = __shfl_up_sync(0xffffffffu, __uint_as_float(rb[j]), 1);     // T_B[oy][ox-1]
+            for (int pass = 0; pass < kPasses; ++pass) {
+                const int tile = (K::kTiles >= 2) ? 2 * pass + (warp >> 2) : 0;
+                const int oy = oy0 + tile * K::kRowsPerTile + r / WOUT, ox = r % WOUT;
+                const uint32_t ta = tbase + ((uint32_t)(32 * (warp & 3)) << 16) + st * K::kAccCols + tile * 2 * NPAD + chb;
+#pragma unroll 1
+                for (int c0 = 0; c0 < kChPerThread; c0 += 8) {
+                    uint32_t ra[8], rb[8];
+                    tmem_ld8(ta + c0, ra);
+                    tmem_ld8(ta + NPAD + c0, rb);
+                    tc_wait_ld();
+                    float* xs = sXchg + ((((group * 4 + pass * (kChPerThread / 8) + c0 / 8) * 2 + (warp >> 2)) * 2 + ((warp & 3) >> 1)) * 8);
                     if constexpr (kSplitRows) {
-                        if (lane == 0 && (warp & 1)) tb = s_xchg[pass * (kChPerThread / 8) + c0 / 8][warp >> 2][(warp & 3) >> 1][j];
-                    }
-                    if (ox == 0) tb = 0.f;
-                    float t = __uint_as_float(ra[j]) + tb + sBias[chb + c0 + j];
-                    if (HSWISH) t = t * fminf(fmaxf(t + 3.f, 0.f), 6.f) / 6.f;
-                    v[j] = (chb + c0 + j < COUT) ? t : 0.f;                         // padding channels stay exactly zero
-                }
-                if (chb + c0 >= COUT) continue;
-                if (OUT_PLANES) {
-                    // this layer's output pixel (oy, ox) is the next layer's input pixel: 8 channels = one chunk, hi | lo
-                    uint32_t hi[4], lo[4];
+                        // an image row spans two warps: column 31's T_B crosses to column 32 through shared memory
+                        if (lane == 31 && !(warp & 1)) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) split_pack2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
-                    uint8_t* ob = reinterpret_cast<uint8_t*>(outp) + (size_t)b * tc_planes_bytes(NEXT_CCH, WOUT / 2);
-                    const int chunk = (chb + c0) / 8;
-                    *reinterpret_cast<uint4*>(ob + tc_planes_offset(0, oy, ox, chunk, NEXT_CCH, WOUT / 2)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<uint4*>(ob + tc_planes_offset(1, oy, ox, chunk, NEXT_CCH, WOUT / 2)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                } else {
-                    const int tok = oy * WOUT + ox;
-                    float* o = reinterpret_cast<float*>(outp) + ((size_t)b * tok_stride_rows + tok_off + tok) * COUT + chb + c0;
-                    const float* pe = pos + (size_t)tok * COUT + chb + c0;
-                    const float4 e0 = __ldg(reinterpret_cast<const float4*>(pe)), e1 = __ldg(reinterpret_cast<const float4*>(pe + 4));
-                    *reinterpret_cast<float4*>(o) = make_float4(v[0] + e0.x, v[1] + e0.y, v[2] + e0.z, v[3] + e0.w);
-                    *reinterpret_cast<float4*>(o + 4) = make_float4(v[4] + e1.x, v[5] + e1.y, v[6] + e1.z, v[7] + e1.w);
+                            for (int j = 0; j < 8; ++j) xs[j] = __uint_as_float(rb[j]);
+                        }
+                        asm volatile("bar.sync %0, 256;" ::"r"(1 + group) : "memory");
+                    }
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float tb = __shfl_up_sync(0xffffffffu, __uint_as_float(rb[j]), 1);     // T_B[oy][ox-1]
+                        if constexpr (kSplitRows) {
+                            if (lane == 0 && (warp & 1)) tb = xs[j];
+                        }
+                        if (ox == 0) tb = 0.f;
+                        float t = __uint_as_float(ra[j]) + tb + sBias[chb + c0 + j];
+                        if (HSWISH) t = t * fminf(fmaxf(t + 3.f, 0.f), 6.f) / 6.f;
+                        v[j] = (chb + c0 + j < COUT) ? t : 0.f;                         // padding channels stay exactly zero
+                    }
+                    if (chb + c0 >= COUT) continue;
+                    if (OUT_PLANES) {
+                        // this layer's output pixel (oy, ox) is the next layer's input pixel: 8 channels = one chunk, hi | lo
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) split_pack2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+                        uint8_t* ob = reinterpret_cast<uint8_t*>(outp) + (size_t)b * tc_planes_bytes(NEXT_CCH, WOUT / 2);
+                        const int chunk = (chb + c0) / 8;
+                        *reinterpret_cast<uint4*>(ob + tc_planes_offset(0, oy, ox, chunk, NEXT_CCH, WOUT / 2)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(ob + tc_planes_offset(1, oy, ox, chunk, NEXT_CCH, WOUT / 2)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    } else {
+                        const int tok = oy * WOUT + ox;
+                        float* o = reinterpret_cast<float*>(outp) + ((size_t)b * tok_stride_rows + tok_off + tok) * COUT + chb + c0;
+                        const float* pe = pos + (size_t)tok * COUT + chb + c0;
+                        const float4 e0 = __ldg(reinterpret_cast<const float4*>(pe)), e1 = __ldg(reinterpret_cast<const float4*>(pe + 4));
+                        *reinterpret_cast<float4*>(o) = make_float4(v[0] + e0.x, v[1] + e0.y, v[2] + e0.z, v[3] + e0.w);
+                        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4] + e1.x, v[5] + e1.y, v[6] + e1.z, v[7] + e1.w);
+                    }
                 }
             }
+            // the row-split exchange slots are reused by the next item: every epilogue warp is past its reads
+            if constexpr (kSplitRows) asm volatile("bar.sync %0, 256;" ::"r"(1 + group) : "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tfree + st);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tbase, K::kTmemCols);
+    if (wid == 16) tmem_dealloc(tbase, K::kTmemCols);
 }
 
 template <int CCH, int COUT, int NPAD, int WOUT, int BR, bool HSWISH, bool OUT_PLANES, int NEXT_CCH>
-static int run_tc_conv(const uint8_t* in, int n, const uint8_t* wt, const float* bias, void* out, size_t out_track_bytes,
-                       const float* pos, int tok_stride_rows, int tok_off, cudaStream_t st) {
+static int run_tc_conv(const uint8_t* in, int n, const uint8_t* wt, const float* bias, void* out, const float* pos,
+                       int tok_stride_rows, int tok_off, cudaStream_t st) {
     using K = TcConv<CCH, COUT, NPAD, WOUT, BR>;
     auto kern = conv_s2_tc_kernel<CCH, COUT, NPAD, WOUT, BR, HSWISH, OUT_PLANES, NEXT_CCH>;
-    static bool configured = false;
-    if (!configured) {
+    static int grid_cap = 0;
+    if (grid_cap == 0) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::kSmemBytes) != cudaSuccess) return -1;
-        configured = true;
+        int dev = 0, sms = 0, per_sm = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K::kThreads, K::kSmemBytes) != cudaSuccess || per_sm < 1) return -1;
+        const int tmem_limit = 512 / K::kTmemCols;                  // resident CTAs also share the SM's 512 TMEM columns
+        grid_cap = sms * (per_sm < tmem_limit ? per_sm : tmem_limit);
     }
-    int launched = 0;
-    for (int first = 0; first < n; first += 32768) {
-        const int m = n - first < 32768 ? n - first : 32768;
-        kern<<<dim3(WOUT / K::kBR, m), 256, K::kSmemBytes, st>>>(in + (size_t)first * tc_planes_bytes(CCH, WOUT), wt, bias,
-                                                                 reinterpret_cast<uint8_t*>(out) + (size_t)first * out_track_bytes, pos,
-                                                                 tok_stride_rows, tok_off);
-        ++launched;
-    }
-    return cudaGetLastError() == cudaSuccess ? launched : -1;
+    const long long items = (long long)n * (WOUT / K::kBR);
+    if (items > 0x7fffffffLL) return -1;
+    const int grid = items < grid_cap ? (int)items : grid_cap;
+    kern<<<grid, K::kThreads, K::kSmemBytes, st>>>(in, wt, bias, out, pos, tok_stride_rows, tok_off, (int)items);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 // Search-branch layers on the tensor cores: conv2 (6 -> 12, 128x128 -> 64x64), conv3 (12 -> 24, -> 32x32), both with
@@ -260,13 +303,12 @@ int launch_stem234_tc(const uint8_t* planes2, int n, const ModelW& w, uint8_t* p
                       int tok_stride_rows, int tok_off, cudaStream_t st) {
     int total = 0, r;
     if ((r = run_tc_conv<kConv2Cch, 12, 16, kConv2Wout, kConv2BR, true, true, kConv3Cch>(planes2, n, w.stem_tc_w[0], w.stem_tc_b[0], planes3,
-                                                                               tc_planes_bytes(kConv3Cch, kConv3Wout), nullptr, 0, 0, st)) < 0) return r;
+                                                                               nullptr, 0, 0, st)) < 0) return r;
     total += r;
     if ((r = run_tc_conv<kConv3Cch, 24, 32, kConv3Wout, kConv3BR, true, true, kConv4Cch>(planes3, n, w.stem_tc_w[1], w.stem_tc_b[1], planes4,
-                                                                               tc_planes_bytes(kConv4Cch, kConv4Wout), nullptr, 0, 0, st)) < 0) return r;
+                                                                               nullptr, 0, 0, st)) < 0) return r;
     total += r;
-    if ((r = run_tc_conv<kConv4Cch, 48, 48, kConv4Wout, 8, false, false, 1>(planes4, n, w.stem_tc_w[2], w.stem_tc_b[2], tokens,
-                                                                          (size_t)tok_stride_rows * 48 * sizeof(float), w.pos_x,
+    if ((r = run_tc_conv<kConv4Cch, 48, 48, kConv4Wout, 8, false, false, 1>(planes4, n, w.stem_tc_w[2], w.stem_tc_b[2], tokens, w.pos_x,
                                                                           tok_stride_rows, tok_off, st)) < 0) return r;
     total += r;
     return total;
