@@ -32,4 +32,4 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.steps
 print(json.dumps({"config": "vit_768_h256_d12 (widest)", "tracks": n, "chunk": a.chunk, "ms_per_step": ms, "frames_per_s": n / ms * 1e3,
-                  "algorithmic_tflops": 66.65e9 * n / (ms * 1e-3) / 1e12, "path": "generic fp32 CUDA-core (im2col + tiled GEMM)"}))
+                  "algorithmic_tflops": 66.65e9 * n / (ms * 1e-3) / 1e12, "path": "generic: im2col + tcgen05 GEMM (fp16 hi/lo split, fp32 accumulate), fp32 CUDA-core GEMM for small shapes"}))

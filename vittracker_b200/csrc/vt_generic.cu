@@ -10,6 +10,7 @@
 // kernels use (vt_decode.cuh).  This path favours coverage over speed; the tuned kernels are vit_48_h32's.
 #include "vt_decode.cuh"
 #include "vt_internal.h"
+#include "vt_tc.cuh"
 
 namespace vt {
 
@@ -101,8 +102,162 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
     }
 }
 
+// ---- tcgen05 GEMM of the generic path: C = act(A B^T + bias) + R with fp32 operands in global memory ------------------------
+// A [M][K] and B [N][K] row-major (torch Linear / flattened conv weight).  A CTA owns a 128 x 128 output tile; four producer
+// warps turn 128 x 32 fp32 panels of A and B into fp16 hi | lo images in shared memory (no-swizzle K-major UMMA layout
+// [k/8][row][8]: a thread owns one row, so its 16-byte stores are conflict free), one thread issues hi*hi + lo*hi + hi*lo
+// tcgen05.mma (M = N = 128, K = 16) into a 128-column fp32 accumulator in TMEM, and the producer warps run the epilogue
+// (bias / ReLU / Hardswish / GELU / residual, thread = output row).  kTcStages panels are in flight behind mbarriers.
+constexpr int kTcBM = 128, kTcBN = 128, kTcBK = 32, kTcStages = 3;
+constexpr int kTcPanel = kTcBM * kTcBK * 2;                 // one operand, one precision: 8192 B
+constexpr int kTcStageBytes = 4 * kTcPanel;                 // A hi | A lo | B hi | B lo
+constexpr int kTcGemmSmem = kTcStages * kTcStageBytes + 2 * kTcStages * 8 + 8 + 16;      // 2 CTAs per SM
+constexpr int kTcGemmThreads = 9 * 32;                      // warps 0-3: A rows, 4-7: B rows (all eight: epilogue), 8: MMA issue
+
+__device__ __forceinline__ void gen_split8(const float4& u, const float4& v, uint4& hi, uint4& lo) {
+    tc::split_pack2(u.x, u.y, hi.x, lo.x);
+    tc::split_pack2(u.z, u.w, hi.y, lo.y);
+    tc::split_pack2(v.x, v.y, hi.z, lo.z);
+    tc::split_pack2(v.z, v.w, hi.w, lo.w);
+}
+
+template <bool NN>
+__global__ void __launch_bounds__(kTcGemmThreads) gemm_tc_kernel(GemmArgs g) {
+    extern __shared__ __align__(128) uint8_t gsm[];
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(gsm + kTcStages * kTcStageBytes);     // [stages] panels written (256 arrivals)
+    uint64_t* bar_empty = bar_full + kTcStages;                                            // [stages] panels consumed (tcgen05.commit)
+    uint64_t* bar_acc = bar_empty + kTcStages;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acc + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int z = blockIdx.z, z1 = z / g.nh, z2 = z % g.nh;
+    const float* A = g.A + z1 * g.sa1 + z2 * g.sa2;
+    const float* B = g.B + z1 * g.sb1 + z2 * g.sb2;
+    float* C = g.C + z1 * g.sc1 + z2 * g.sc2;
+    const float* R = g.R ? g.R + z1 * g.sr1 + z2 * g.sr2 : nullptr;
+    const int m0 = blockIdx.y * kTcBM, n0 = blockIdx.x * kTcBN;
+    const int ksteps = (g.K + kTcBK - 1) / kTcBK;
+
+    if (warp == 8) tc::tmem_alloc(s_tmem, 128);
+    if (tid == 0) {
+        for (int i = 0; i < kTcStages; ++i) { tc::mbar_init(bar_full + i, 256); tc::mbar_init(bar_empty + i, 1); }
+        tc::mbar_init(bar_acc, 1);
+        tc::mbar_fence_init();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tbase = __shfl_sync(0xffffffffu, *s_tmem, 0);
+
+    if (warp < 8) {
+        // ---- producers: thread = one row of the A panel (warps 0-3) or of the B panel (warps 4-7) ----
+        const int op = warp >> 2, rloc = tid & 127;
+        const int row = (op == 0 ? m0 : n0) + rloc;
+        const float* src0 = (op == 0 ? A + (size_t)row * g.lda : B + (size_t)row * g.ldb);
+        const bool valid = row < (op == 0 ? g.M : g.N);
+#pragma unroll 1
+        for (int ks = 0; ks < ksteps; ++ks) {
+            const int st = ks % kTcStages;
+            const int k0 = ks * kTcBK;
+            float4 v[8];
+            if (NN && op == 1) {
+                // B[k][n]: a warp reads 32 consecutive n of one k row per load (coalesced); the thread still owns operand row n
+                const float* bp = B + (size_t)k0 * g.ldb + row;
+                float* vf = reinterpret_cast<float*>(v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) vf[j] = (valid && k0 + j < g.K) ? __ldg(bp + (size_t)j * g.ldb) : 0.f;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    v[j] = (valid && k0 + 4 * j < g.K) ? __ldg(reinterpret_cast<const float4*>(src0 + k0 + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (ks >= kTcStages) tc::mbar_wait(bar_empty + st, ((ks / kTcStages) - 1) & 1);
+            uint8_t* sp = gsm + st * kTcStageBytes + (2 * op) * kTcPanel + rloc * 16;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint4 hi, lo;
+                gen_split8(v[2 * c], v[2 * c + 1], hi, lo);
+                *reinterpret_cast<uint4*>(sp + c * (kTcBM * 16)) = hi;
+                *reinterpret_cast<uint4*>(sp + kTcPanel + c * (kTcBM * 16)) = lo;
+            }
+            tc::fence_async_smem();
+            tc::mbar_arrive(bar_full + st);
+        }
+        // ---- epilogue: thread = output row (TMEM lane 32 (warp % 4) + lane), warps 0-3 columns 0-63, warps 4-7 columns 64-127 ----
+        tc::mbar_wait(bar_acc, 0);
+        tc::tc_fence_after();
+        const int m = m0 + 32 * (warp & 3) + (tid & 31);
+        const uint32_t ta = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
+#pragma unroll 1
+        for (int c0 = 64 * op; c0 < 64 * op + 64; c0 += 16) {
+            if (n0 + c0 >= g.N) break;
+            uint32_t r[16];
+            tc::tmem_ld16(ta + c0, r);
+            tc::tc_wait_ld();
+            if (m >= g.M) continue;
+            float* cp = C + (size_t)m * g.ldc + n0 + c0;
+            const float* rp = R ? R + (size_t)(g.rmod > 0 ? m % g.rmod : m) * g.ldr + n0 + c0 : nullptr;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (n0 + c0 + j >= g.N) break;
+                float v = __uint_as_float(r[j]) * g.alpha;
+                if (g.bias) v += __ldg(g.bias + n0 + c0 + j);
+                if (g.act == ACT_RELU) v = fmaxf(v, 0.f);
+                else if (g.act == ACT_HSWISH) v = v * fminf(fmaxf(v + 3.f, 0.f), 6.f) / 6.f;
+                else if (g.act == ACT_GELU) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+                if (rp) v += rp[j];
+                cp[j] = v;
+            }
+        }
+    } else {
+        // ---- MMA issue: the warp runs convergently, one elected lane issues ----
+        const uint32_t sbase = tc::smem_u32(gsm);
+        const uint32_t idesc = tc::instr_desc_f16(128, kTcBN, false);
+#pragma unroll 1
+        for (int ks = 0; ks < ksteps; ++ks) {
+            const int st = ks % kTcStages;
+            tc::mbar_wait(bar_full + st, (ks / kTcStages) & 1);
+            tc::tc_fence_after();
+            const uint32_t pa = sbase + st * kTcStageBytes;
+#pragma unroll
+            for (int kk = 0; kk < kTcBK / 16; ++kk) {
+                const uint32_t off = kk * 2 * (kTcBM * 16);
+                const uint64_t ah = tc::smem_desc(pa + off, kTcBM * 16, 128), al = tc::smem_desc(pa + kTcPanel + off, kTcBM * 16, 128);
+                const uint64_t bh = tc::smem_desc(pa + 2 * kTcPanel + off, kTcBN * 16, 128), bl = tc::smem_desc(pa + 3 * kTcPanel + off, kTcBN * 16, 128);
+                tc::mma_ss_elect(tbase, ah, bh, idesc, (ks | kk) != 0 ? 1u : 0u);
+                tc::mma_ss_elect(tbase, al, bh, idesc, 1u);
+                tc::mma_ss_elect(tbase, ah, bl, idesc, 1u);
+            }
+            tc::mma_commit_elect(bar_empty + st);
+        }
+        tc::mma_commit_elect(bar_acc);
+        __syncwarp();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tc::tmem_dealloc(tbase, 128);
+}
+
+bool gemm_tc_ok(const GemmArgs& g, bool nn) {
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (!(g.K % 8 == 0 && g.K >= 64 && g.N >= 64 && g.M >= 128 && g.lda % 4 == 0 && al16(g.A) && g.sa1 % 4 == 0 && g.sa2 % 4 == 0)) return false;
+    return nn || (g.ldb % 4 == 0 && al16(g.B) && g.sb1 % 4 == 0 && g.sb2 % 4 == 0);     // B[k][n] is read with scalar loads
+}
+
+template <bool NN>
+int launch_gemm_tc(const GemmArgs& g, int batch, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(gemm_tc_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcGemmSmem) != cudaSuccess) return -1;
+        configured = true;
+    }
+    dim3 grid((g.N + kTcBN - 1) / kTcBN, (g.M + kTcBM - 1) / kTcBM, batch);
+    gemm_tc_kernel<NN><<<grid, kTcGemmThreads, kTcGemmSmem, st>>>(g);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
 int run_gemm(const GemmArgs& g, int batch, bool nn, cudaStream_t st) {
     if (g.M <= 0 || g.N <= 0 || batch <= 0) return 0;
+    if (gemm_tc_ok(g, nn)) return nn ? launch_gemm_tc<true>(g, batch, st) : launch_gemm_tc<false>(g, batch, st);
     dim3 grid((g.N + kBN - 1) / kBN, (g.M + kBM - 1) / kBM, batch);
     if (nn) sgemm_kernel<true><<<grid, 256, 0, st>>>(g);
     else sgemm_kernel<false><<<grid, 256, 0, st>>>(g);
