@@ -15,7 +15,8 @@ from concurrent.futures import ThreadPoolExecutor
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
-LIB_DIR = os.path.join(PKG_DIR, "lib")
+# VT_LIB_DIR: development builds (cycle traces, experiments) go to a side directory and are loaded from there
+LIB_DIR = os.path.abspath(os.environ["VT_LIB_DIR"]) if os.environ.get("VT_LIB_DIR") else os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libvittrack_b200.so")
 STAMP = os.path.join(LIB_DIR, "build.stamp")
 

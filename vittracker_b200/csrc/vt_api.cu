@@ -888,4 +888,16 @@ int vt_profile_read(VtHandle h, double* stage_ms, int64_t* stage_launches, int64
     return VT_OK;
 }
 
+// Development aid (not part of the documented ABI): which profiled stage launches have started / finished.  Non-blocking, meant to be
+// called from a watchdog thread while the owning thread is stuck in a synchronisation.  out[i] = stage * 4 + (started ? 1 : 0) + (finished ? 2 : 0).
+int vt_debug_pending(VtHandle h, int32_t* out, int32_t cap) {
+    if (!h || !out) return -1;
+    int k = 0;
+    for (auto& r : h->prof) {
+        if (k >= cap) break;
+        out[k++] = r.stage * 4 + (cudaEventQuery(r.a) == cudaSuccess ? 1 : 0) + (cudaEventQuery(r.b) == cudaSuccess ? 2 : 0);
+    }
+    return k;
+}
+
 }  // extern "C"

@@ -328,11 +328,14 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                         if (t < 2) scores_half(t + 1, 1);
                         mma_commit_elect(mb_done);
                     }
+                    // ---- MLP, pipelined over row tiles (tile 0 -> H_A/Y_A, tile 1 -> H_B/Y_B, tile 2 -> H_A/Y_A) ----
+                    // fc1 of tile 0 goes out at once: its operand (LayerNorm 2 of tile 0) was complete before softmax(2) began, and its
+                    // output H_A overwrites P(2)'s columns behind P V'(2) in the tensor pipe's issue order - so the first GELU starts
+                    // as soon as the epilogue warps are through with tile 2's attention output instead of one MMA round trip later
+                    mbar_wait(mb_w1, w1_ph); w1_ph ^= 1;                         // W1 was prefetched during attention
+                    fc1(0, kColHA); mma_commit_elect(mb_h);
                     wait_go(); load_w2(blk);                                     // 7: attention output + LN2 of every tile done; K/V' dead
                     if (!(last_track && blk == kDepth - 1)) load_wa((blk + 1) % kDepth);
-                    mbar_wait(mb_w1, w1_ph); w1_ph ^= 1;                         // W1 was prefetched during attention
-                    // ---- MLP, pipelined over row tiles (tile 0 -> H_A/Y_A, tile 1 -> H_B/Y_B, tile 2 -> H_A/Y_A) ----
-                    fc1(0, kColHA); mma_commit_elect(mb_h);
                     wait_on(mb_h, h_ph[0]);                                      // H_B aliases operand slot 0: fc1(0) must be done
                     fc1(1, kColHB); mma_commit_elect(mb_h + 1);
                     wait_on(mb_g, g_ph[0]);                                      // GELU(0) operand in H_A

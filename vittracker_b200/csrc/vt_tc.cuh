@@ -191,12 +191,20 @@ __device__ __forceinline__ void bulk_g2s_elect(void* dst_smem, const void* src_g
 
 // ---- fp32 -> fp16 hi/lo split ------------------------------------------------------------------------
 // v ~= hi + lo with hi = fp16(v), lo = fp16(v - hi): ~22 significant bits for |v| well inside fp16 range.
+// Two instructions per element: one packed conversion gives both hi halves, one mixed-precision FMA per element (sm_100
+// fma.rn.f32.f16: an fp16 product accumulated onto an fp32 addend, exact here) gives v - hi without unpacking, one packed conversion
+// gives both lo halves.
 __device__ __forceinline__ void split_pack2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-    const __half2 h = __floats2half2_rn(v0, v1);
-    const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-    hi = *reinterpret_cast<const uint32_t*>(&h);
-    lo = *reinterpret_cast<const uint32_t*>(&l);
+    float l0, l1;
+    asm("{\n\t.reg .b16 h0, h1, m;\n\t"
+        "cvt.rn.f16x2.f32 %0, %4, %3;\n\t"
+        "mov.b32 {h0, h1}, %0;\n\t"
+        "mov.b16 m, 0xBC00;\n\t"                       // -1.0
+        "fma.rn.f32.f16 %1, h0, m, %3;\n\t"
+        "fma.rn.f32.f16 %2, h1, m, %4;\n\t}"
+        : "=&r"(hi), "=f"(l0), "=f"(l1)
+        : "f"(v0), "f"(v1));
+    asm("cvt.rn.f16x2.f32 %0, %2, %1;" : "=r"(lo) : "f"(l0), "f"(l1));
 }
 
 }  // namespace tc
