@@ -592,28 +592,34 @@ int vt_finalize_weights(VtHandle h, void* stream) {
         };
         uint8_t* base8 = reinterpret_cast<uint8_t*>(&pk.buf[o_htc]);
         const float* w1 = &pk.buf[hw[0]];                       // folded, [ci][ky*3+kx][96]
+        // conv1: piece p = (h * 3 + ky) * 3 + ks holds one K step (input channels 16 ks .. 16 ks + 15) of vertical tap ky for ALL three
+        // horizontal taps: B[n = kx * 48 + (co - 48 h)][k = ci], [hi | lo] x [chunk 2][n 144][8] - one N = 144 MMA feeds the three
+        // per-kx accumulators (adjacent TMEM columns) from a single read of the A operand
         for (int h2 = 0; h2 < 2; ++h2)
-            for (int kx = 0; kx < 3; ++kx)
-                for (int ky = 0; ky < 3; ++ky) {                // piece p = (h * 3 + kx) * 3 + ky: B[n = co - 48 h][k = ci]
-                    uint8_t* hi8 = base8 + (size_t)((h2 * 3 + kx) * 3 + ky) * kHeadTcPieceBytes;
+            for (int ky = 0; ky < 3; ++ky)
+                for (int ks = 0; ks < 3; ++ks) {
+                    uint8_t* hi8 = base8 + (size_t)((h2 * 3 + ky) * 3 + ks) * kHeadTcPieceBytes;
                     uint8_t* lo8 = hi8 + kHeadTcPieceBytes / 2;
-                    for (int n = 0; n < 48; ++n)
-                        for (int ci = 0; ci < 48; ++ci)
-                            put(hi8, lo8, ((size_t)(ci / 8) * 48 + n) * 16 + (ci % 8) * 2, w1[((size_t)ci * 9 + ky * 3 + kx) * 96 + h2 * 48 + n]);
+                    for (int kx = 0; kx < 3; ++kx)
+                        for (int n = 0; n < 48; ++n)
+                            for (int e = 0; e < 16; ++e) {
+                                const int ci = 16 * ks + e;
+                                put(hi8, lo8, ((size_t)(e / 8) * 144 + kx * 48 + n) * 16 + (e % 8) * 2, w1[((size_t)ci * 9 + ky * 3 + kx) * 96 + h2 * 48 + n]);
+                            }
                 }
         uint8_t* base2 = reinterpret_cast<uint8_t*>(&pk.buf[o_htc2]);
         const float* w2 = &pk.buf[hw[1]];                       // folded, [ci][ky*3+kx][tower][16]
-        for (int t = 0; t < 3; ++t)
-            for (int kx = 0; kx < 3; ++kx) {                    // blob (tower, kx): B[n = co][k = ky * 32 + ci]
-                uint8_t* hi8 = base2 + (size_t)(t * 3 + kx) * 6144;
-                uint8_t* lo8 = hi8 + 3072;
+        for (int t = 0; t < 3; ++t) {                           // blob (tower): B[n = kx * 16 + co][k = ky * 32 + ci], [hi | lo] x [k/8 12][n 48][8]
+            uint8_t* hi8 = base2 + (size_t)t * 18432;
+            uint8_t* lo8 = hi8 + 9216;
+            for (int kx = 0; kx < 3; ++kx)
                 for (int n = 0; n < 16; ++n)
                     for (int ky = 0; ky < 3; ++ky)
                         for (int ci = 0; ci < 32; ++ci) {
                             const int k = ky * 32 + ci;
-                            put(hi8, lo8, ((size_t)(k / 8) * 16 + n) * 16 + (k % 8) * 2, w2[(((size_t)ci * 9 + ky * 3 + kx) * 3 + t) * 16 + n]);
+                            put(hi8, lo8, ((size_t)(k / 8) * 48 + kx * 16 + n) * 16 + (k % 8) * 2, w2[(((size_t)ci * 9 + ky * 3 + kx) * 3 + t) * 16 + n]);
                         }
-            }
+        }
     }
     hw[4] = slot(3 * 4 * 2); hb[4] = slot(3 * 2);
     for (int t = 0; t < 3; ++t) {

@@ -50,16 +50,17 @@ static_assert(kHeadSmemBytes <= 227 * 1024, "head smem");
 //        later the zero-bordered fp32 planes of conv2 / conv3 / conv4 outputs
 constexpr int kTcAChunk = 18 * 16 * 16;                 // bytes of one 8-channel chunk image: 18 rows x 16 px x 16 B
 constexpr int kT_R0 = 0, kT_R0Bytes = 2 * 6 * kTcAChunk;                   // 55296
-constexpr int kT_Ring = kT_R0 + kT_R0Bytes, kT_PieceBytes = 2 * 6 * 48 * 16;   // piece (h, kx, ky): hi | lo, N = 48, K = 48 -> 9216
+constexpr int kT_Ring = kT_R0 + kT_R0Bytes, kT_PieceBytes = 2 * 2 * 144 * 16;  // piece (h, ky, K step): hi | lo, N = 144 (kx, co), K = 16 -> 9216
 constexpr int kT_RingSlots = 5;                          // conv1 weight pieces in flight: 4 x 432 cycles of MMA cover an L2 round trip
 constexpr int kT_R1 = kT_Ring + kT_RingSlots * kT_PieceBytes, kT_R1Half = 12 * kTcAChunk; // 55296 per precision
 constexpr int kT_Out2 = kT_R1, kT_Out3 = kT_Out2 + 48 * kPlane * 4, kT_Out4 = kT_Out3 + 24 * kPlane * 4;
 constexpr int kT_Bias = kT_R1 + 2 * kT_R1Half;
 constexpr int kT_Maps = kT_Bias + 256 * 4;
 constexpr int kT_Red = kT_Maps + 6 * 256 * 4;
-constexpr int kT_Bar = kT_Red + 32 * 4;                 // loaded[slots], consumed[slots], acc_ready, w2_loaded, tmem base
-constexpr size_t kHeadTcSmemBytes = kT_Bar + (2 * kT_RingSlots + 3) * 8;
-constexpr int kT_W2Bytes = 9 * 2 * 12 * 16 * 16;        // conv2 weights: (tower, kx) x [hi | lo] x K-major [12 chunks][16][8] = 55296
+constexpr int kT_Bar = kT_Red + 32 * 4;                 // loaded[slots], consumed[slots], acc_ready, w2_loaded, acc2_ready, tmem base
+constexpr size_t kHeadTcSmemBytes = kT_Bar + (2 * kT_RingSlots + 4) * 8;
+constexpr int kT_Issue1 = 2, kT_Issue2 = 6;             // warps issuing conv1's (one per M tile) and conv2's (one per tower x M tile) MMAs
+constexpr int kT_W2Bytes = 3 * 2 * 12 * 48 * 16;        // conv2 weights: (tower) x [hi | lo] x K-major [12 chunks][n = kx*16 + co][8] = 55296
 static_assert(kT_W2Bytes <= kT_R0Bytes && kT_Out4 + 12 * kPlane * 4 <= kT_Bias && kT_RingSlots * kT_PieceBytes >= 2 * kWChunk * 4, "head tc smem plan");
 static_assert(kHeadTcSmemBytes <= 227 * 1024 && kT_Bar % 8 == 0 && kT_R1 % 128 == 0, "head smem (tc)");
 
@@ -275,7 +276,8 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
     uint64_t* bar_consumed = bar_loaded + kT_RingSlots;                    // [kT_RingSlots]
     uint64_t* bar_acc = bar_loaded + 2 * kT_RingSlots;
     uint64_t* bar_w2 = bar_acc + 1;
-    uint32_t* tc_tmem = reinterpret_cast<uint32_t*>(bar_acc + 2);
+    uint64_t* bar_acc2 = bar_acc + 2;
+    uint32_t* tc_tmem = reinterpret_cast<uint32_t*>(bar_acc + 3);
     const int trk = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int py = tid >> 4, px = tid & 15;
@@ -295,7 +297,10 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
     if (tid < 6) sb[204 + tid] = w.head.b5[tid];
     if (warp == 0) tc::tmem_alloc(tc_tmem, 512);
     if (tid == 32) {
-        for (int i = 0; i < 2 * kT_RingSlots + 2; ++i) tc::mbar_init(bar_loaded + i, 1);
+        for (int i = 0; i < kT_RingSlots; ++i) { tc::mbar_init(bar_loaded + i, 1); tc::mbar_init(bar_consumed + i, kT_Issue1); }
+        tc::mbar_init(bar_acc, kT_Issue1);
+        tc::mbar_init(bar_w2, 1);
+        tc::mbar_init(bar_acc2, kT_Issue2);
         tc::mbar_fence_init();
     }
     __syncthreads();
@@ -331,41 +336,40 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
     const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
     const int tile = warp >> 2;                                            // epilogue: pixel = tid, M tile = warp / 4
 
-    // ---- conv1: 18 weight pieces p = (h * 3 + kx) * 3 + ky through a 3-deep ring; D(tile, kx) = columns (tile * 3 + kx) * 48 ----
+    // ---- conv1: 18 weight pieces p = (h * 3 + ky) * 3 + ks through the ring; D(tile, kx) = columns (tile * 3 + kx) * 48 ----
     {
-        const uint32_t id48 = tc::instr_desc_f16(128, 48, false);
+        const uint32_t id144 = tc::instr_desc_f16(128, 144, false);
         auto load_piece = [&](int p) {
             tc::bulk_g2s_elect(sm8 + kT_Ring + (p % kT_RingSlots) * kT_PieceBytes, w.head_tc_w1 + (size_t)p * kT_PieceBytes, kT_PieceBytes,
                                bar_loaded + p % kT_RingSlots);
         };
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
-            if (warp == 0) {                     // convergent: every lane runs the program, one elected lane issues
+            // A single warp issues a 48-column tcgen05.mma every ~35 cycles (descriptor transfers to uniform registers), the tensor
+            // pipe needs 24: one issuing warp per M tile (on different schedulers) keeps the pipe fed.  Warp 0 also streams the pieces.
+            if (warp < kT_Issue1) {              // convergent: every lane runs the program, one elected lane issues
+                const int tl = warp;
 #pragma unroll 1
                 for (int q = 0; q < 9; ++q) {
-                    const int p = 9 * h + q, kx = q / 3, ky = q % 3;
-                    if (p + kT_RingSlots - 1 < 18) {
+                    const int p = 9 * h + q, ky = q / 3, ks = q % 3;
+                    if (warp == 0 && p + kT_RingSlots - 1 < 18) {
                         if (p >= 1) tc::mbar_wait(bar_consumed + (p - 1) % kT_RingSlots, ((p - 1) / kT_RingSlots) & 1);    // ring slot of piece p-1 is free
                         load_piece(p + kT_RingSlots - 1);
                     }
                     tc::mbar_wait(bar_loaded + p % kT_RingSlots, (p / kT_RingSlots) & 1);
                     tc::tc_fence_after();
+                    // one N = 144 MMA per product: the piece holds all three horizontal taps, the three per-kx accumulators are adjacent
+                    // TMEM columns - the A operand (4 KB of shared-memory reads per MMA, the bound of these small-N MMAs) is read once
                     const uint32_t wb = sbase + kT_Ring + (p % kT_RingSlots) * kT_PieceBytes;
-#pragma unroll
-                    for (int tl = 0; tl < 2; ++tl) {
-                        const uint32_t d = tbase + (tl * 3 + kx) * 48;
-#pragma unroll
-                        for (int ks = 0; ks < 3; ++ks) {
-                            const uint32_t aoff = kT_R0 + (2 * ks) * kTcAChunk + (8 * tl + ky) * 256;
-                            const uint64_t ah = tc::smem_desc(sbase + aoff, kTcAChunk, 128);
-                            const uint64_t al = tc::smem_desc(sbase + aoff + 6 * kTcAChunk, kTcAChunk, 128);
-                            const uint64_t bh = tc::smem_desc(wb + (2 * ks) * 768, 768, 128);
-                            const uint64_t bl = tc::smem_desc(wb + kT_PieceBytes / 2 + (2 * ks) * 768, 768, 128);
-                            tc::mma_ss_elect(d, ah, bh, id48, (ky | ks) != 0);
-                            tc::mma_ss_elect(d, al, bh, id48, 1);
-                            tc::mma_ss_elect(d, ah, bl, id48, 1);
-                        }
-                    }
+                    const uint32_t d = tbase + tl * 144;
+                    const uint32_t aoff = kT_R0 + (2 * ks) * kTcAChunk + (8 * tl + ky) * 256;
+                    const uint64_t ah = tc::smem_desc(sbase + aoff, kTcAChunk, 128);
+                    const uint64_t al = tc::smem_desc(sbase + aoff + 6 * kTcAChunk, kTcAChunk, 128);
+                    const uint64_t bh = tc::smem_desc(wb, 144 * 16, 128);
+                    const uint64_t bl = tc::smem_desc(wb + kT_PieceBytes / 2, 144 * 16, 128);
+                    tc::mma_ss_elect(d, ah, bh, id144, q != 0);
+                    tc::mma_ss_elect(d, al, bh, id144, 1);
+                    tc::mma_ss_elect(d, ah, bl, id144, 1);
                     tc::mma_commit_elect(bar_consumed + p % kT_RingSlots);
                 }
                 tc::mma_commit_elect(bar_acc);
@@ -414,35 +418,29 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
     HEAD_TRACE(2);
 
     // ---- conv2 (per tower 32 -> 16): D(tower, tile, kx) = columns ((tower * 2 + tile) * 3 + kx) * 16 ----------------------
-    if (warp == 0) {
-        const uint32_t id16 = tc::instr_desc_f16(128, 16, false);
+    if (warp < kT_Issue2) {                      // one issuing warp per (tower, M tile); N = 48 = the three horizontal taps side by side
+        const uint32_t id48 = tc::instr_desc_f16(128, 48, false);
+        const int tw = warp >> 1, tl = warp & 1;
         tc::mbar_wait(bar_w2, 0);
         tc::tc_fence_after();
-#pragma unroll 1
-        for (int tw = 0; tw < 3; ++tw)
+        const uint32_t d = tbase + (tw * 2 + tl) * 48;
+        const uint32_t wb = sbase + kT_R0 + tw * 18432;
 #pragma unroll
-            for (int tl = 0; tl < 2; ++tl)
+        for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const uint32_t d = tbase + ((tw * 2 + tl) * 3 + kx) * 16;
-                    const uint32_t wb = sbase + kT_R0 + (tw * 3 + kx) * 6144;
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                        for (int kp = 0; kp < 2; ++kp) {
-                            const uint32_t aoff = kT_R1 + (4 * tw + 2 * kp) * kTcAChunk + (8 * tl + ky) * 256;
-                            const uint64_t ah = tc::smem_desc(sbase + aoff, kTcAChunk, 128);
-                            const uint64_t al = tc::smem_desc(sbase + aoff + kT_R1Half, kTcAChunk, 128);
-                            const uint64_t bh = tc::smem_desc(wb + (ky * 4 + 2 * kp) * 256, 256, 128);
-                            const uint64_t bl = tc::smem_desc(wb + 3072 + (ky * 4 + 2 * kp) * 256, 256, 128);
-                            tc::mma_ss_elect(d, ah, bh, id16, (ky | kp) != 0);
-                            tc::mma_ss_elect(d, al, bh, id16, 1);
-                            tc::mma_ss_elect(d, ah, bl, id16, 1);
-                        }
-                }
-        tc::mma_commit_elect(bar_acc);
+            for (int kp = 0; kp < 2; ++kp) {
+                const uint32_t aoff = kT_R1 + (4 * tw + 2 * kp) * kTcAChunk + (8 * tl + ky) * 256;
+                const uint64_t ah = tc::smem_desc(sbase + aoff, kTcAChunk, 128);
+                const uint64_t al = tc::smem_desc(sbase + aoff + kT_R1Half, kTcAChunk, 128);
+                const uint64_t bh = tc::smem_desc(wb + (ky * 4 + 2 * kp) * 768, 768, 128);
+                const uint64_t bl = tc::smem_desc(wb + 9216 + (ky * 4 + 2 * kp) * 768, 768, 128);
+                tc::mma_ss_elect(d, ah, bh, id48, (ky | kp) != 0);
+                tc::mma_ss_elect(d, al, bh, id48, 1);
+                tc::mma_ss_elect(d, ah, bl, id48, 1);
+            }
+        tc::mma_commit_elect(bar_acc2);
     }
-    tc::mbar_wait(bar_acc, 0);
+    tc::mbar_wait(bar_acc2, 0);
     tc::tc_fence_after();
     // conv2's operand is dead: its place becomes the zero-bordered fp32 planes of the remaining (CUDA-core) layers
     for (int i = tid * 4; i < (48 + 24 + 12) * kPlane; i += kHeadThreads * 4)
