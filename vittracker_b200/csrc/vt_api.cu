@@ -582,7 +582,7 @@ int vt_finalize_weights(VtHandle h, void* stream) {
         }
     }
     // head conv1 / conv2 for the tensor cores (fp16 hi | lo, K-major [k/8][n][8]); see vt_head.cu
-    const size_t o_htc = slot(18 * kHeadTcPieceBytes / 4), o_htc2 = slot(kHeadTcW2Bytes / 4);
+    const size_t o_htc = slot(18 * kHeadTcPieceBytes / 4), o_htc2 = slot(kHeadTcW2Bytes / 4), o_htc3 = slot(kHeadTcW3Bytes / 4);
     {
         auto put = [&](uint8_t* hi8, uint8_t* lo8, size_t off, float v) {
             const __half hi = __float2half_rn(v);
@@ -618,6 +618,28 @@ int vt_finalize_weights(VtHandle h, void* stream) {
                         for (int ci = 0; ci < 32; ++ci) {
                             const int k = ky * 32 + ci;
                             put(hi8, lo8, ((size_t)(k / 8) * 48 + kx * 16 + n) * 16 + (k % 8) * 2, w2[(((size_t)ci * 9 + ky * 3 + kx) * 3 + t) * 16 + n]);
+                        }
+        }
+    }
+    {
+        auto put = [&](uint8_t* hi8, uint8_t* lo8, size_t off, float v) {
+            const __half hi = __float2half_rn(v);
+            const __half lo = __float2half_rn(v - __half2float(hi));
+            memcpy(hi8 + off, &hi, 2);
+            memcpy(lo8 + off, &lo, 2);
+        };
+        uint8_t* base3 = reinterpret_cast<uint8_t*>(&pk.buf[o_htc3]);
+        memset(base3, 0, kHeadTcW3Bytes);                       // output columns 24..31 are padding
+        const float* w3 = &pk.buf[hw[2]];                       // folded, [ci][ky*3+kx][tower][8]
+        for (int t = 0; t < 3; ++t) {                           // blob (tower): B[n = kx * 8 + co][k = ky * 16 + ci], [hi | lo] x [k/8 6][n 32][8]
+            uint8_t* hi8 = base3 + (size_t)t * 6144;
+            uint8_t* lo8 = hi8 + 3072;
+            for (int kx = 0; kx < 3; ++kx)
+                for (int n = 0; n < 8; ++n)
+                    for (int ky = 0; ky < 3; ++ky)
+                        for (int ci = 0; ci < 16; ++ci) {
+                            const int k = ky * 16 + ci;
+                            put(hi8, lo8, ((size_t)(k / 8) * 32 + kx * 8 + n) * 16 + (k % 8) * 2, w3[(((size_t)ci * 9 + ky * 3 + kx) * 3 + t) * 8 + n]);
                         }
         }
     }
@@ -665,6 +687,7 @@ int vt_finalize_weights(VtHandle h, void* stream) {
     m.head.w5 = base + hw[4]; m.head.b5 = base + hb[4];
     m.head_tc_w1 = reinterpret_cast<const uint8_t*>(base + o_htc);
     m.head_tc_w2 = reinterpret_cast<const uint8_t*>(base + o_htc2);
+    m.head_tc_w3 = reinterpret_cast<const uint8_t*>(base + o_htc3);
     for (int i = 0; i < 3; ++i) { m.stem_tc_w[i] = reinterpret_cast<const uint8_t*>(base + stc_w[i]); m.stem_tc_b[i] = base + stc_b[i]; }
     m.hann = base + o_hann; m.lut = base + o_lut;
     h->finalized = true;

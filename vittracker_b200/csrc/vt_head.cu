@@ -53,15 +53,16 @@ constexpr int kT_R0 = 0, kT_R0Bytes = 2 * 6 * kTcAChunk;                   // 55
 constexpr int kT_Ring = kT_R0 + kT_R0Bytes, kT_PieceBytes = 2 * 2 * 144 * 16;  // piece (h, ky, K step): hi | lo, N = 144 (kx, co), K = 16 -> 9216
 constexpr int kT_RingSlots = 5;                          // conv1 weight pieces in flight: 4 x 432 cycles of MMA cover an L2 round trip
 constexpr int kT_R1 = kT_Ring + kT_RingSlots * kT_PieceBytes, kT_R1Half = 12 * kTcAChunk; // 55296 per precision
-constexpr int kT_Out2 = kT_R1, kT_Out3 = kT_Out2 + 48 * kPlane * 4, kT_Out4 = kT_Out3 + 24 * kPlane * 4;
+constexpr int kT_W3 = kT_Ring + 2 * kWChunk * 4;        // conv3's weights: the ring's tail (the CUDA-core layer's cp.async ring keeps the head of it)
+constexpr int kT_Out3 = kT_R0, kT_Out4 = kT_Out3 + 24 * kPlane * 4;     // zero-bordered fp32 planes of conv3 / conv4 outputs (conv2's weights are dead by then)
 constexpr int kT_Bias = kT_R1 + 2 * kT_R1Half;
 constexpr int kT_Maps = kT_Bias + 256 * 4;
 constexpr int kT_Red = kT_Maps + 6 * 256 * 4;
 constexpr int kT_Bar = kT_Red + 32 * 4;                 // loaded[slots], consumed[slots], acc_ready, w2_loaded, acc2_ready, tmem base
-constexpr size_t kHeadTcSmemBytes = kT_Bar + (2 * kT_RingSlots + 4) * 8;
+constexpr size_t kHeadTcSmemBytes = kT_Bar + (2 * kT_RingSlots + 6) * 8;
 constexpr int kT_Issue1 = 2, kT_Issue2 = 6;             // warps issuing conv1's (one per M tile) and conv2's (one per tower x M tile) MMAs
 constexpr int kT_W2Bytes = 3 * 2 * 12 * 48 * 16;        // conv2 weights: (tower) x [hi | lo] x K-major [12 chunks][n = kx*16 + co][8] = 55296
-static_assert(kT_W2Bytes <= kT_R0Bytes && kT_Out4 + 12 * kPlane * 4 <= kT_Bias && kT_RingSlots * kT_PieceBytes >= 2 * kWChunk * 4, "head tc smem plan");
+static_assert(kT_W2Bytes <= kT_R0Bytes && kT_Out4 + 12 * kPlane * 4 <= kT_R0 + kT_R0Bytes && kT_W3 + kHeadTcW3Bytes <= kT_R1 && kT_W3 % 128 == 0, "head tc smem plan");
 static_assert(kHeadTcSmemBytes <= 227 * 1024 && kT_Bar % 8 == 0 && kT_R1 % 128 == 0, "head smem (tc)");
 
 __device__ __forceinline__ void cp_async16(float* dst_smem, const float* src_gmem) {
@@ -277,7 +278,9 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
     uint64_t* bar_acc = bar_loaded + 2 * kT_RingSlots;
     uint64_t* bar_w2 = bar_acc + 1;
     uint64_t* bar_acc2 = bar_acc + 2;
-    uint32_t* tc_tmem = reinterpret_cast<uint32_t*>(bar_acc + 3);
+    uint64_t* bar_w3 = bar_acc + 3;
+    uint64_t* bar_acc3 = bar_acc + 4;
+    uint32_t* tc_tmem = reinterpret_cast<uint32_t*>(bar_acc + 5);
     const int trk = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int py = tid >> 4, px = tid & 15;
@@ -301,6 +304,8 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
         tc::mbar_init(bar_acc, kT_Issue1);
         tc::mbar_init(bar_w2, 1);
         tc::mbar_init(bar_acc2, kT_Issue2);
+        tc::mbar_init(bar_w3, 1);
+        tc::mbar_init(bar_acc3, kT_Issue2);
         tc::mbar_fence_init();
     }
     __syncthreads();
@@ -376,8 +381,10 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
             }
             tc::mbar_wait(bar_acc, h);
             tc::tc_fence_after();
-            if (h == 1 && warp == 0)             // conv1's operand is dead: conv2's weights stream into its place
+            if (h == 1 && warp == 0) {           // conv1's operand and weight ring are dead: conv2's and conv3's weights stream into their place
                 tc::bulk_g2s_elect(sm8 + kT_R0, w.head_tc_w2, kT_W2Bytes, bar_w2);
+                tc::bulk_g2s_elect(sm8 + kT_W3, w.head_tc_w3, kHeadTcW3Bytes, bar_w3);
+            }
             // epilogue: combine the three horizontal taps, bias, ReLU -> conv2's operand image (channels 48 h ..)
             {
                 const uint32_t ta = tbase + lane_addr + tile * 144;
@@ -442,15 +449,15 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
     }
     tc::mbar_wait(bar_acc2, 0);
     tc::tc_fence_after();
-    // conv2's operand is dead: its place becomes the zero-bordered fp32 planes of the remaining (CUDA-core) layers
-    for (int i = tid * 4; i < (48 + 24 + 12) * kPlane; i += kHeadThreads * 4)
-        *reinterpret_cast<float4*>(sm8 + kT_Out2 + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    float* out2 = reinterpret_cast<float*>(sm8 + kT_Out2);
+    // conv2's weights are dead: their place becomes the zero-bordered fp32 planes of conv3's / conv4's outputs
+    for (int i = tid * 4; i < (24 + 12) * kPlane; i += kHeadThreads * 4)
+        *reinterpret_cast<float4*>(sm8 + kT_Out3 + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     float* out3 = reinterpret_cast<float*>(sm8 + kT_Out3);
     float* out4 = reinterpret_cast<float*>(sm8 + kT_Out4);
+    // conv2's epilogue -> conv3's operand image: tower tw's 16 channels = chunk images 2 tw, 2 tw + 1 of R1 (hi | lo), whose zero rows
+    // 0 and 17 were never written
     {
-        float* op = out2 + (py + 1) * 18 + px + 1;
+        uint8_t* ob = sm8 + kT_R1 + ((py + 1) * 16 + px) * 16;
 #pragma unroll 1
         for (int tw = 0; tw < 3; ++tw) {
             const uint32_t ta = tbase + lane_addr + ((tw * 2 + tile) * 3) * 16;
@@ -459,20 +466,76 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
             tc::tmem_ld16(ta + 16, r1);
             tc::tmem_ld16(ta + 32, r2);
             tc::tc_wait_ld();
+            float v[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 float t0 = __shfl_up_sync(0xffffffffu, __uint_as_float(r0[j]), 1);
                 float t2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[j]), 1);
                 if (px == 0) t0 = 0.f;
                 if (px == 15) t2 = 0.f;
-                op[(tw * 16 + j) * kPlane] = fmaxf((t0 + __uint_as_float(r1[j])) + t2 + sb[96 + tw * 16 + j], 0.f);
+                v[j] = fmaxf((t0 + __uint_as_float(r1[j])) + t2 + sb[96 + tw * 16 + j], 0.f);
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) tc::split_pack2(v[8 * c + 2 * j], v[8 * c + 2 * j + 1], hi[j], lo[j]);
+                *reinterpret_cast<uint4*>(ob + (2 * tw + c) * kTcAChunk) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(ob + kT_R1Half + (2 * tw + c) * kTcAChunk) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    HEAD_TRACE(3);
+
+    // ---- conv3 (per tower 16 -> 8): N = 32 = three horizontal taps x 8 channels (+ 8 padding); D(tower, tile) = columns 288 + (tower * 2 + tile) * 32 ----
+    if (warp < kT_Issue2) {
+        const uint32_t id32 = tc::instr_desc_f16(128, 32, false);
+        const int tw = warp >> 1, tl = warp & 1;
+        tc::mbar_wait(bar_w3, 0);
+        tc::tc_fence_after();
+        const uint32_t d = tbase + 288 + (tw * 2 + tl) * 32;
+        const uint32_t wb = sbase + kT_W3 + tw * 6144;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const uint32_t aoff = kT_R1 + (2 * tw) * kTcAChunk + (8 * tl + ky) * 256;
+            const uint64_t ah = tc::smem_desc(sbase + aoff, kTcAChunk, 128);
+            const uint64_t al = tc::smem_desc(sbase + aoff + kT_R1Half, kTcAChunk, 128);
+            const uint64_t bh = tc::smem_desc(wb + (ky * 2) * 512, 512, 128);
+            const uint64_t bl = tc::smem_desc(wb + 3072 + (ky * 2) * 512, 512, 128);
+            tc::mma_ss_elect(d, ah, bh, id32, ky != 0);
+            tc::mma_ss_elect(d, al, bh, id32, 1);
+            tc::mma_ss_elect(d, ah, bl, id32, 1);
+        }
+        tc::mma_commit_elect(bar_acc3);
+    }
+    tc::mbar_wait(bar_acc3, 0);
+    tc::tc_fence_after();
+    {
+        float* op = out3 + (py + 1) * 18 + px + 1;
+#pragma unroll 1
+        for (int tw = 0; tw < 3; ++tw) {
+            const uint32_t ta = tbase + lane_addr + 288 + (tw * 2 + tile) * 32;
+            uint32_t r0[8], r1[8], r2[8];
+            tc::tmem_ld8(ta, r0);
+            tc::tmem_ld8(ta + 8, r1);
+            tc::tmem_ld8(ta + 16, r2);
+            tc::tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float t0 = __shfl_up_sync(0xffffffffu, __uint_as_float(r0[j]), 1);
+                float t2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[j]), 1);
+                if (px == 0) t0 = 0.f;
+                if (px == 15) t2 = 0.f;
+                op[(tw * 8 + j) * kPlane] = fmaxf((t0 + __uint_as_float(r1[j])) + t2 + sb[144 + tw * 8 + j], 0.f);
             }
         }
     }
     tc::tc_fence_before();
     __syncthreads();
-    HEAD_TRACE(3);
-    head_conv<16, 8, 3, true, 16>(out2, out3, w.head.w3, sb + 144, wbuf);          // 16 -> 8
     HEAD_TRACE(4);
     head_conv<8, 4, 3, true, 8>(out3, out4, w.head.w4, sb + 168, wbuf);            // 8 -> 4
     head_finish(a, w, trk, out4, sb, maps, red, tbase);

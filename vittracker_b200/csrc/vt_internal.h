@@ -46,6 +46,7 @@ struct HeadW {               // CENTER head, BN folded, towers ordered ctr, offs
 constexpr int kTcWaBytes = 2 * (144 * 48 * 2);                         // [Wq; Wk; Wproj Wv] hi|lo = 27648 (the output projection is folded into V)
 constexpr int kTcWbBytes = 2 * (192 * 48 * 2) + 2 * (48 * 192 * 2);     // W1 hi|lo, W2 hi|lo     = 73728
 constexpr int kHeadTcPieceBytes = 2 * (48 * 48 * 2);       // one (half, ky, K step) piece of head conv1: hi | lo, N = 144 (kx, co), K = 16 -> 9216
+constexpr int kHeadTcW3Bytes = 3 * 2 * (48 * 32 * 2);      // head conv3: 3 tower blobs of hi | lo, N = 32 (kx, co; 24 used), K = 48 -> 18432
 constexpr int kHeadTcW2Bytes = 9 * 2 * (96 * 16 * 2);      // head conv2: 3 tower blobs of hi | lo, N = 48 (kx, co), K = 96 -> 55296
 constexpr int kTcParFloats = 624;   // ln1_g 48 | ln1_b 48 | bq 48 | bk 48 | Wproj bv 48 | bproj 48 | ln2_g 48 | ln2_b 48 | bfc1 192 | bfc2 48
 struct BlockTcW {
@@ -64,6 +65,7 @@ struct ModelW {
     const uint8_t* stem_tc_w[3];   // stem conv2 / conv3 / conv4 for tcgen05 (vt_stem_tc.cu): fp16 hi | lo blobs in K-step order
     const float* stem_tc_b[3];     // biases
     const uint8_t* head_tc_w1;     // head conv1 for tcgen05: 18 pieces (half h, ky, K step) x [hi | lo] x K-major [2 chunks][n = kx*48 + co][8]
+    const uint8_t* head_tc_w3;     // head conv3 for tcgen05: 3 blobs (tower) x [hi | lo] x K-major [k/8][n = kx*8 + co, 32][8], k = ky*16 + ci
     const uint8_t* head_tc_w2;     // head conv2 for tcgen05: 3 blobs (tower) x [hi | lo] x K-major [k/8][n = kx*16 + co][8], k = ky*32 + ci
     const float* hann;             // [256] fp32 window (lib/test/utils/hann.py)
     const float* lut;              // [3][256] normalisation table ((v/255 - mean)/std)
