@@ -76,7 +76,7 @@ constexpr int kSmW1hi = kSmW1, kSmW1lo = kSmW1 + 18432;
 constexpr int kSmPar = kSmW1 + 36864;                     // fp32 parameters of all blocks
 constexpr int kSmRed = kSmPar + kDepth * kTcParFloats * 4;   // 5 arrays x kNS column groups x 128 rows fp32
 constexpr int kSmBar = kSmRed + 5 * kNS * 128 * 4;        // mbarriers
-constexpr int kSmTmem = kSmBar + 16 * 8;
+constexpr int kSmTmem = kSmBar + 20 * 8;
 static_assert(kSmTmem + 16 <= 227 * 1024, "shared memory");
 constexpr int kTcSmemBytes = kSmTmem + 16;
 static_assert(kTcWbBytes == 2 * 36864 && 36864 <= 4 * kKBytes, "W2 overlays the K/V region");
@@ -204,6 +204,11 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
     uint64_t* mb_qd = mb_go + 12;      // [2] QKV output of a tile ready in buffer 0 / 1     (tcgen05.commit)
     uint64_t* mb_pa = mb_go + 15;      // first part of P (keys 0..159) written            (one arrival per epilogue warp)
     uint64_t* mb_qf = mb_go + 14;      // QKV buffer 0 has been read (tile 0's epilogue)     (one arrival per epilogue warp)
+    // LayerNorm-1 operand of tile t written: one barrier PER TILE.  The three hand-overs follow each other without the epilogue warps
+    // ever waiting for the control warp in between, so on a shared barrier two phases can complete before a late control warp (cold
+    // weight load, preempted issue) has looked at the first - and a parity wait cannot tell "two phases ago" from "not yet" (deadlock
+    // seen under ncu's cache-flushed launches).  Every other barrier's next completion depends on its waiters having seen the last one.
+    uint64_t* mb_l1 = mb_go + 16;      // [3]                                              (one arrival per epilogue warp)
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kSmTmem);
 
     if (warp == kEpiWarps) tmem_alloc(s_tmem, 512);
@@ -216,6 +221,7 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
         mbar_init(mb_qd, 1); mbar_init(mb_qd + 1, 1);
         mbar_init(mb_qf, kEpiWarps);
         mbar_init(mb_pa, kEpiWarps);
+        for (int t = 0; t < 3; ++t) mbar_init(mb_l1 + t, kEpiWarps);
         mbar_init(mb_h, 1); mbar_init(mb_h + 1, 1);
         mbar_init(mb_y, 1); mbar_init(mb_y + 1, 1);
         mbar_init(mb_g, kEpiWarps); mbar_init(mb_g + 1, kEpiWarps);
@@ -294,7 +300,7 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                     mma_ts_elect(tbase + y_col, a, bl, id48, true);
                 }
             };
-            uint32_t h_ph[2] = {0, 0}, y_ph[2] = {0, 0}, g_ph[2] = {0, 0}, yfree_ph = 0, qf_ph = 0, pa_ph = 0;
+            uint32_t h_ph[2] = {0, 0}, y_ph[2] = {0, 0}, g_ph[2] = {0, 0}, yfree_ph = 0, qf_ph = 0, pa_ph = 0, l1_ph[3] = {0, 0, 0};
             auto wait_on = [&](uint64_t* bar, uint32_t& ph) { TC_TRACE(0); mbar_wait(bar, ph); ph ^= 1; tc_fence_after(); TC_TRACE(0); };
             bool first = true;
             for (int trk = blockIdx.x; trk < n; trk += gridDim.x) {
@@ -302,11 +308,11 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                 for (int blk = 0; blk < kDepth; ++blk) {
                     if (first) { load_wa(0); load_w1(0); first = false; }
                     // QKV per tile, overlapped with the LayerNorms / epilogues of the other tiles (two output buffers)
-                    wait_go();                                                   // 1a: LN1 operand of tile 0
+                    wait_on(mb_l1, l1_ph[0]);                                    // 1a: LN1 operand of tile 0
                     mbar_wait(mb_wa, wa_ph); wa_ph ^= 1;
                     qkv(0, kColBig); mma_commit_elect(mb_qd);
-                    wait_go(); qkv(1, kColBig + 160); mma_commit_elect(mb_qd + 1);     // 1b
-                    wait_go();                                                   // 1c: LN1 operand of tile 2
+                    wait_on(mb_l1 + 1, l1_ph[1]); qkv(1, kColBig + 160); mma_commit_elect(mb_qd + 1);     // 1b
+                    wait_on(mb_l1 + 2, l1_ph[2]);                                // 1c: LN1 operand of tile 2
                     wait_on(mb_qf, qf_ph);                                       // 2: tile 0's QKV output has been read
                     qkv(2, kColBig); mma_commit_elect(mb_qd);
                     wait_go(); scores_half(0, 0); scores_half(0, 1); mma_commit_elect(mb_done);     // 3: K, V' complete
@@ -328,14 +334,13 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                         if (t < 2) scores_half(t + 1, 1);
                         mma_commit_elect(mb_done);
                     }
-                    // ---- MLP, pipelined over row tiles (tile 0 -> H_A/Y_A, tile 1 -> H_B/Y_B, tile 2 -> H_A/Y_A) ----
-                    // fc1 of tile 0 goes out at once: its operand (LayerNorm 2 of tile 0) was complete before softmax(2) began, and its
-                    // output H_A overwrites P(2)'s columns behind P V'(2) in the tensor pipe's issue order - so the first GELU starts
-                    // as soon as the epilogue warps are through with tile 2's attention output instead of one MMA round trip later
-                    mbar_wait(mb_w1, w1_ph); w1_ph ^= 1;                         // W1 was prefetched during attention
-                    fc1(0, kColHA); mma_commit_elect(mb_h);
                     wait_go(); load_w2(blk);                                     // 7: attention output + LN2 of every tile done; K/V' dead
                     if (!(last_track && blk == kDepth - 1)) load_wa((blk + 1) % kDepth);
+                    mbar_wait(mb_w1, w1_ph); w1_ph ^= 1;                         // W1 was prefetched during attention
+                    // ---- MLP, pipelined over row tiles (tile 0 -> H_A/Y_A, tile 1 -> H_B/Y_B, tile 2 -> H_A/Y_A) ----
+                    // (issuing fc1 of tile 0 ahead of step 7, behind P V'(2), saves one MMA round trip but hangs under ncu's serialised
+                    // launches - cause not understood; the conservative order stays)
+                    fc1(0, kColHA); mma_commit_elect(mb_h);
                     wait_on(mb_h, h_ph[0]);                                      // H_B aliases operand slot 0: fc1(0) must be done
                     fc1(1, kColHB); mma_commit_elect(mb_h + 1);
                     wait_on(mb_g, g_ph[0]);                                      // GELU(0) operand in H_A
@@ -401,7 +406,7 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                     float y[kCW];
                     e.ln(x[t], par + kPLn1g, par + kPLn1b, y);
                     if (e.active(t)) e.store_opa(t, y);
-                    e.signal_go(false);         // -> 1a, 1b, 1c  (the LayerNorm barriers keep the three phases apart)
+                    e.signal(mb_l1 + t, false); // -> 1a, 1b, 1c
                 }
 
                 // ---- QKV epilogue: a column group handles kQW of the 144 output columns: part 0 -> q (scaled) into the
@@ -581,6 +586,15 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
     __syncthreads();
     if (warp == kEpiWarps) tmem_dealloc(tbase, 512);
 }
+
+#ifdef VT_TC_WATCHDOG
+extern "C" int vt_tc_watchdog_read(int* rec, int* n) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(n, tc::g_wd_n, sizeof(int));
+    cudaMemcpyFromSymbol(rec, tc::g_wd_rec, sizeof(int) * 256 * 6);
+    return 0;
+}
+#endif
 
 #ifdef VT_TC_TRACE
 extern "C" int vt_tc_trace_read(long long* host, int* n) {

@@ -32,9 +32,35 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
                  : "memory");
     return ok != 0;
 }
+#ifdef VT_TC_WATCHDOG
+// Development aid: a wait that does not return within ~2^22 polls records (block, warp, barrier address, parity, caller tag) and raises a
+// global abort flag that makes every later wait return at once, so that a deadlocked kernel terminates and the records can be read.
+__device__ int g_wd_abort;
+__device__ int g_wd_n;
+__device__ int g_wd_rec[256][6];
+__device__ int g_wd_tag[40];           // per-warp progress tags of block 0 (set by the kernels)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    unsigned n = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (*reinterpret_cast<volatile int*>(&g_wd_abort)) return;
+        if (++n == (1u << 22)) {
+            if ((threadIdx.x & 31) == 0) {
+                const int k = atomicAdd(&g_wd_n, 1);
+                if (k < 256) {
+                    g_wd_rec[k][0] = blockIdx.x; g_wd_rec[k][1] = threadIdx.x >> 5; g_wd_rec[k][2] = (int)smem_u32(bar);
+                    g_wd_rec[k][3] = (int)parity; g_wd_rec[k][4] = (int)clock(); g_wd_rec[k][5] = 0;
+                }
+                __threadfence();
+            }
+        }
+        if (n == (1u << 23)) { *reinterpret_cast<volatile int*>(&g_wd_abort) = 1; __threadfence(); return; }
+    }
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
+#endif
 
 // ---- bulk async copy global -> shared (completes on an mbarrier with complete_tx) ---------------------
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
@@ -195,6 +221,14 @@ __device__ __forceinline__ void bulk_g2s_elect(void* dst_smem, const void* src_g
 // fma.rn.f32.f16: an fp16 product accumulated onto an fp32 addend, exact here) gives v - hi without unpacking, one packed conversion
 // gives both lo halves.
 __device__ __forceinline__ void split_pack2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+#ifdef VT_OLD_SPLIT
+    const __half2 h = __floats2half2_rn(v0, v1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+    return;
+#endif
     float l0, l1;
     asm("{\n\t.reg .b16 h0, h1, m;\n\t"
         "cvt.rn.f16x2.f32 %0, %4, %3;\n\t"
