@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
             float v = acc[i][j] * g.alpha;
             if (g.bias) v += __ldg(g.bias + n);
             if (g.act == ACT_RELU) v = fmaxf(v, 0.f);
-            else if (g.act == ACT_HSWISH) v = v * fminf(fmaxf(v + 3.f, 0.f), 6.f) / 6.f;
+            else if (g.act == ACT_HSWISH) v = hardswish_exact(v);
             else if (g.act == ACT_GELU) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
             if (R) v += R[(size_t)(g.rmod > 0 ? m % g.rmod : m) * g.ldr + n];
             C[(size_t)m * g.ldc + n] = v;
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kTcGemmThreads) gemm_tc_kernel(GemmArgs g) {
                 float v = __uint_as_float(r[j]) * g.alpha;
                 if (g.bias) v += __ldg(g.bias + n0 + c0 + j);
                 if (g.act == ACT_RELU) v = fmaxf(v, 0.f);
-                else if (g.act == ACT_HSWISH) v = v * fminf(fmaxf(v + 3.f, 0.f), 6.f) / 6.f;
+                else if (g.act == ACT_HSWISH) v = hardswish_exact(v);
                 else if (g.act == ACT_GELU) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
                 if (rp) v += rp[j];
                 cp[j] = v;

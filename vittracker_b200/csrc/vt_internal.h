@@ -18,6 +18,20 @@ constexpr int kTz = 128;        // template crop side
 constexpr int kSx = 256;        // search crop side
 constexpr float kLnEps = 1e-5f;
 
+#ifdef __CUDACC__
+// Hardswish exactly as PyTorch evaluates it, x * relu6(x + 3) / 6 (vit_dist.py:41, torch.nn.Hardswish): the product is rounded to fp32 and
+// then DIVIDED by 6, correctly rounded.  The division is  q = p r;  q' = fma(fma(-6, q, p), r, q)  with r = fl(1/6): checked over all 2^32
+// bit patterns (tools/div6_check.cu) to equal IEEE p / 6.f for every |p| >= 2^-125; below that (subnormal quotients, signed zeros - a
+// negative x <= -3 gives p = -0) the IEEE division runs.  4 instructions instead of the ~12 + slow path of a general fp32 division.
+__device__ __forceinline__ float div6_exact(float p) {
+    const float r = 0.16666667163372039794921875f;
+    const float q = __fmul_rn(p, r);
+    const float fast = __fmaf_rn(__fmaf_rn(-6.f, q, p), r, q);
+    return fabsf(p) >= 1e-36f ? fast : __fdiv_rn(p, 6.f);
+}
+__device__ __forceinline__ float hardswish_exact(float x) { return div6_exact(__fmul_rn(x, fminf(fmaxf(x + 3.f, 0.f), 6.f))); }
+#endif
+
 // ---- packed weights (device, fp32) --------------------------------------------------------------
 struct StemLayerW {          // conv3x3 s2 p1 with BN folded
     const float* w;          // [cin][3][3][cout]

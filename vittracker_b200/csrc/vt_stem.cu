@@ -119,7 +119,7 @@ __device__ __forceinline__ void conv_compute(const float* tile, const float* ws,
 #pragma unroll
         for (int q = 0; q < QG; ++q) {
             float v = acc[p][q];
-            if (HSWISH) v = v * fminf(fmaxf(v + 3.f, 0.f), 6.f) / 6.f;     // x * relu6(x + 3) / 6
+            if (HSWISH) v = hardswish_exact(v);                            // x * relu6(x + 3) / 6
             acc[p][q] = v;
         }
         if (TCOUT_CCH > 0) {

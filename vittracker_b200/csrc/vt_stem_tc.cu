@@ -241,7 +241,7 @@ conv_s2_tc_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wt
                         }
                         if (ox == 0) tb = 0.f;
                         float t = __uint_as_float(ra[j]) + tb + sBias[chb + c0 + j];
-                        if (HSWISH) t = t * fminf(fmaxf(t + 3.f, 0.f), 6.f) / 6.f;
+                        if (HSWISH) t = hardswish_exact(t);
                         v[j] = (chb + c0 + j < COUT) ? t : 0.f;                         // padding channels stay exactly zero
                     }
                     if (chb + c0 >= COUT) continue;
