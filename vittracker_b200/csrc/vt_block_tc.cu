@@ -183,6 +183,48 @@ __device__ __forceinline__ float gelu_erf(float v) {
     return fmaf(-(av * (p * t)), e, fmaxf(v, 0.f));
 }
 
+// Two GELUs at once with sm_100's packed fp32 arithmetic (fma / mul .f32x2, SASS FFMA2 / FMUL2: two independent IEEE operations per issue
+// slot).  Same operation sequence as gelu_erf per element - the polynomial carries the minus sign of the last product in its coefficients,
+// which is exact - so the results are bit-identical; 19 issue slots per pair instead of 28.
+__device__ __forceinline__ uint64_t f2pack(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2bcast(float c) { return f2pack(c, c); }
+__device__ __forceinline__ uint64_t f2fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2mul(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2add(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ void gelu_erf2(uint64_t v, float& h0, float& h1) {
+    float v0, v1;
+    f2unpack(v, v0, v1);
+    const uint64_t av = f2pack(fabsf(v0), fabsf(v1));
+    float d0, d1;
+    f2unpack(f2fma(f2bcast(0.3275911f * 0.70710678118654752f), av, f2bcast(1.f)), d0, d1);
+    const uint64_t t = f2pack(rcp_approx(d0), rcp_approx(d1));
+    uint64_t p = f2fma(f2bcast(-0.5f * 1.061405429f), t, f2bcast(0.5f * 1.453152027f));       // -P(t) / 2
+    p = f2fma(p, t, f2bcast(-0.5f * 1.421413741f));
+    p = f2fma(p, t, f2bcast(0.5f * 0.284496736f));
+    p = f2fma(p, t, f2bcast(-0.5f * 0.254829592f));
+    float w0, w1;
+    f2unpack(f2mul(v, f2mul(f2bcast(-0.5f * 1.4426950408889634f), v)), w0, w1);
+    const uint64_t e = f2pack(ex2_approx(w0), ex2_approx(w1));
+    f2unpack(f2fma(f2mul(av, f2mul(p, t)), e, f2pack(fmaxf(v0, 0.f), fmaxf(v1, 0.f))), h0, h1);
+}
+
 }  // namespace
 
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -490,6 +532,7 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                             tmem_ld16(a0 + 16 * kNS * k, r);
                             tc_wait_ld();
                             uint32_t hi[8], lo[8];
+#ifdef VT_SCALAR_GELU
                             float l0 = 0.f, l1 = 0.f;
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
@@ -498,6 +541,21 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                                 l0 += p0; l1 += p1;
                                 split_pack2(p0, p1, hi[j], lo[j]);
                             }
+#else
+                            // packed fp32 (FFMA2 / FADD2): the same two sums, two keys per issue slot
+                            uint64_t l2 = 0ull;
+                            const uint64_t nmb2 = f2bcast(-mb);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float a0, a1;
+                                f2unpack(f2fma(f2pack(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), f2bcast(kLog2e), nmb2), a0, a1);
+                                const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
+                                l2 = f2add(l2, f2pack(p0, p1));
+                                split_pack2(p0, p1, hi[j], lo[j]);
+                            }
+                            float l0, l1;
+                            f2unpack(l2, l0, l1);
+#endif
                             l += l0 + l1;
                             tmem_st8(a0 + 16 * kNS * k, hi);       // P overwrites S in place: [hi x8 | lo x8] per 16 keys
                             tmem_st8(a0 + 16 * kNS * k + 8, lo);
@@ -544,8 +602,14 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                         uint32_t hi[8], lo[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
+#ifdef VT_SCALAR_GELU
                             const float h0 = gelu_erf(__uint_as_float(r[2 * j]) + par[kPBfc1 + kHW * s + 16 * g + 2 * j]);
                             const float h1 = gelu_erf(__uint_as_float(r[2 * j + 1]) + par[kPBfc1 + kHW * s + 16 * g + 2 * j + 1]);
+#else
+                            float h0, h1;
+                            gelu_erf2(f2add(f2pack(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])),
+                                            f2pack(par[kPBfc1 + kHW * s + 16 * g + 2 * j], par[kPBfc1 + kHW * s + 16 * g + 2 * j + 1])), h0, h1);
+#endif
                             split_pack2(h0, h1, hi[j], lo[j]);
                         }
                         tmem_st8(a0 + 16 * g, hi);

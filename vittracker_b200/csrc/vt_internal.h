@@ -30,6 +30,45 @@ __device__ __forceinline__ float div6_exact(float p) {
     return fabsf(p) >= 1e-36f ? fast : __fdiv_rn(p, 6.f);
 }
 __device__ __forceinline__ float hardswish_exact(float x) { return div6_exact(__fmul_rn(x, fminf(fmaxf(x + 3.f, 0.f), 6.f))); }
+
+// The same function over N values (N even) with sm_100's packed fp32 arithmetic (add / mul / fma .f32x2: two independent IEEE operations
+// per issue slot, SASS FADD2 / FMUL2 / FFMA2) and ONE branch: the fast quotient keeps the sign of a zero product through an OR with the
+// product's sign bit (p = -0 for every x <= -3), and the products that need the IEEE division (0 < |p| < 1e-36) only raise a flag; the
+// division then runs for the whole group, out of line.  Bit-identical to hardswish_exact per element.
+template <int N>
+__device__ __forceinline__ void hardswish_exact_n(float (&v)[N]) {
+    static_assert(N % 2 == 0, "pairs");
+    const uint64_t k3 = 0x4040000040400000ull, kr = 0x3e2aaaab3e2aaaabull, km6 = 0xc0c00000c0c00000ull;   // {3, 3}, {fl(1/6)} x 2, {-6, -6}
+    float p[N];
+    bool slow = false;
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+        uint64_t x, t, pp, q, e, f;
+        float t0, t1;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(v[i]), "f"(v[i + 1]));
+        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(x), "l"(k3));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(t0), "=f"(t1) : "l"(t));
+        t0 = fminf(fmaxf(t0, 0.f), 6.f);
+        t1 = fminf(fmaxf(t1, 0.f), 6.f);
+        asm("mov.b64 %0, {%1, %2};" : "=l"(t) : "f"(t0), "f"(t1));
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(pp) : "l"(x), "l"(t));
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(q) : "l"(pp), "l"(kr));
+        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(e) : "l"(km6), "l"(q), "l"(pp));
+        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(f) : "l"(e), "l"(kr), "l"(q));
+        const uint32_t p0 = (uint32_t)pp, p1 = (uint32_t)(pp >> 32);
+        p[i] = __uint_as_float(p0);
+        p[i + 1] = __uint_as_float(p1);
+        v[i] = __uint_as_float((uint32_t)f | (p0 & 0x80000000u));
+        v[i + 1] = __uint_as_float((uint32_t)(f >> 32) | (p1 & 0x80000000u));
+        // 0 < |p| < 1e-36f (bits 0x03aa2425): shift the sign out, map zero above everything
+        slow |= (2u * p0 - 1u) < (2u * 0x03aa2425u - 1u);
+        slow |= (2u * p1 - 1u) < (2u * 0x03aa2425u - 1u);
+    }
+    if (__builtin_expect(slow, 0)) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = __fdiv_rn(p[i], 6.f);
+    }
+}
 #endif
 
 // ---- packed weights (device, fp32) --------------------------------------------------------------

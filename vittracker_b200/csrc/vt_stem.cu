@@ -52,8 +52,22 @@ struct ConvCfg {
     static_assert(kPitch % 2 == 0 && kOOff % 2 == 0, "8-byte aligned odd-slot stores");
 };
 
+// sm_100 packed fp32 FMA (SASS FFMA2): two independent IEEE fmaf in one issue slot - bit-identical to two scalar FFMA
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 // Accumulate and store: the tile / weights / bias are in shared memory (see ConvCfg for the tile layout).
-template <int CIN, int COUT, int QG, int P, int TW, int TH, bool HSWISH, bool TOKENS, int TCOUT_CCH = 0>
+// PAIRED: the weights sit in shared memory duplicated, [cin][ky][kx][cout] of float2 {w, w}, and two output pixels of a
+// thread share one packed FMA (the accumulation order of every output is unchanged, so the results are too).
+template <int CIN, int COUT, int QG, int P, int TW, int TH, bool HSWISH, bool TOKENS, int TCOUT_CCH = 0, bool PAIRED = false>
 __device__ __forceinline__ void conv_compute(const float* tile, const float* ws, const float* bs, int tx0, int ty0, int Hout,
                                              int Wout, int b, float* __restrict__ out, const float* __restrict__ pos,
                                              int tok_stride_rows, int tok_off) {
@@ -69,6 +83,57 @@ __device__ __forceinline__ void conv_compute(const float* tile, const float* ws,
     for (int p = 0; p < P; ++p) ly[p] = (wq * P + p) * kRowsPerWarp + lane / TW;
 
     float acc[P][QG];
+    if constexpr (PAIRED) {
+        static_assert(!PAIRED || (P % 2 == 0 && QG % 2 == 0), "pixel pairs, channel pairs per 16-byte weight load");
+        uint64_t acc2[P / 2][QG];
+#pragma unroll
+        for (int pp = 0; pp < P / 2; ++pp)
+#pragma unroll
+            for (int q = 0; q < QG; ++q) acc2[pp][q] = pack_f32x2(bs[cg * QG + q], bs[cg * QG + q]);
+#pragma unroll 1
+        for (int ci = 0; ci < CIN; ++ci) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                uint64_t x2[P / 2][3];
+#pragma unroll
+                for (int pp = 0; pp < P / 2; ++pp) {
+                    const float* r0 = tile + (ci * K::kInRows + 2 * ly[2 * pp] + ky) * K::kPitch;
+                    const float* r1 = tile + (ci * K::kInRows + 2 * ly[2 * pp + 1] + ky) * K::kPitch;
+                    x2[pp][0] = pack_f32x2(r0[K::kEOff + lx], r1[K::kEOff + lx]);
+                    x2[pp][1] = pack_f32x2(r0[K::kOOff + lx], r1[K::kOOff + lx]);
+                    x2[pp][2] = pack_f32x2(r0[K::kEOff + lx + 1], r1[K::kEOff + lx + 1]);
+                }
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(ws) + ((((ci * 3 + ky) * 3 + kx) * COUT + cg * QG) >> 1);
+#pragma unroll
+                    for (int q = 0; q < QG; q += 2) {
+                        const ulonglong2 w2 = wp[q >> 1];                      // {w[q], w[q]}, {w[q+1], w[q+1]}
+#pragma unroll
+                        for (int pp = 0; pp < P / 2; ++pp) {
+                            acc2[pp][q] = ffma2(x2[pp][kx], w2.x, acc2[pp][q]);
+                            acc2[pp][q + 1] = ffma2(x2[pp][kx], w2.y, acc2[pp][q + 1]);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int pp = 0; pp < P / 2; ++pp) {
+            float h[2 * QG];                                               // the pixel pair's values, still register pairs
+#pragma unroll
+            for (int q = 0; q < QG; ++q) {
+                h[2 * q] = __uint_as_float((uint32_t)acc2[pp][q]);
+                h[2 * q + 1] = __uint_as_float((uint32_t)(acc2[pp][q] >> 32));
+            }
+            if (HSWISH) hardswish_exact_n<2 * QG>(h);                      // x * relu6(x + 3) / 6
+#pragma unroll
+            for (int q = 0; q < QG; ++q) {
+                acc[2 * pp][q] = h[2 * q];
+                acc[2 * pp + 1][q] = h[2 * q + 1];
+            }
+        }
+    } else {
 #pragma unroll
     for (int p = 0; p < P; ++p)
 #pragma unroll
@@ -110,18 +175,14 @@ __device__ __forceinline__ void conv_compute(const float* tile, const float* ws,
             }
         }
     }
+    }
 
     const int ox = tx0 + lx;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         const int oy = ty0 + ly[p];
         if (ox >= Wout || oy >= Hout) continue;
-#pragma unroll
-        for (int q = 0; q < QG; ++q) {
-            float v = acc[p][q];
-            if (HSWISH) v = hardswish_exact(v);                            // x * relu6(x + 3) / 6
-            acc[p][q] = v;
-        }
+        if (HSWISH && !PAIRED) hardswish_exact_n<QG>(acc[p]);              // x * relu6(x + 3) / 6
         if (TCOUT_CCH > 0) {
             // the next layer runs on the tensor cores: write its operand image (fp16 hi | lo, 8-channel chunks, parity planes)
             static_assert(TCOUT_CCH == 0 || QG == COUT, "thread must own every channel of the pixel");
@@ -236,7 +297,8 @@ conv3x3s2_kernel(const float* __restrict__ in, int Hin, int Win, const float* __
 using Conv1Cfg = ConvCfg<3, 6, 6, 4, 32, 32>;
 constexpr int kCc1Threads = Conv1Cfg::kThreads;                         // 256
 constexpr int kCc1TileSide = 2 * 32 + 1;                                // 65 resized-crop pixels per side
-constexpr size_t kCc1SmemBytes = Conv1Cfg::kSmemBytes + 64 + 2 * 80 * sizeof(int4);     // 4 CTAs / SM
+constexpr int kCc1WFloats = 2 * Conv1Cfg::kWFloats;                    // conv1 weights duplicated {w, w} for the packed FMAs
+constexpr size_t kCc1SmemBytes = Conv1Cfg::kSmemBytes + Conv1Cfg::kWFloats * sizeof(float) + 64 + 2 * 80 * sizeof(int4);     // 4 CTAs / SM
 
 // Per-track tap tables of the fused gather, computed once per track (float64 geometry + the resize taps) instead of by
 // every tile's CTA: taps[item][0][d + 1] = column record of resized-crop column d, taps[item][1][d + 1] = row record,
@@ -299,8 +361,8 @@ crop_conv1_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict_
     extern __shared__ __align__(16) float smem[];
     float* tile = smem;
     float* ws = smem + K::kTileFloats;
-    float* bs = ws + K::kWFloats;
-    int4* s_col = reinterpret_cast<int4*>(smem + ((K::kTileFloats + K::kWFloats + 6 + 3) / 4 * 4));
+    float* bs = ws + kCc1WFloats;
+    int4* s_col = reinterpret_cast<int4*>(smem + ((K::kTileFloats + kCc1WFloats + 6 + 3) / 4 * 4));
     int4* s_row = s_col + 80;
 
     constexpr int Hout = S / 2;
@@ -310,7 +372,10 @@ crop_conv1_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict_
     const int item = blockIdx.y;
     const int tid = threadIdx.x;
 
-    for (int i = tid * 4; i < K::kWFloats; i += kCc1Threads * 4) cp_async<16>(ws + i, wg + i, true);
+    if (tid < 3 * 9 * 6) {                                                 // weights as {w, w} pairs (conv_compute PAIRED)
+        const float wv = __ldg(wg + tid);
+        reinterpret_cast<float2*>(ws)[tid] = make_float2(wv, wv);
+    }
     if (tid < 6) cp_async<4>(bs + tid, bg + tid, true);
     asm volatile("cp.async.commit_group;\n" ::: "memory");
 
@@ -330,6 +395,7 @@ crop_conv1_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict_
     auto gather_col = [&](auto kb_tag, int r_first, int r_step, int n_batches, const int4 ct, int slot) {
         constexpr int kB = decltype(kb_tag)::value;
         const unsigned wx = (unsigned)ct.y;
+        const uint8_t* __restrict__ colp = im + ct.x;                     // this thread's column; row offsets are unsigned 32-bit (< 2^31)
 #pragma unroll 1
         for (int rb = 0; rb < n_batches; ++rb) {
             uint32_t wd[kB][6];
@@ -339,13 +405,13 @@ crop_conv1_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict_
 #pragma unroll
             for (int k = 0; k < kB; ++k) {
                 const int4 rt = s_row[r_first + (rb * kB + k) * r_step];
-                const uintptr_t q0 = reinterpret_cast<uintptr_t>(im + (rt.x + ct.x));
-                const uintptr_t q1 = reinterpret_cast<uintptr_t>(im + (rt.y + ct.x));
+                const uintptr_t q0 = reinterpret_cast<uintptr_t>(colp + (unsigned)rt.x);
+                const uintptr_t q1 = reinterpret_cast<uintptr_t>(colp + (unsigned)rt.y);
                 const uint32_t* p0 = reinterpret_cast<const uint32_t*>(q0 & ~static_cast<uintptr_t>(3));
                 const uint32_t* p1 = reinterpret_cast<const uint32_t*>(q1 & ~static_cast<uintptr_t>(3));
                 wd[k][0] = __ldg(p0); wd[k][1] = __ldg(p0 + 1); wd[k][2] = __ldg(p0 + 2);
                 wd[k][3] = __ldg(p1); wd[k][4] = __ldg(p1 + 1); wd[k][5] = __ldg(p1 + 2);
-                sh[k][0] = ((unsigned)q0 & 3u) * 8u; sh[k][1] = ((unsigned)q1 & 3u) * 8u;
+                sh[k][0] = (unsigned)q0 << 3; sh[k][1] = (unsigned)q1 << 3;           // the funnel shift takes the amount mod 32 = 8 * (q & 3)
                 bz[k] = rt.z;
                 outside[k] = ((ct.w | rt.w) & 1) != 0;
             }
@@ -383,7 +449,7 @@ crop_conv1_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict_
     }
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncthreads();
-    conv_compute<3, 6, 6, 4, 32, 32, true, false, TCOUT_CCH>(tile, ws, bs, tx0, ty0, Hout, Hout, item, out, nullptr, 0, 0);
+    conv_compute<3, 6, 6, 4, 32, 32, true, false, TCOUT_CCH, true>(tile, ws, bs, tx0, ty0, Hout, Hout, item, out, nullptr, 0, 0);
 }
 
 template <int CIN, int COUT, int QG, int P, int TW, int TH, bool HSWISH, bool TOKENS, int TCOUT_CCH = 0>

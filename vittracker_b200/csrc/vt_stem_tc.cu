@@ -240,10 +240,12 @@ conv_s2_tc_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wt
                             if (lane == 0 && (warp & 1)) tb = xs[j];
                         }
                         if (ox == 0) tb = 0.f;
-                        float t = __uint_as_float(ra[j]) + tb + sBias[chb + c0 + j];
-                        if (HSWISH) t = hardswish_exact(t);
-                        v[j] = (chb + c0 + j < COUT) ? t : 0.f;                         // padding channels stay exactly zero
+                        v[j] = __uint_as_float(ra[j]) + tb + sBias[chb + c0 + j];
                     }
+                    if (HSWISH) hardswish_exact_n<8>(v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (chb + c0 + j >= COUT) v[j] = 0.f;                           // padding channels stay exactly zero
                     if (chb + c0 >= COUT) continue;
                     if (OUT_PLANES) {
                         // this layer's output pixel (oy, ox) is the next layer's input pixel: 8 channels = one chunk, hi | lo
