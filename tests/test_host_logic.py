@@ -136,3 +136,13 @@ def test_sharded_gather_gloo_world2(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=180)
         assert p.returncode == 0 and "OK" in out, out
+
+
+def test_table_free_normalisation_is_exact():
+    """The fused crop + conv1 kernel normalises pixels in registers (vt_stem.cu: normalize_px): its two divisions by constants
+    must equal the reference's rounded ((v / 255) - mean) / std for all 256 values x 3 channels (exact rational arithmetic)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("norm_exact_check", os.path.join(ROOT, "tools", "norm_exact_check.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.check() == 0

@@ -64,6 +64,49 @@ __device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
     return r;
 }
 
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+// Preprocessor.process (lib/test/tracker/data_utils.py:8-14) on a uint8 pixel value without a table:  ((v / 255) - mean) / std, every
+// step rounded to fp32.  Both divisions are by constants and take the same form as div6_exact -  q = a r;  q' = fma(fma(-d, q, a), r, q)
+// with r = fl(1 / d)  - which equals the IEEE quotient for each of the 256 pixel values and each of the three channels (checked
+// exhaustively in exact rational arithmetic: tools/norm_exact_check.py; the table of vt_api.cu fill_hann_and_lut holds the same bits).
+// The gather was bound by L1 wavefronts, and three scattered table loads per pixel were half of them.
+struct NormConst {
+    static constexpr float kR255 = 1.0f / 255.0f;
+    __device__ static constexpr float mean(int ch) { return ch == 0 ? 0.485f : ch == 1 ? 0.456f : 0.406f; }
+    __device__ static constexpr float stdv(int ch) { return ch == 0 ? 0.229f : ch == 1 ? 0.224f : 0.225f; }
+    __device__ static constexpr float rstd(int ch) { return ch == 0 ? 1.0f / 0.229f : ch == 1 ? 1.0f / 0.224f : 1.0f / 0.225f; }
+};
+template <int CH>
+__device__ __forceinline__ float normalize_px(int v) {                     // 0 <= v <= 255
+    const float a = __int_as_float(0x4b000000 | v) - 8388608.f;            // exact int -> float
+    const float q = __fmul_rn(a, NormConst::kR255);
+    const float x = __fmaf_rn(__fmaf_rn(-255.f, q, a), NormConst::kR255, q);
+    const float y = __fadd_rn(x, -NormConst::mean(CH));
+    const float z = __fmul_rn(y, NormConst::rstd(CH));
+    return __fmaf_rn(__fmaf_rn(-NormConst::stdv(CH), z, y), NormConst::rstd(CH), z);
+}
+template <int CH>
+__device__ __forceinline__ void normalize_px2(int v0, int v1, float& o0, float& o1) {      // two pixels per issue slot
+    const uint64_t a = fadd2(pack_f32x2(__int_as_float(0x4b000000 | v0), __int_as_float(0x4b000000 | v1)), pack_f32x2(-8388608.f, -8388608.f));
+    const uint64_t r = pack_f32x2(NormConst::kR255, NormConst::kR255), rs = pack_f32x2(NormConst::rstd(CH), NormConst::rstd(CH));
+    const uint64_t q = fmul2(a, r);
+    const uint64_t x = ffma2(ffma2(pack_f32x2(-255.f, -255.f), q, a), r, q);
+    const uint64_t y = fadd2(x, pack_f32x2(-NormConst::mean(CH), -NormConst::mean(CH)));
+    const uint64_t z = fmul2(y, rs);
+    const uint64_t o = ffma2(ffma2(pack_f32x2(-NormConst::stdv(CH), -NormConst::stdv(CH)), z, y), rs, z);
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(o0), "=f"(o1) : "l"(o));
+}
+
 // Accumulate and store: the tile / weights / bias are in shared memory (see ConvCfg for the tile layout).
 // PAIRED: the weights sit in shared memory duplicated, [cin][ky][kx][cout] of float2 {w, w}, and two output pixels of a
 // thread share one packed FMA (the accumulation order of every output is unchanged, so the results are too).
@@ -353,9 +396,9 @@ crop_taps_kernel(const int32_t* __restrict__ frame_hw, const double* __restrict_
 }
 
 template <int S, int TCOUT_CCH>
-__global__ void __launch_bounds__(kCc1Threads)
+__global__ void __launch_bounds__(kCc1Threads, 4)
 crop_conv1_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict__ frame_offsets,
-                  const int4* __restrict__ taps, const float* __restrict__ lut, const float* __restrict__ wg,
+                  const int4* __restrict__ taps, const float* __restrict__ wg,
                   const float* __restrict__ bg, float* __restrict__ out) {
     using K = Conv1Cfg;
     extern __shared__ __align__(16) float smem[];
@@ -386,11 +429,11 @@ crop_conv1_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict_
 
     const uint8_t* __restrict__ im = frames + frame_offsets[item];
     // One resized-crop pixel (3 channels) of tile position (r, c): 2x2 source taps, 11-bit fixed point exactly as
-    // cv::resize (HResize then VResizeLinear 8U), then the normalisation table.  Each tap row is read as three aligned
+    // cv::resize (HResize then VResizeLinear 8U), then the normalisation (normalize_px).  Each tap row is read as three aligned
     // 32-bit words covering the pair's six bytes (R0 G0 B0 R1 G1 B1), realigned with funnel shifts; a channel's
     // horizontal pass is one byte permute + one two-way dot product with the packed weights.
     // kB tile rows of one column per batch, in three explicit phases so that every global load of the batch is in
-    // flight before its first use: (1) 6 word loads per row, (2) fixed-point bilinear + table loads, (3) tile stores.
+    // flight before its first use: (1) 6 word loads per row, (2) fixed-point bilinear + normalisation, (3) tile stores.
     // Branch-free: padding positions read offset 0 with weight 0 and are zeroed at the end.
     auto gather_col = [&](auto kb_tag, int r_first, int r_step, int n_batches, const int4 ct, int slot) {
         constexpr int kB = decltype(kb_tag)::value;
@@ -416,6 +459,7 @@ crop_conv1_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict_
                 outside[k] = ((ct.w | rt.w) & 1) != 0;
             }
             float val[kB][3];
+            int px[kB][3];
 #pragma unroll
             for (int k = 0; k < kB; ++k) {
                 const uint32_t u0 = __funnelshift_r(wd[k][0], wd[k][1], sh[k][0]), u1 = __funnelshift_r(wd[k][1], wd[k][2], sh[k][0]);   // R0 G0 B0 R1 | G1 B1 . .
@@ -426,9 +470,20 @@ crop_conv1_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict_
                     const unsigned sel = ch == 0 ? 0x0030u : ch == 1 ? 0x0041u : 0x0052u;             // (first, second) pixel's byte
                     const int h0 = (int)__dp2a_lo(wx, __byte_perm(u0, u1, sel), 0u);
                     const int h1 = (int)__dp2a_lo(wx, __byte_perm(t0, t1, sel), 0u);
-                    const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;     // always in [0, 255]
-                    val[k][ch] = __ldg(lut + 256 * ch + v);                                           // 3 KB table, L1 resident
+                    px[k][ch] = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;       // always in [0, 255]
                 }
+            }
+            // normalisation in registers (no table: the gather is bound by L1 wavefronts), two rows per packed operation
+#pragma unroll
+            for (int k = 0; k + 1 < kB; k += 2) {
+                normalize_px2<0>(px[k][0], px[k + 1][0], val[k][0], val[k + 1][0]);
+                normalize_px2<1>(px[k][1], px[k + 1][1], val[k][1], val[k + 1][1]);
+                normalize_px2<2>(px[k][2], px[k + 1][2], val[k][2], val[k + 1][2]);
+            }
+            if constexpr (kB % 2 == 1) {
+                val[kB - 1][0] = normalize_px<0>(px[kB - 1][0]);
+                val[kB - 1][1] = normalize_px<1>(px[kB - 1][1]);
+                val[kB - 1][2] = normalize_px<2>(px[kB - 1][2]);
             }
 #pragma unroll
             for (int k = 0; k < kB; ++k) {
@@ -499,7 +554,7 @@ static int run_crop_conv1(const uint8_t* frames, const int64_t* frame_offsets, c
     for (int first = 0; first < n; first += 32768) {
         const int m = min(32768, n - first);
         kern<<<dim3(tiles, m), kCc1Threads, kCc1SmemBytes, st>>>(frames, frame_offsets + first, taps + (size_t)first * 2 * kTapPitch,
-                                                                 w.lut, w.stem[0].w, w.stem[0].b,
+                                                                 w.stem[0].w, w.stem[0].b,
                                                                  TCOUT_CCH > 0 ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(out) + (size_t)first * tc_planes_bytes(TCOUT_CCH, S / 4))
                                                                                : out + (size_t)first * 6 * (S / 2) * (S / 2));
         ++launched;
