@@ -219,6 +219,7 @@ def main():
     ap.add_argument("--blocks", default="tcgen05", choices=["simt", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--latency-frames", type=int, default=300, help="open-loop frames of the batch-1 latency leg (SURVEY C2 asks for 10000)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
 
@@ -396,7 +397,7 @@ def main():
         line["stages"]["crop"]["note"] = "HBM-bound gather; see profiles/ for achieved GB/s"
 
     if world == 1 and not args.no_latency:
-        line["latency_b1"] = latency_b1(cfg, sd)
+        line["latency_b1"] = latency_b1(cfg, sd, iters=args.latency_frames)
     if world == 1 and not args.no_cpu_baseline:
         v, cores, sample = cpu_sample(sd)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
@@ -406,9 +407,10 @@ def main():
         dist.destroy_process_group()
 
 
-def latency_b1(cfg, sd, frames_n=8, iters=300):
-    """BASELINE configs[1]: batch-1 initialize() + track() loop through the drop-in tracker (host numpy
-    frame in, Python list out), wall clock per track() call."""
+def latency_b1(cfg, sd, frames_n=8, iters=300, burst=8):
+    """BASELINE configs[1] (SURVEY 8d, C2): batch-1 initialize() + track() loop through the drop-in tracker (host numpy
+    frame in, Python list out), wall clock per call.  `iters` open-loop frames (state re-seeded per frame), then
+    closed-loop bursts of `burst` frames after a re-initialisation (iters // 40 bursts), initialize() timed as well."""
     from oracle import vt_oracle as O
     from vittracker_b200 import get_tracker_class, parameters
     params = parameters("vit_48_h32_noKD")
@@ -424,8 +426,31 @@ def latency_b1(cfg, sd, frames_n=8, iters=300):
         trk.track(frames[i % frames_n], {})
         lat.append(time.perf_counter() - t0)
     lat = np.array(lat[20:]) * 1e3
-    return {"p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)), "frames": iters,
-            "path": "Vit_dist.track(): host frame rows H2D + crop + forward + decode + D2H, blocking"}
+    out = {"p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)), "frames": iters,
+           "path": "Vit_dist.track(): host frame rows H2D + crop + forward + decode + D2H, blocking"}
+    n_bursts = iters // 40
+    if n_bursts > 0 and burst > 0:
+        try:
+            out.update(_latency_bursts(trk, frames, boxes, frames_n, n_bursts, burst))
+        except Exception as e:                         # the headline line must not depend on this leg
+            out["closed_loop"] = {"error": f"{type(e).__name__}: {e}"}
+    return out
+
+
+def _latency_bursts(trk, frames, boxes, frames_n, n_bursts, burst):
+    lat_c, lat_i = [], []
+    for b in range(n_bursts):
+        t0 = time.perf_counter()
+        trk.initialize(frames[b % frames_n], {"init_bbox": list(boxes[b])})
+        lat_i.append(time.perf_counter() - t0)
+        for k in range(burst):                          # closed loop: the tracker follows its own state
+            t0 = time.perf_counter()
+            trk.track(frames[(b + 1 + k) % frames_n], {})
+            lat_c.append(time.perf_counter() - t0)
+    lat_c, lat_i = np.array(lat_c) * 1e3, np.array(lat_i) * 1e3
+    return {"closed_loop": {"p50_ms": float(np.percentile(lat_c, 50)), "p99_ms": float(np.percentile(lat_c, 99)),
+                            "frames": int(lat_c.size), "bursts": n_bursts, "burst": burst},
+            "initialize": {"p50_ms": float(np.percentile(lat_i, 50)), "p99_ms": float(np.percentile(lat_i, 99)), "calls": n_bursts}}
 
 
 if __name__ == "__main__":
