@@ -146,3 +146,20 @@ def test_table_free_normalisation_is_exact():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.check() == 0
+
+
+def test_ab_identity_compare_detects_a_single_bit(tmp_path):
+    """tools/ab_identity.py --compare is the gate for instruction-level rewrites: equal dumps pass, one flipped mantissa bit fails."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ab_identity", os.path.join(ROOT, "tools", "ab_identity.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(0)
+    a = {"boxes": rng.standard_normal((4, 5)), "score": rng.standard_normal((4, 1, 16, 16)).astype(np.float32)}
+    np.savez(tmp_path / "a.npz", **a)
+    np.savez(tmp_path / "b.npz", **a)
+    assert mod.compare(str(tmp_path / "a.npz"), str(tmp_path / "b.npz")) == 0
+    b = {k: v.copy() for k, v in a.items()}
+    b["score"].view(np.uint32)[0, 0, 3, 7] ^= 1
+    np.savez(tmp_path / "c.npz", **b)
+    assert mod.compare(str(tmp_path / "a.npz"), str(tmp_path / "c.npz")) == 1
