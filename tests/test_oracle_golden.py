@@ -119,3 +119,26 @@ def test_oracle_repinned_against_reference_itself():
     out = O.OracleModel(sd).forward(z, x)
     for k in ref:
         assert (ref[k] - out[k]).abs().max().item() <= 1e-6
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not mounted")
+@pytest.mark.parametrize("C,heads,depth,hc", [(96, 3, 2, 64), (40, 5, 1, 24)])
+def test_oracle_generic_family_against_reference_itself(C, heads, depth, hc):
+    """The generic-configuration path (BASELINE configs[4]) is checked on the GPU against the oracle at other widths / head counts /
+    depths: pin the oracle there too, against the reference's own build_ostrack_dist(cfg, depth) (vit_dist.py:159-164)."""
+    import copy
+    ns = ref_shim.load_reference()
+    cfg = copy.deepcopy(ref_shim.reference_cfg())
+    cfg.MODEL.BACKBONE.CHANNELS, cfg.MODEL.BACKBONE.HEADS, cfg.MODEL.HEAD.NUM_CHANNELS = C, heads, hc
+    sd = O.make_state_dict(seed=9, stress=True, C=C, depth=depth, head_ch=hc)
+    net = ns.build_ostrack_dist(cfg, depth=depth)
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    torch.manual_seed(2)
+    z, x = torch.randn(2, 3, 128, 128), torch.randn(2, 3, 256, 256)
+    with torch.no_grad():
+        ref = net.forward(z=z.clone(), x=x.clone())
+    out = O.OracleModel(sd, depth=depth, num_heads=heads).forward(z, x)
+    for k in ref:
+        assert ref[k].shape == out[k].shape
+        assert (ref[k] - out[k]).abs().max().item() <= 1e-6, k
