@@ -5,6 +5,7 @@ rewrite that must not change a single result bit).
     VT_LIB_DIR=<build A> python tools/ab_identity.py --dump gpurun_out/ab_a.npz
     VT_LIB_DIR=<build B> python tools/ab_identity.py --dump gpurun_out/ab_b.npz
     python tools/ab_identity.py --compare gpurun_out/ab_a.npz gpurun_out/ab_b.npz
+    python tools/ab_identity.py --ab <build A dir> <build B dir>            # the same in one process
 
 The workload is 2048 seeded open-loop tracks on smooth + white-noise 360x640 frames (boxes incl. border-touching and
 up-scaling cases, stress-init weights): dumped are the decoded boxes + confidence, the per-track detail row and the
@@ -22,6 +23,13 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+
+
+def use_library(lib_dir: str) -> None:
+    """Point the ctypes binding at another build (both builds can live in one process: dlopen handles are local)."""
+    from vittracker_b200 import _lib, build as _build
+    _build.LIB_PATH = os.path.join(os.path.abspath(lib_dir), "libvittrack_b200.so")
+    _lib._lib = None
 
 
 def dump(path: str, n: int, blocks: str) -> None:
@@ -64,7 +72,17 @@ if __name__ == "__main__":
     ap.add_argument("--compare", nargs=2)
     ap.add_argument("--n", type=int, default=2048)
     ap.add_argument("--blocks", default="tcgen05")
+    ap.add_argument("--ab", nargs=2, metavar=("LIB_DIR_A", "LIB_DIR_B"), help="dump both builds in this process and compare")
     a = ap.parse_args()
     if a.compare:
         sys.exit(compare(*a.compare))
+    if a.ab:
+        import tempfile
+        tmp = tempfile.mkdtemp()
+        paths = []
+        for tag, d in zip("ab", a.ab):
+            use_library(d)
+            paths.append(os.path.join(tmp, f"{tag}.npz"))
+            dump(paths[-1], a.n, a.blocks)
+        sys.exit(compare(*paths))
     dump(a.dump, a.n, a.blocks)
