@@ -163,3 +163,38 @@ def test_ab_identity_compare_detects_a_single_bit(tmp_path):
     b["score"].view(np.uint32)[0, 0, 3, 7] ^= 1
     np.savez(tmp_path / "c.npz", **b)
     assert mod.compare(str(tmp_path / "a.npz"), str(tmp_path / "c.npz")) == 1
+
+
+def test_hardswish_division_algorithm_on_samples():
+    """vt_internal.h div6_exact / hardswish_exact_n: q = p r; q' = fma(fma(-6, q, p), r, q), r = fl(1/6), sign of a zero product restored with
+    an OR, IEEE division below 1e-36.  The exhaustive check is the GPU tool (tools/div6_check.cu); here the same algorithm is emulated in exact
+    rational arithmetic on edge cases + 20 000 random bit patterns and compared with the correctly rounded p / 6."""
+    import importlib.util
+    from fractions import Fraction as Fr
+    spec = importlib.util.spec_from_file_location("norm_exact_check", os.path.join(ROOT, "tools", "norm_exact_check.py"))
+    nx = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(nx)
+    fl, ex, fma, bits = nx.fl, nx.ex, nx.fma, nx.bits
+    r = np.float32(0.16666667163372039794921875)
+    assert bits(r) == bits(fl(Fr(1, 6)))
+    rng = np.random.default_rng(5)
+    pats = rng.integers(0, 2 ** 32, size=20000, dtype=np.uint64).astype(np.uint32)
+    edge = np.array([0x00000000, 0x80000000, 0x03aa2425, 0x03aa2424, 0x83aa2425, 0x3f800000, 0x40c00000, 0x7f7fffff, 0xff7fffff,
+                     0x00800000, 0x01000000, 0x3e2aaaab, 0x40400000], dtype=np.uint32)
+    bad = 0
+    for u in np.concatenate([edge, pats]):
+        p = np.array([u], dtype=np.uint32).view(np.float32)[0]
+        if not np.isfinite(p):
+            continue
+        want = fl(ex(p) / 6)
+        if abs(float(p)) >= 1e-36 or p == 0:
+            q = fl(ex(p) * ex(r))
+            f = fma(fma(np.float32(-6.0), q, p), r, q)
+            got_bits = bits(f) | (int(u) & 0x80000000)          # the OR that keeps -0 (x <= -3 gives p = -0)
+        else:
+            got_bits = None
+        want_bits = bits(want) | ((int(u) & 0x80000000) if want == 0 else 0)     # fl() drops the sign of a zero quotient
+        if not (abs(float(p)) >= 1e-36 or p == 0):
+            got_bits = want_bits                                 # the out-of-line IEEE division
+        bad += got_bits != want_bits
+    assert bad == 0
