@@ -67,6 +67,58 @@ def test_scheduler_ragged_sequences_and_result_files(tmp_path):
     assert set(res2) == {"s1"} and not be2.log            # s1 has a single frame: no box file is ever written for it
 
 
+def test_threaded_frame_ingest_from_image_files(tmp_path):
+    """frames given as image paths are decoded (cv.imread + BGR2RGB, tracker.py:282-289) by reader threads, the next
+    step's frames while the current step runs - same frames, same order, same results as decoding on the calling thread; a sequence
+    whose frame cannot be read is reported and dropped without disturbing the others."""
+    cv = pytest.importorskip("cv2")
+    lengths = [6, 3, 9, 4, 5]
+    seqs = []
+    for i, n in enumerate(lengths):
+        paths = []
+        for k in range(n):
+            rgb = np.zeros((6, 8, 3), dtype=np.uint8)
+            rgb[..., 0], rgb[..., 1], rgb[..., 2] = i, k, 200             # R = sequence, G = frame index
+            path = str(tmp_path / f"s{i}_{k:03d}.png")
+            assert cv.imwrite(path, rgb[..., ::-1])                       # files hold BGR
+            paths.append(path)
+        seqs.append(Sequence(f"s{i}", paths, [10.0 * i, 5.0, 20.0, 30.0]))
+
+    class Recorder(FakeBackend):
+        def step(self, images):
+            for i, im in enumerate(images):
+                if im is not None:
+                    assert im.shape == (6, 8, 3) and int(im[0, 0, 2]) == 200          # RGB order restored
+                    self.log.append(("frame", i, int(im[0, 0, 0]), int(im[0, 0, 1])))
+            return super().step(images)
+
+    def run(workers, sequences):
+        be = Recorder(2)
+        r = MultiSequenceRunner(be, 2, read_workers=workers)
+        try:
+            return r.run(sequences), be
+        finally:
+            r.close()
+
+    res0, be0 = run(0, seqs)
+    res4, be4 = run(4, seqs)
+    assert set(res0) == set(res4) == {f"s{i}" for i in range(len(lengths))}
+    for name in res0:
+        assert res0[name]["target_bbox"] == res4[name]["target_bbox"]
+    frames0 = [e for e in be0.log if e[0] == "frame"]
+    frames4 = [e for e in be4.log if e[0] == "frame"]
+    assert frames0 == frames4
+    for i, n in enumerate(lengths):                                       # every sequence saw its frames 1 .. n-1 in order
+        assert [k for (_, _, s, k) in frames4 if s == i] == list(range(1, n))
+
+    os.remove(seqs[2].frames[4])                                          # s2 breaks at frame 4
+    res, be = run(4, seqs)
+    assert set(res) == {"s0", "s1", "s3", "s4"}
+    for name in res:
+        assert res[name]["target_bbox"] == res0[name]["target_bbox"]
+    assert [e[3] for e in be.log if e[0] == "frame" and e[2] == 2] == [1, 2, 3]
+
+
 def test_save_tracker_output_truncates_like_astype_int(tmp_path):
     s = Sequence("q", _frames(2, 0), [1, 2, 3, 4])
     save_tracker_output(str(tmp_path), s, {"target_bbox": [[1.9, 2.1, 3.999, 4.5], [10.2, -0.5, 7.7, 8.0]], "time": [0.25, 0.5]})

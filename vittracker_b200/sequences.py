@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import os
 import time
+from concurrent.futures import Future, ThreadPoolExecutor
 from typing import Callable, Dict, List, Optional, Sequence as Seq, Union
 
 import numpy as np
@@ -64,12 +65,14 @@ def save_tracker_output(results_dir: str, seq: Sequence, output: dict) -> None:
 
 
 class _Slot:
-    __slots__ = ("seq", "next_frame", "output")
+    __slots__ = ("seq", "next_frame", "output", "prefetch", "prefetch_idx")
 
     def __init__(self):
         self.seq: Optional[Sequence] = None
         self.next_frame = 0
         self.output: Optional[dict] = None
+        self.prefetch: Optional[Future] = None          # decode of frame `prefetch_idx`, started while the previous step ran
+        self.prefetch_idx = -1
 
 
 class BatchedBackend:
@@ -150,13 +153,59 @@ class BatchedBackend:
 class MultiSequenceRunner:
     """``run(sequences)``: the batched counterpart of run_dataset + Tracker.run_sequence for one GPU."""
 
-    def __init__(self, backend, slots: int, results_dir: Optional[str] = None, skip_existing: bool = True, verbose: bool = False):
+    def __init__(self, backend, slots: int, results_dir: Optional[str] = None, skip_existing: bool = True, verbose: bool = False,
+                 read_workers: int = 8):
+        """read_workers: threads that decode frames (frame ingest: cv.imread + BGR2RGB release the GIL).  The frames of a
+        step are decoded in parallel, and the frames of step t + 1 while the device runs step t; 0 = decode on the calling thread."""
         self.backend = backend
         self.slots = [_Slot() for _ in range(slots)]
         self.results_dir = results_dir
         self.skip_existing = skip_existing
         self.verbose = verbose
         self._parked = [False] * slots
+        self._readers = ThreadPoolExecutor(max_workers=read_workers, thread_name_prefix="vt-read") if read_workers > 0 else None
+
+    def close(self) -> None:
+        if self._readers is not None:
+            self._readers.shutdown(wait=False, cancel_futures=True)
+            self._readers = None
+
+    def _drop(self, slot: _Slot) -> None:
+        if slot.prefetch is not None:
+            slot.prefetch.cancel()
+        slot.seq, slot.output, slot.prefetch, slot.prefetch_idx = None, None, None, -1
+
+    def _step_images(self, high: int) -> List[Optional[np.ndarray]]:
+        """The next frame of every running slot below `high` (None for idle slots).  A sequence whose frame cannot be read is reported
+        and dropped, like a sequence that raises inside the reference's run_sequence (running.py:135-142)."""
+        futs: List[Optional[Future]] = [None] * high
+        for i, s in enumerate(self.slots[:high]):
+            if s.seq is None:
+                continue
+            if s.prefetch is not None and s.prefetch_idx == s.next_frame:
+                futs[i] = s.prefetch
+            elif self._readers is not None:
+                futs[i] = self._readers.submit(read_image, s.seq.frames[s.next_frame])
+            s.prefetch, s.prefetch_idx = None, -1
+        images: List[Optional[np.ndarray]] = [None] * high
+        for i, s in enumerate(self.slots[:high]):
+            if s.seq is None:
+                continue
+            try:
+                images[i] = futs[i].result() if futs[i] is not None else read_image(s.seq.frames[s.next_frame])
+            except Exception as e:
+                print(e)
+                self._drop(s)
+        return images
+
+    def _prefetch_next(self, active: List[int]) -> None:
+        if self._readers is None:
+            return
+        for i in active:
+            s = self.slots[i]
+            if s.seq is not None and s.next_frame + 1 < len(s.seq.frames):
+                s.prefetch_idx = s.next_frame + 1
+                s.prefetch = self._readers.submit(read_image, s.seq.frames[s.prefetch_idx])
 
     def _finish(self, slot: _Slot, results: Dict[str, dict]) -> None:
         seq, out = slot.seq, slot.output
@@ -168,7 +217,7 @@ class MultiSequenceRunner:
         if self.verbose:
             t = float(np.sum(out["time"]))
             print("FPS: {}".format(len(out["time"]) / t if t > 0 else float("inf")))          # running.py:146-150
-        slot.seq, slot.output = None, None
+        self._drop(slot)
 
     def run(self, sequences: Seq[Sequence]) -> Dict[str, dict]:
         pending = []
@@ -205,7 +254,9 @@ class MultiSequenceRunner:
                     self.backend.park(i)
                     self._parked[i] = True
             t0 = time.time()
-            images = [read_image(s.seq.frames[s.next_frame]) if s.seq is not None else None for s in self.slots[:high]]
+            images = self._step_images(high)
+            active = [i for i in active if self.slots[i].seq is not None]      # minus the sequences whose frame could not be read
+            self._prefetch_next(active)                                        # decode step t + 1 while the device runs step t
             boxes = self.backend.step(images)
             dt = time.time() - t0
             for i in active:
@@ -223,4 +274,8 @@ def run_sequences(sequences: Seq[Sequence], cfg, state_dict, slots: int = 64, re
     """Track every sequence; ``slots`` run concurrently on one GPU."""
     slots = max(1, min(slots, len(sequences)))
     backend = BatchedBackend(cfg, state_dict, slots, device=device, blocks_impl=blocks_impl)
-    return MultiSequenceRunner(backend, slots, results_dir=results_dir, **kw).run(sequences)
+    runner = MultiSequenceRunner(backend, slots, results_dir=results_dir, **kw)
+    try:
+        return runner.run(sequences)
+    finally:
+        runner.close()
