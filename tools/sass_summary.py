@@ -26,8 +26,11 @@ def main() -> None:
         c = collections.Counter(ops)
         dem = subprocess.run(["c++filt", name], capture_output=True, text=True).stdout.strip()
         dem = re.sub(r"\(.*", "", dem).replace("void ", "").replace("vt::", "")
-        if "(anonymous namespace)" in dem or not dem:
-            dem = re.sub(r"\(anonymous namespace\)::", "", dem) or name[:60]
+        m = re.search(r"_GLOBAL__N__[0-9a-f]+_\d+_\w+?_cu_[0-9a-f]{8}(\d+)", name)     # nvcc's internal-linkage mangling
+        if m:
+            n, rest = int(m.group(1)), name[m.end():]
+            targs = re.search(r"ILi(\d+)ELi(\d+)", rest[n:])
+            dem = rest[:n] + (f"<{targs.group(1)}, {targs.group(2)}>" if targs else "")
         print(f"| `{dem[:90]}` | {len(ops)} | " + " | ".join(str(c.get(k, 0) or "") for k in KEYS) + " |")
 
 
