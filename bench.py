@@ -165,6 +165,34 @@ def cpu_sample(sd, budget_s=12.0, tracks=64, frames_n=4):
     return done / el, torch.get_num_threads(), f"{done} tracked frames ({step} steps x {tracks} tracks, forward batched by 16) in {el:.1f} s"
 
 
+def cpu_model_name() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_b1_sample(sd, threads, budget_s=2.0):
+    """The reference's own shape of the path - one sequence, batch 1 (B = 1, all threads and one thread) - on the host:
+    frames/s of crop + forward + decode for a single track."""
+    from oracle import vt_oracle as O
+    torch.set_num_threads(threads)
+    frames = O.synth_frames(2, FRAME_H, FRAME_W, seed=110)
+    cp = CpuPath(sd, frames, group=1)
+    cp.prepare(O.synth_boxes(1, FRAME_H, FRAME_W, seed=111))
+    boxes = O.synth_boxes(64, FRAME_H, FRAME_W, seed=112)
+    cp.step(boxes[:1], 0)
+    done, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        cp.step(boxes[done % 64:done % 64 + 1], done)
+        done += 1
+    return done / (time.perf_counter() - t0)
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path on this box's host cores."""
     if rank != 0:
@@ -400,7 +428,12 @@ def main():
         line["latency_b1"] = latency_b1(cfg, sd, iters=args.latency_frames)
     if world == 1 and not args.no_cpu_baseline:
         v, cores, sample = cpu_sample(sd)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                                "cpu_model": cpu_model_name(), "os_cpu_count": os.cpu_count()}
+        try:                                           # the reference's own batch-1 shape, all threads and one thread
+            line["cpu_baseline"]["batch1_frames_per_s"] = {"all_threads": cpu_b1_sample(sd, cores), "one_thread": cpu_b1_sample(sd, 1)}
+        except Exception as e:
+            line["cpu_baseline"]["batch1_frames_per_s"] = {"error": f"{type(e).__name__}: {e}"}
     print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()
