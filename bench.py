@@ -58,6 +58,38 @@ def ncu_traffic(blocks, items_per_launch):
         return None
 
 
+def hbm_rooflines(boxes_xywh, stages, peaks, S=256, factor=4.0):
+    """The HBM-bound stages against the measured copy bandwidth (north star: achieved HBM GB/s for the crop and the head), on
+    ALGORITHMIC bytes.  Stem (crop + resize + normalise fused into conv1, conv2-4): read = the unique source bytes the
+    crops touch, 3 * min(crop_sz^2, 4 S^2) per track clipped to the image, write = the 256 x 48 fp32 search tokens.  Head + decode:
+    read = the tokens, write = (x, y, w, h, conf)."""
+    b = np.asarray(boxes_xywh, dtype=np.float64)
+    crop_sz = np.ceil(np.sqrt(b[:, 2] * b[:, 3]) * factor)
+    x1 = np.rint(b[:, 0] + 0.5 * b[:, 2] - 0.5 * crop_sz)
+    y1 = np.rint(b[:, 1] + 0.5 * b[:, 3] - 0.5 * crop_sz)
+    wx = np.clip(np.minimum(x1 + crop_sz, FRAME_W - 1) - np.maximum(x1, 0), 0, None)       # columns / rows 0 .. W-2 / H-2 are readable
+    wy = np.clip(np.minimum(y1 + crop_sz, FRAME_H - 1) - np.maximum(y1, 0), 0, None)
+    frac_in = np.where(crop_sz > 0, (wx * wy) / np.maximum(crop_sz * crop_sz, 1), 0.0)
+    src = 3.0 * np.minimum(crop_sz * crop_sz, 4.0 * S * S) * frac_in
+    tokens = 256 * 48 * 4
+    per_track = {"stem": float(src.mean()) + tokens, "head": tokens + 5 * 4}
+    out = {}
+    for k, bytes_per_track in per_track.items():
+        st = stages[k]
+        launches = max(1, st["launches"])
+        ms, items = st["ms"] / launches, st["items"] / launches
+        achieved = bytes_per_track * items / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                traffic = json.load(f)[k]["dram_bytes_per_track"] * items
+        except Exception:
+            pass
+        out[k] = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                  "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_track * items, "avg_launch_ms": ms}
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -423,6 +455,10 @@ def main():
     }
     if crop["ms"] > 0:
         line["stages"]["crop"]["note"] = "HBM-bound gather; see profiles/ for achieved GB/s"
+    try:
+        line["roofline_hbm"] = hbm_rooflines(O.synth_boxes(n, FRAME_H, FRAME_W, seed=3000 + 97 * rank), stages, peaks)
+    except Exception as e:                             # secondary figures: never at the expense of the line
+        line["roofline_hbm"] = {"error": f"{type(e).__name__}: {e}"}
 
     if world == 1 and not args.no_latency:
         line["latency_b1"] = latency_b1(cfg, sd, iters=args.latency_frames)
