@@ -470,7 +470,7 @@ def main():
             line["cpu_baseline"]["batch1_frames_per_s"] = {"all_threads": cpu_b1_sample(sd, cores), "one_thread": cpu_b1_sample(sd, 1)}
         except Exception as e:
             line["cpu_baseline"]["batch1_frames_per_s"] = {"error": f"{type(e).__name__}: {e}"}
-    print(json.dumps(line), file=_JSON_OUT, flush=True)
+    print(json.dumps(line, default=float), file=_JSON_OUT, flush=True)     # default: NumPy scalars, should one slip in
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
