@@ -42,3 +42,22 @@ def test_recorded_b200_line_has_every_contract_key():
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
     assert d["gpu_launches"] > 0 and d["warmup"] >= 3 and d["n_gpus"] == 1
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_secondary_figures_are_json_safe_and_sane():
+    """The pieces bench.py adds after the timed region (HBM rooflines of the stem and head, batch-1 CPU legs) run on the host: check them here,
+    so that a mistake in them cannot cost the GPU run its line."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import vt_oracle as O
+    stages = {k: {"ms": ms * 20, "launches": 20, "items": 1024 * 20} for k, ms in (("stem", 0.794), ("head", 0.173), ("blocks", 0.58), ("crop", 0.0))}
+    r = bench.hbm_rooflines(O.synth_boxes(1024, bench.FRAME_H, bench.FRAME_W, seed=3000), stages, bench.measured_peaks())
+    json.dumps(r)
+    for k in ("stem", "head"):
+        assert r[k]["bound"] == "hbm" and 0 < r[k]["frac"] < 1 and abs(r[k]["frac"] - r[k]["achieved"] / r[k]["peak"]) < 1e-12
+    # a 720p crop reads at most 4 S^2 pixels x 3 bytes, and the tokens are 48 KB
+    assert 49152 * 1024 < r["stem"]["algorithmic_bytes_per_launch"] <= (3 * 4 * 256 * 256 + 49152) * 1024
+    assert r["stem"]["traffic"] > r["stem"]["algorithmic_bytes_per_launch"]
+    assert isinstance(bench.cpu_model_name(), str)
+    sd = O.make_state_dict(seed=1, stress=True)
+    assert bench.cpu_b1_sample(sd, 1, budget_s=0.5) > 0
