@@ -45,6 +45,10 @@ typedef enum VtStatus {
 #define VT_TRACK_OK 0
 #define VT_TRACK_TOO_SMALL 1      /* crop_sz < 1: 'Too small bounding box.'                       */
 #define VT_TRACK_OUT_OF_DOMAIN 2  /* crop does not overlap the image: undefined in the reference  */
+#define VT_TRACK_NUMERIC_RANGE 3  /* an activation was non-finite, or left the fp16 operand range of the
+                                   * tensor-core path (|v| >= 65504; operands are fp16 hi + lo): the result is
+                                   * withheld (state kept, confidence -1, maps NaN) instead of silently wrong.
+                                   * Rerun the track with VT_BLOCKS_SIMT_FP32 (all fp32).                    */
 
 /* Which implementation of the ViT blocks vt_forward / vt_tracks_step use. */
 #define VT_BLOCKS_SIMT_FP32 0     /* fp32 CUDA-core kernel: bring-up / exact mode                 */
@@ -177,6 +181,11 @@ int64_t vt_launch_count(VtHandle h);
 #define VT_NUM_STAGES 4
 int vt_profile_enable(VtHandle h, int32_t enable);
 int vt_profile_read(VtHandle h, double* stage_ms, int64_t* stage_launches, int64_t* stage_items);
+
+/* Development aid: which profiled stage launches (vt_profile_enable) have started / finished.  Non-blocking;
+ * meant for a watchdog thread while the owning thread waits in a synchronisation (tools/hang_probe.py,
+ * tests/test_gpu_soak.py).  out[i] = stage * 4 + (started ? 1 : 0) + (finished ? 2 : 0); returns the count. */
+int vt_debug_pending(VtHandle h, int32_t* out, int32_t cap);
 
 #ifdef __cplusplus
 }

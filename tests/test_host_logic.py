@@ -113,12 +113,13 @@ for total in (8, 7, 3):
     full = sh.gather(local)
     want = torch.arange(0, total, dtype=torch.float64).unsqueeze(1) * torch.tensor([[1., 10., 100., 1000., 0.5]], dtype=torch.float64)
     assert full.shape == (total, 5) and torch.equal(full, want), (total, full)
-    if total % 2 == 0:          # overlapped form: two gathers in flight one after the other, alternating buffers
-        w1, r1 = sh.gather_async(local)
-        w1.wait()
-        w2, r2 = sh.gather_async(local * 2)
-        w2.wait()
-        assert torch.equal(r1, want) and torch.equal(r2, want * 2)
+    # overlapped form: two gathers one after the other, alternating buffers; ragged shards (7, 3) come back compacted too
+    w1, r1 = sh.gather_async(local)
+    w1.wait()
+    w2, r2 = sh.gather_async(local * 2)
+    w2.wait()
+    assert r1.shape == (total, 5) and r2.shape == (total, 5), (total, r1.shape)
+    assert torch.equal(r1, want) and torch.equal(r2, want * 2), (total, r1, r2)
 dist.barrier()
 dist.destroy_process_group()
 print("OK", os.environ["RANK"])

@@ -14,7 +14,7 @@ from . import build as _build
 VT_OK = 0
 VT_BLOCKS_SIMT_FP32 = 0
 VT_BLOCKS_TCGEN05 = 1
-VT_TRACK_OK, VT_TRACK_TOO_SMALL, VT_TRACK_OUT_OF_DOMAIN = 0, 1, 2
+VT_TRACK_OK, VT_TRACK_TOO_SMALL, VT_TRACK_OUT_OF_DOMAIN, VT_TRACK_NUMERIC_RANGE = 0, 1, 2, 3
 
 STATUS_NAMES = {0: "VT_OK", -1: "VT_ERR_INVALID_ARG", -2: "VT_ERR_CUDA", -3: "VT_ERR_WEIGHTS", -4: "VT_ERR_STATE",
                 -5: "VT_ERR_UNSUPPORTED", -6: "VT_ERR_NO_DEVICE"}
@@ -54,6 +54,7 @@ SIGNATURES = {
     "vt_launch_count": (C.c_int64, [_P]),
     "vt_profile_enable": (C.c_int, [_P, C.c_int32]),
     "vt_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "vt_debug_pending": (C.c_int, [_P, C.POINTER(C.c_int32), C.c_int32]),
 }
 
 _lib = None
@@ -70,9 +71,17 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
-        path = _build.LIB_PATH
-        if not os.path.isfile(path):
-            path = _build.build()          # raises if nvcc is unavailable
+        # always go through build(): a no-op when the stamp matches the sources and flags, a rebuild when the library is stale
+        # (an old .so after edits to csrc/ would otherwise be measured silently).  Without nvcc an existing library is used as is.
+        try:
+            path = _build.build()
+        except _build.NvccMissing:
+            path = _build.LIB_PATH
+            if not os.path.isfile(path):
+                raise
+            if not _build.is_fresh():
+                import warnings
+                warnings.warn(f"{path} is older than its sources and nvcc is unavailable: loading the stale library")
         lib = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)        # AttributeError if the .so does not export a declared symbol

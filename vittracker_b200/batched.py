@@ -128,6 +128,18 @@ class PipelinedFrameFeeder:
         self._free[i] = ev
 
 
+class _CompactingWork:
+    """``wait()`` of an asynchronous all-gather over ragged shards: waits, then gathers the valid rows into ``out``."""
+
+    def __init__(self, work, flat, index, out):
+        self.work, self.flat, self.index, self.out = work, flat, index, out
+
+    def wait(self):
+        r = self.work.wait()
+        torch.index_select(self.flat, 0, self.index, out=self.out)
+        return r
+
+
 def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous slice [lo, hi) of ``total`` tracks owned by ``rank`` (sizes differ by at most one)."""
     base, rem = divmod(total, world)
@@ -186,11 +198,20 @@ class ShardedTracker:
     def gather_async(self, local_boxes: torch.Tensor):
         """Start the gather of this step's boxes and return ``(work, result)``: the collective runs on NCCL's stream, so the
         next step's kernels are not ordered behind it (nor behind the slowest rank); call ``work.wait()`` before reading
-        ``result`` ([total, 5], valid for two calls - the buffers alternate).  At most one gather may be outstanding."""
+        ``result`` ([total, 5] ordered by global track id, valid for two calls - the buffers alternate).  At most one gather
+        may be outstanding.  With ragged shards (total % world != 0) ``work.wait()`` also drops the padding rows."""
         if self.world == 1:
             return None, local_boxes
         self._flip = getattr(self, "_flip", 0) ^ 1
         buf, send = self._buffers(self._flip, local_boxes.device, local_boxes.dtype)
         send[: self.n_local].copy_(local_boxes)
         work = self.dist.all_gather_into_tensor(buf.view(-1, 5), send, group=self.group, async_op=True)
-        return work, (buf.view(-1, 5) if self.total % self.world == 0 else buf)
+        if self.total % self.world == 0:
+            return work, buf.view(-1, 5)
+        # ragged: rows of the padded [world, max_local, 5] buffer in global-track order, compacted once the gather has landed
+        if getattr(self, "_order_idx", None) is None or self._order_idx.device != buf.device:
+            idx = [r * self.max_local + k for r in range(self.world) for k in range(shard_range(self.total, r, self.world)[1] - shard_range(self.total, r, self.world)[0])]
+            self._order_idx = torch.tensor(idx, dtype=torch.int64, device=buf.device)
+            self._ordered_out = [torch.zeros((self.total, 5), dtype=buf.dtype, device=buf.device) for _ in range(2)]
+        res = self._ordered_out[self._flip]
+        return _CompactingWork(work, buf.view(-1, 5), self._order_idx, res), res

@@ -25,11 +25,15 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-fast-math", "--fmad=true", "-I", INCLUDE]
 
 
+class NvccMissing(RuntimeError):
+    pass
+
+
 def _nvcc() -> str:
     for c in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if c and os.path.isfile(c):
             return c
-    raise RuntimeError("nvcc not found: libvittrack_b200.so cannot be built (there is no CPU fallback)")
+    raise NvccMissing("nvcc not found: libvittrack_b200.so cannot be built (there is no CPU fallback)")
 
 
 def _sources():
@@ -39,6 +43,7 @@ def _sources():
 def _digest() -> str:
     h = hashlib.sha256()
     h.update(" ".join(f for f in NVCC_FLAGS if f != INCLUDE).encode())
+    h.update(os.environ.get("NVCC_EXTRA", "").encode())
     files = sorted(os.listdir(CSRC)) + [os.path.join(INCLUDE, f) for f in sorted(os.listdir(INCLUDE))]
     for f in files:
         p = f if os.path.isabs(f) else os.path.join(CSRC, f)
@@ -62,6 +67,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     nvcc = _nvcc()
     os.makedirs(LIB_DIR, exist_ok=True)
+    # one builder at a time (torchrun starts every rank at once): the others wait on the lock and find a fresh library
+    import fcntl
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_fresh():
+                return LIB_PATH
+            return _build_locked(nvcc, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(nvcc: str, verbose: bool) -> str:
     objs = []
 
     def compile_one(src: str) -> str:

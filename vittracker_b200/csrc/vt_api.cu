@@ -14,6 +14,7 @@
 #include "vt_internal.h"
 
 using namespace vt;
+static_assert(vt::VT_TRACK_NUMERIC_RANGE_ == VT_TRACK_NUMERIC_RANGE, "status code shared with the kernels");
 
 namespace {
 
@@ -363,7 +364,8 @@ int vt_create(const VtConfig* cfg, VtHandle* out) {
     h->generic = !fast;
     h->chunk = cfg->chunk_tracks > 0 ? cfg->chunk_tracks : (fast ? 1024 : 8);
     if (h->chunk > cfg->max_tracks) h->chunk = cfg->max_tracks;
-    if (cudaSetDevice(cfg->device) != cudaSuccess) { delete h; return fail(nullptr, VT_ERR_CUDA, "cudaSetDevice failed"); }
+    DeviceGuard dg(cfg->device);                 // the caller's current device is restored on return
+    if (dg.err != cudaSuccess) { delete h; return fail(nullptr, VT_ERR_CUDA, "cudaSetDevice failed"); }
     const size_t ch = h->chunk, mt = cfg->max_tracks, Cd = cfg->embed_dim;
     cudaError_t e = cudaSuccess;
     auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
@@ -405,9 +407,8 @@ int vt_create(const VtConfig* cfg, VtHandle* out) {
 
 int vt_destroy(VtHandle h) {
     if (!h) return VT_ERR_INVALID_ARG;
-    cudaSetDevice(h->cfg.device);
-    cudaDeviceSynchronize();
-    free_all(h);
+    DeviceGuard dg(h->cfg.device);
+    free_all(h);                                 // cudaFree waits for work that still uses the allocation
     delete h;
     return VT_OK;
 }
@@ -439,7 +440,8 @@ int vt_set_tensor(VtHandle h, const char* name, const float* data_host, const in
 int vt_finalize_weights(VtHandle h, void* stream) {
     if (!h) return VT_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    VT_CUDA(h, cudaSetDevice(h->cfg.device));
+    DeviceGuard dg(h->cfg.device);
+    VT_CUDA(h, dg.err);
     if (h->generic) return finalize_generic(h, st);
     std::string missing;
     auto T = [&](const std::string& n) -> const float* {
@@ -704,7 +706,8 @@ int vt_crop_normalize(VtHandle h, const uint8_t* frames, const int64_t* frame_of
     if (!frames || !frame_offsets || !frame_hw || !boxes_xywh || !out_nchw || n < 0) return fail(h, VT_ERR_INVALID_ARG, "vt_crop_normalize: null pointer or negative n");
     if (out_size != 128 && out_size != 256) return fail(h, VT_ERR_UNSUPPORTED, "vt_crop_normalize: out_size must be 128 or 256");
     if (!(factor > 0)) return fail(h, VT_ERR_INVALID_ARG, "vt_crop_normalize: factor must be positive");
-    VT_CUDA(h, cudaSetDevice(h->cfg.device));
+    DeviceGuard dg(h->cfg.device);
+    VT_CUDA(h, dg.err);
     const int k = launch_crop_normalize(frames, frame_offsets, frame_hw, boxes_xywh, factor, out_size, n, h->mw.lut, out_nchw,
                                         out_u8_hwc, out_mask, out_resize_factor, out_status, (cudaStream_t)stream);
     if (k < 0) return fail(h, VT_ERR_CUDA, "crop kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -719,7 +722,8 @@ int vt_forward(VtHandle h, const float* z, const float* x, int32_t n, float* pre
     if (n == 0) return VT_OK;
     if (!z || !x || n < 0) return fail(h, VT_ERR_INVALID_ARG, "vt_forward: null input or negative n");
     cudaStream_t st = (cudaStream_t)stream;
-    VT_CUDA(h, cudaSetDevice(h->cfg.device));
+    DeviceGuard dg(h->cfg.device);
+    VT_CUDA(h, dg.err);
     if (h->generic) {
         const int C = h->cfg.embed_dim;
         const size_t gtap = (size_t)n * kN * C;
@@ -762,7 +766,8 @@ int vt_cal_bbox(VtHandle h, const float* score, const float* size_map, const flo
                 float* boxes, void* stream) {
     if (!h) return VT_ERR_INVALID_ARG;
     if (!score || !size_map || !offset_map || !boxes || n < 0) return fail(h, VT_ERR_INVALID_ARG, "vt_cal_bbox: null pointer or negative n");
-    VT_CUDA(h, cudaSetDevice(h->cfg.device));
+    DeviceGuard dg(h->cfg.device);
+    VT_CUDA(h, dg.err);
     const int k = launch_cal_bbox(score, size_map, offset_map, n, boxes, (cudaStream_t)stream);
     if (k < 0) return fail(h, VT_ERR_CUDA, "cal_bbox launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     h->launches += k;
@@ -777,7 +782,8 @@ int vt_tracks_init(VtHandle h, const uint8_t* frames, const int64_t* frame_offse
     if (!frames || !frame_offsets || !frame_hw || !boxes_xywh) return fail(h, VT_ERR_INVALID_ARG, "vt_tracks_init: null pointer");
     if (first < 0 || n < 0 || first + n > h->cfg.max_tracks) return fail(h, VT_ERR_INVALID_ARG, "vt_tracks_init: tracks [%d, %d) exceed max_tracks %d", first, first + n, h->cfg.max_tracks);
     cudaStream_t st = (cudaStream_t)stream;
-    VT_CUDA(h, cudaSetDevice(h->cfg.device));
+    DeviceGuard dg(h->cfg.device);
+    VT_CUDA(h, dg.err);
     for (int c0 = 0; c0 < n && h->generic; c0 += h->chunk) {
         const int m = (n - c0 < h->chunk) ? n - c0 : h->chunk;
         VT_LAUNCH(h, VT_STAGE_CROP, m, st, "vt_tracks_init/crop",
@@ -807,7 +813,8 @@ int vt_tracks_step(VtHandle h, const uint8_t* frames, const int64_t* frame_offse
     if (!frames || !frame_offsets || !frame_hw || !out_boxes) return fail(h, VT_ERR_INVALID_ARG, "vt_tracks_step: null pointer");
     if (first < 0 || n < 0 || first + n > h->cfg.max_tracks) return fail(h, VT_ERR_INVALID_ARG, "vt_tracks_step: tracks [%d, %d) exceed max_tracks %d", first, first + n, h->cfg.max_tracks);
     cudaStream_t st = (cudaStream_t)stream;
-    VT_CUDA(h, cudaSetDevice(h->cfg.device));
+    DeviceGuard dg(h->cfg.device);
+    VT_CUDA(h, dg.err);
     if (h->generic) {
         // every stage runs per chunk: crop -> stem into the chunk's token buffer, cached template tokens copied in front
         const int C = h->cfg.embed_dim;

@@ -232,12 +232,8 @@ blocks_simt_kernel(const float* __restrict__ tok_z, int z_stride_rows, const flo
 int launch_blocks_simt(const float* tok_z, int z_stride_rows, const float* tok_x, int x_stride_rows,
                        float* out, int n, const ModelW& w, float* taps, size_t tap_stride, cudaStream_t st) {
     if (n <= 0) return 0;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(blocks_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlkSmemBytes) != cudaSuccess)
-            return -1;
-        configured = true;
-    }
+    static DeviceOnce once;
+    if (!ensure_dyn_smem(once, blocks_simt_kernel, kBlkSmemBytes)) return -1;
     blocks_simt_kernel<<<n, kBlkThreads, kBlkSmemBytes, st>>>(tok_z, z_stride_rows, tok_x, x_stride_rows, out, w, taps, tap_stride);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

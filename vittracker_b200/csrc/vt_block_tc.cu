@@ -674,11 +674,8 @@ extern "C" int vt_tc_trace_read(long long* host, int* n) {
 int launch_blocks_tc(const float* tok_z, int z_stride_rows, const float* tok_x, int x_stride_rows, float* out, int n,
                      const ModelW& w, float* taps, size_t tap_stride, int num_sms, cudaStream_t st) {
     if (n <= 0) return 0;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(blocks_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) != cudaSuccess) return -1;
-        configured = true;
-    }
+    static DeviceOnce once;
+    if (!ensure_dyn_smem(once, blocks_tc_kernel, kTcSmemBytes)) return -1;
     const int grid = n < num_sms ? n : num_sms;
     blocks_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(tok_z, z_stride_rows, tok_x, x_stride_rows, out, n, w, taps, tap_stride);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;

@@ -40,21 +40,24 @@ __device__ __forceinline__ void decode_argmax(const float* m_score, const float*
 
 // One thread: forward's pred_boxes from the raw arg-max; the tracker's box from the windowed arg-max mapped back to the
 // frame, clipped, and written to out_boxes / out_detail / state.  m_size: [2][256], m_off: [2][256].
+// numeric_status: 0, or VT_TRACK_NUMERIC_RANGE when the track's activations left the representable range (result withheld).
 __device__ __forceinline__ void decode_box(const HeadArgs& a, int trk, const float* m_size, const float* m_off, float raw_max,
-                                           int raw_idx, float win_max, int win_idx) {
+                                           int raw_idx, float win_max, int win_idx, int numeric_status = 0) {
     if (a.pred_boxes) {
         float* pb = a.pred_boxes + (size_t)trk * 4;
-        pb[0] = ((float)(raw_idx & 15) + m_off[raw_idx]) / 16.f;
-        pb[1] = ((float)(raw_idx >> 4) + m_off[256 + raw_idx]) / 16.f;
-        pb[2] = m_size[raw_idx];
-        pb[3] = m_size[256 + raw_idx];
+        const float qnan = __int_as_float(0x7fc00000);
+        pb[0] = numeric_status ? qnan : ((float)(raw_idx & 15) + m_off[raw_idx]) / 16.f;
+        pb[1] = numeric_status ? qnan : ((float)(raw_idx >> 4) + m_off[256 + raw_idx]) / 16.f;
+        pb[2] = numeric_status ? qnan : m_size[raw_idx];
+        pb[3] = numeric_status ? qnan : m_size[256 + raw_idx];
     }
     if (a.state) {
         double* st = a.state + (size_t)trk * 4;
         const double sx = st[0], sy = st[1], sw = st[2], sh = st[3];
         const int H = a.frame_hw[2 * trk], W = a.frame_hw[2 * trk + 1];
         const CropGeom g = crop_geometry(sx, sy, sw, sh, a.search_factor, kSx, H, W);
-        const int status = a.status ? a.status[trk] : g.status;
+        int status = a.status ? a.status[trk] : g.status;
+        if (status == 0) status = numeric_status;
         double* ob = a.out_boxes + (size_t)trk * 5;
         double* od = a.out_detail ? a.out_detail + (size_t)trk * 8 : nullptr;
         if (status != 0) {            // the reference raises here; keep the state and flag the track

@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
             if (n >= g.N) continue;
             float v = acc[i][j] * g.alpha;
             if (g.bias) v += __ldg(g.bias + n);
-            if (g.act == ACT_RELU) v = fmaxf(v, 0.f);
+            if (g.act == ACT_RELU) v = v < 0.f ? 0.f : v;      // NaN stays NaN (fmaxf would squash it): the range guard in gen_decode_kernel relies on it
             else if (g.act == ACT_HSWISH) v = hardswish_exact(v);
             else if (g.act == ACT_GELU) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
             if (R) v += R[(size_t)(g.rmod > 0 ? m % g.rmod : m) * g.ldr + n];
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(kTcGemmThreads) gemm_tc_kernel(GemmArgs g) {
                 if (n0 + c0 + j >= g.N) break;
                 float v = __uint_as_float(r[j]) * g.alpha;
                 if (g.bias) v += __ldg(g.bias + n0 + c0 + j);
-                if (g.act == ACT_RELU) v = fmaxf(v, 0.f);
+                if (g.act == ACT_RELU) v = v < 0.f ? 0.f : v;      // NaN stays NaN (fmaxf would squash it): the range guard in gen_decode_kernel relies on it
                 else if (g.act == ACT_HSWISH) v = hardswish_exact(v);
                 else if (g.act == ACT_GELU) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
                 if (rp) v += rp[j];
@@ -245,11 +245,8 @@ bool gemm_tc_ok(const GemmArgs& g, bool nn) {
 
 template <bool NN>
 int launch_gemm_tc(const GemmArgs& g, int batch, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(gemm_tc_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcGemmSmem) != cudaSuccess) return -1;
-        configured = true;
-    }
+    static DeviceOnce once;
+    if (!ensure_dyn_smem(once, gemm_tc_kernel<NN>, kTcGemmSmem)) return -1;
     dim3 grid((g.N + kTcBN - 1) / kTcBN, (g.M + kTcBM - 1) / kTcBM, batch);
     gemm_tc_kernel<NN><<<grid, kTcGemmThreads, kTcGemmSmem, st>>>(g);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
@@ -341,7 +338,11 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ s
 }
 
 // raw conv5 outputs [n][256][5] (ctr, offset x, offset y, size w, size h) -> maps, arg-max, boxes, tracker state
-__global__ void __launch_bounds__(256) gen_decode_kernel(const float* __restrict__ raw5, HeadArgs a, const float* __restrict__ hann) {
+// Range guard: the tensor-core GEMMs take fp16 hi + lo operands, so an activation beyond fp16 range becomes inf and then inf / NaN
+// downstream.  Two chokepoints catch every such track: the final LayerNorm's output row (`ln_x`, first element: a non-finite input
+// makes the whole row NaN) for everything up to the blocks, and the raw conv5 outputs for the head (its ReLUs keep NaN).
+__global__ void __launch_bounds__(256) gen_decode_kernel(const float* __restrict__ raw5, HeadArgs a, const float* __restrict__ hann,
+                                                        const float* __restrict__ ln_x, int C) {
     __shared__ float maps[6 * 256];
     __shared__ float red[32];
     const int trk = blockIdx.x, tid = threadIdx.x;
@@ -349,15 +350,25 @@ __global__ void __launch_bounds__(256) gen_decode_kernel(const float* __restrict
     const float* r = raw5 + ((size_t)trk * 256 + tid) * 5;
     const float sc = sigmoid_clamp(r[0]), sw = sigmoid_clamp(r[3]), sh = sigmoid_clamp(r[4]);
     const float ox = r[1], oy = r[2];
+    int bad = 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) bad |= !(fabsf(r[k]) < INFINITY);
+    bad |= !(fabsf(__ldg(ln_x + ((size_t)trk * kN + kNz + tid) * C)) < INFINITY);
     m_score[tid] = sc; m_size[tid] = sw; m_size[256 + tid] = sh; m_off[tid] = ox; m_off[256 + tid] = oy;
     m_resp[tid] = __ldg(hann + tid) * sc;
     if (a.score_map) a.score_map[(size_t)trk * 256 + tid] = sc;
     if (a.size_map) { a.size_map[(size_t)trk * 512 + tid] = sw; a.size_map[(size_t)trk * 512 + 256 + tid] = sh; }
     if (a.offset_map) { a.offset_map[(size_t)trk * 512 + tid] = ox; a.offset_map[(size_t)trk * 512 + 256 + tid] = oy; }
-    __syncthreads();
+    const int any_bad = __syncthreads_or(bad);
+    if (any_bad) {                                   // never a silent wrong answer (see head_finish in vt_head.cu)
+        const float qnan = __int_as_float(0x7fc00000);
+        if (a.score_map) a.score_map[(size_t)trk * 256 + tid] = qnan;
+        if (a.size_map) { a.size_map[(size_t)trk * 512 + tid] = qnan; a.size_map[(size_t)trk * 512 + 256 + tid] = qnan; }
+        if (a.offset_map) { a.offset_map[(size_t)trk * 512 + tid] = qnan; a.offset_map[(size_t)trk * 512 + 256 + tid] = qnan; }
+    }
     float raw_max, win_max; int raw_idx, win_idx;
     decode_argmax(m_score, m_resp, red, raw_max, raw_idx, win_max, win_idx);
-    if (tid == 0) decode_box(a, trk, m_size, m_off, raw_max, raw_idx, win_max, win_idx);
+    if (tid == 0) decode_box(a, trk, m_size, m_off, raw_max, raw_idx, win_max, win_idx, any_bad ? VT_TRACK_NUMERIC_RANGE_ : 0);
 }
 
 #define GEN_TRY(expr)                      \
@@ -489,7 +500,7 @@ int gen_launch_blocks_head(float* tokens, int n, const GenModelW& w, const GenWo
             GEN_TRY(run_gemm(gemm_args(ws.t4 + t * c4, 3 * c4, w.head_w5 + (size_t)col0[t] * c4, c4, ws.raw5 + col0[t], 5, prow, outs[t], c4,
                                        w.head_b5 + col0[t], ACT_NONE), 1, false, st));
     }
-    gen_decode_kernel<<<n, 256, 0, st>>>(ws.raw5, a, w.hann);
+    gen_decode_kernel<<<n, 256, 0, st>>>(ws.raw5, a, w.hann, ws.ln, C);
     if (cudaGetLastError() != cudaSuccess) return -1;
     return total + 1;
 }

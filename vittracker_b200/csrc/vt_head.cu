@@ -148,7 +148,10 @@ __device__ __forceinline__ void head_conv(const float* in, float* outp, const fl
 }
 
 // Final LayerNorm of one token row (vit_dist.py:94); optionally stores the normalised row (tokens_norm tap).
-__device__ __forceinline__ void head_norm_row(const HeadArgs& a, const ModelW& w, int trk, int row, float (&y)[kC]) {
+// `bad` is raised when the row holds a non-finite value (an fp16-range overflow anywhere upstream on the tensor-core path ends as
+// inf / NaN in the residual stream: K / V' / q / P poison every query row of their track, the MLP its own row) or when the
+// normalised row itself would not fit the fp16 operand range.
+__device__ __forceinline__ void head_norm_row(const HeadArgs& a, const ModelW& w, int trk, int row, float (&y)[kC], int& bad) {
     const float* src = a.tokens + ((size_t)trk * kN + row) * kC;
     float x[kC];
 #pragma unroll
@@ -166,6 +169,10 @@ __device__ __forceinline__ void head_norm_row(const HeadArgs& a, const ModelW& w
     const float rstd = rsqrtf(var * (1.f / kC) + kLnEps);
 #pragma unroll
     for (int k = 0; k < kC; ++k) y[k] = (x[k] - mean) * rstd * __ldg(w.norm_g + k) + __ldg(w.norm_b + k);
+    float ymax = 0.f;
+#pragma unroll
+    for (int k = 0; k < kC; ++k) ymax = fmaxf(ymax, fabsf(y[k]));
+    bad |= (!(var < INFINITY) ? 1 : 0) | (!(ymax < kF16Max) ? 2 : 0);     // bit 0: non-finite input, bit 1: fp16 operand range (NaN compares false)
     if (a.tokens_norm) {
         float* t = a.tokens_norm + ((size_t)trk * kN + row) * kC;
 #pragma unroll
@@ -176,7 +183,7 @@ __device__ __forceinline__ void head_norm_row(const HeadArgs& a, const ModelW& w
 // conv5 (1x1) + sigmoid/clamp, raw and Hann-weighted arg-max, box decode, state update (thread = pixel).
 // out4: [3 towers][4][324] zero-bordered planes; sb: bias block (w5 at +180, b5 at +204).
 __device__ __forceinline__ void head_finish(const HeadArgs& a, const ModelW& w, int trk, const float* out4, const float* sb,
-                                            float* maps, float* red, uint32_t tmem_to_free) {
+                                            float* maps, float* red, uint32_t tmem_to_free, int bad) {
     const int tid = threadIdx.x;
     HEAD_TRACE(5);
     // ---- conv5 (1x1) + sigmoid/clamp: thread = pixel ---------------------------------------------
@@ -205,7 +212,15 @@ __device__ __forceinline__ void head_finish(const HeadArgs& a, const ModelW& w, 
         if (a.size_map) { a.size_map[(size_t)trk * 512 + tid] = sw; a.size_map[(size_t)trk * 512 + 256 + tid] = sh; }
         if (a.offset_map) { a.offset_map[(size_t)trk * 512 + tid] = o[1][0]; a.offset_map[(size_t)trk * 512 + 256 + tid] = o[1][1]; }
     }
-    __syncthreads();
+    const int any_bad = __syncthreads_or(bad);
+    if (any_bad) {
+        // never a silent wrong answer: the maps of a track whose activations left the representable range are NaN (ReLU and the
+        // sigmoid would otherwise squash inf / NaN into plausible numbers), and the tracker output carries VT_TRACK_NUMERIC_RANGE
+        const float qnan = __int_as_float(0x7fc00000);
+        if (a.score_map) a.score_map[(size_t)trk * 256 + tid] = qnan;
+        if (a.size_map) { a.size_map[(size_t)trk * 512 + tid] = qnan; a.size_map[(size_t)trk * 512 + 256 + tid] = qnan; }
+        if (a.offset_map) { a.offset_map[(size_t)trk * 512 + tid] = qnan; a.offset_map[(size_t)trk * 512 + 256 + tid] = qnan; }
+    }
 
     // ---- cal_bbox on the raw score (forward's pred_boxes) and on the windowed response (tracker) ----
     float raw_max, win_max; int raw_idx, win_idx;
@@ -213,7 +228,7 @@ __device__ __forceinline__ void head_finish(const HeadArgs& a, const ModelW& w, 
     HEAD_TRACE(6);
     if (tmem_to_free != 0xffffffffu && tid < 32) tc::tmem_dealloc(tmem_to_free, 512);     // all TMEM reads ended before the barriers above
     if (tid != 0) return;
-    decode_box(a, trk, m_size, m_off, raw_max, raw_idx, win_max, win_idx);
+    decode_box(a, trk, m_size, m_off, raw_max, raw_idx, win_max, win_idx, any_bad ? VT_TRACK_NUMERIC_RANGE_ : 0);
 }
 
 __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(HeadArgs a, ModelW w) {
@@ -226,6 +241,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(HeadArgs a, Model
     float* red = smem + kOffRed;
     const int trk = blockIdx.x;
     const int tid = threadIdx.x;
+    int bad = 0;
 
     HEAD_TRACE(0);
     // zero the activation planes once: layer outputs only ever write interiors, borders stay zero
@@ -241,11 +257,13 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(HeadArgs a, Model
     // ---- final LayerNorm (vit_dist.py:94) on search token `tid`; tokens -> (C,16,16) (vit_dist.py:126-129)
     {
         float y[kC];
-        head_norm_row(a, w, trk, kNz + tid, y);
+        int flags = 0, unused = 0;
+        head_norm_row(a, w, trk, kNz + tid, y, flags);
+        bad = flags & 1;                             // fp32 path: only non-finite inputs are flagged
         const int py = tid >> 4, px = tid & 15;
 #pragma unroll
         for (int k = 0; k < kC; ++k) feat[k * kPlane + (py + 1) * 18 + px + 1] = y[k];
-        if (a.tokens_norm && tid < kNz) { float yz[kC]; head_norm_row(a, w, trk, tid, yz); }
+        if (a.tokens_norm && tid < kNz) { float yz[kC]; head_norm_row(a, w, trk, tid, yz, unused); }
     }
     __syncthreads();
 
@@ -262,7 +280,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(HeadArgs a, Model
     float* out4 = out1 + 24 * kPlane;                                              // [3][4] planes
     head_conv<8, 4, 3, true, 8>(out3, out4, w.head.w4, sb + 168, wbuf);            // 8 -> 4
 
-    head_finish(a, w, trk, out4, sb, maps, red, 0xffffffffu);
+    head_finish(a, w, trk, out4, sb, maps, red, 0xffffffffu, bad);
 }
 
 // Tensor-core head: conv1 (48 -> 96 merged) and conv2 (32 -> 16 per tower) on tcgen05, conv3-5 on CUDA cores.
@@ -284,6 +302,8 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
     const int trk = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int py = tid >> 4, px = tid & 15;
+    int bad = 0;                 // fp16 operand range guard (see head_norm_row); OR-reduced over the CTA in head_finish
+    float vmax = 0.f;            // largest value this thread hands to a tensor-core operand image
 
     HEAD_TRACE(0);
     // zero rows 0 and 17 of every chunk image (the vertical zero padding of both tensor-core convolutions)
@@ -318,7 +338,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
     // ---- final LayerNorm -> conv1's operand image (fp16 hi | lo, 8-channel chunks) ----------------------------------
     {
         float y[kC];
-        head_norm_row(a, w, trk, kNz + tid, y);
+        head_norm_row(a, w, trk, kNz + tid, y, bad);
         uint8_t* ab = sm8 + kT_R0 + ((py + 1) * 16 + px) * 16;
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
@@ -328,7 +348,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
             *reinterpret_cast<uint4*>(ab + c * kTcAChunk) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             *reinterpret_cast<uint4*>(ab + (6 + c) * kTcAChunk) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
-        if (a.tokens_norm && tid < kNz) { float yz[kC]; head_norm_row(a, w, trk, tid, yz); }
+        if (a.tokens_norm && tid < kNz) { float yz[kC]; int unused = 0; head_norm_row(a, w, trk, tid, yz, unused); }
     }
     tc::fence_async_smem();
     tc::tc_fence_before();
@@ -404,6 +424,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
                         if (px == 0) t0 = 0.f;
                         if (px == 15) t2 = 0.f;
                         v[j] = fmaxf((t0 + __uint_as_float(r1[j])) + t2 + sb[h * 48 + c0 + j], 0.f);
+                        vmax = fmaxf(vmax, v[j]);
                     }
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
@@ -474,6 +495,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
                 if (px == 0) t0 = 0.f;
                 if (px == 15) t2 = 0.f;
                 v[j] = fmaxf((t0 + __uint_as_float(r1[j])) + t2 + sb[96 + tw * 16 + j], 0.f);
+                vmax = fmaxf(vmax, v[j]);
             }
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -538,17 +560,14 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
     __syncthreads();
     HEAD_TRACE(4);
     head_conv<8, 4, 3, true, 8>(out3, out4, w.head.w4, sb + 168, wbuf);            // 8 -> 4
-    head_finish(a, w, trk, out4, sb, maps, red, tbase);
+    bad |= !(vmax < kF16Max);
+    head_finish(a, w, trk, out4, sb, maps, red, tbase, bad);
 }
 
 int launch_head(const HeadArgs& a, const ModelW& w, cudaStream_t st) {
     if (a.n <= 0) return 0;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmemBytes) != cudaSuccess) return -1;
-        if (cudaFuncSetAttribute(head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadTcSmemBytes) != cudaSuccess) return -1;
-        configured = true;
-    }
+    static DeviceOnce once_simt, once_tc;
+    if (!ensure_dyn_smem(once_simt, head_kernel, kHeadSmemBytes) || !ensure_dyn_smem(once_tc, head_tc_kernel, kHeadTcSmemBytes)) return -1;
     if (a.use_tc) head_tc_kernel<<<a.n, kHeadThreads, kHeadTcSmemBytes, st>>>(a, w);
     else head_kernel<<<a.n, kHeadThreads, kHeadSmemBytes, st>>>(a, w);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;

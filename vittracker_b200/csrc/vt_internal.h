@@ -17,6 +17,8 @@ constexpr int kHeadC = 32;      // head tower width
 constexpr int kTz = 128;        // template crop side
 constexpr int kSx = 256;        // search crop side
 constexpr float kLnEps = 1e-5f;
+constexpr float kF16Max = 65504.f;           // largest finite fp16: operands of the tensor-core path are fp16 hi + lo
+constexpr int VT_TRACK_NUMERIC_RANGE_ = 3;    // == VT_TRACK_NUMERIC_RANGE of include/vittrack_b200.h
 
 #ifdef __CUDACC__
 // Hardswish exactly as PyTorch evaluates it, x * relu6(x + 3) / 6 (vit_dist.py:41, torch.nn.Hardswish): the product is rounded to fp32 and
@@ -135,6 +137,45 @@ __host__ __device__ inline size_t tc_planes_offset(int prec, int gy, int gx, int
 constexpr int kConv2Cch = 1, kConv2Wout = 64;     // conv2 input:  6 channels -> 1 chunk, 128x128 -> planes of 65 x 64
 constexpr int kConv3Cch = 2, kConv3Wout = 32;     // conv3 input: 12 channels -> 2 chunks, 64x64 -> planes of 33 x 32
 constexpr int kConv4Cch = 3, kConv4Wout = 16;     // conv4 input: 24 channels -> 3 chunks, 32x32 -> planes of 17 x 16
+
+// ---- per-device one-off kernel configuration ------------------------------------------------------
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device only, and one process may hold handles on
+// several GPUs (VtConfig.device): every launcher keeps one flag per device ordinal instead of one per process.
+constexpr int kMaxDevices = 64;
+struct DeviceOnce {
+    bool done[kMaxDevices] = {};
+    // returns the current device ordinal if its flag is still clear (the caller configures, then calls set()), -1 if already
+    // configured, -2 on a CUDA error; ordinals beyond the table are configured on every launch
+    int pending() const {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return -2;
+        return (dev >= 0 && dev < kMaxDevices && done[dev]) ? -1 : dev;
+    }
+    void set(int dev) { if (dev >= 0 && dev < kMaxDevices) done[dev] = true; }
+};
+template <typename Kern>
+inline bool ensure_dyn_smem(DeviceOnce& once, Kern kern, size_t bytes) {
+    const int dev = once.pending();
+    if (dev == -1) return true;
+    if (dev == -2) return false;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return false;
+    once.set(dev);
+    return true;
+}
+
+// RAII: make `device` current for the duration of a C-ABI call and restore the caller's device afterwards (the host
+// language's runtime - PyTorch - keeps its own notion of the current device).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) err = cudaSetDevice(device); else if (err == cudaSuccess) prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 // ---- kernel launchers (each returns the number of kernels it launched, or <0 on a CUDA error) -----
 int launch_crop_normalize(const uint8_t* frames, const int64_t* frame_offsets, const int32_t* frame_hw,

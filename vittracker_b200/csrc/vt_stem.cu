@@ -512,11 +512,8 @@ static int run_conv(const float* in, int Hin, int n, const StemLayerW& w, float*
                     int tok_stride_rows, int tok_off, cudaStream_t st) {
     using K = ConvCfg<CIN, COUT, QG, P, TW, TH>;
     auto kern = conv3x3s2_kernel<CIN, COUT, QG, P, TW, TH, HSWISH, TOKENS, TCOUT_CCH>;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::kSmemBytes) != cudaSuccess) return -1;
-        configured = true;
-    }
+    static DeviceOnce once;
+    if (!ensure_dyn_smem(once, kern, K::kSmemBytes)) return -1;
     const int Hout = Hin / 2;
     const int tiles = ((Hout + TW - 1) / TW) * ((Hout + TH - 1) / TH);
     int launched = 0;
@@ -543,11 +540,8 @@ template <int S, int TCOUT_CCH>
 static int run_crop_conv1(const uint8_t* frames, const int64_t* frame_offsets, const int32_t* frame_hw, const double* boxes,
                           double factor, int n, const ModelW& w, float* out, int32_t* out_status, int4* taps, cudaStream_t st) {
     auto kern = crop_conv1_kernel<S, TCOUT_CCH>;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCc1SmemBytes) != cudaSuccess) return -1;
-        configured = true;
-    }
+    static DeviceOnce once;
+    if (!ensure_dyn_smem(once, kern, kCc1SmemBytes)) return -1;
     constexpr int tiles = (S / 64) * (S / 64);
     crop_taps_kernel<S><<<n, 288, 0, st>>>(frame_hw, boxes, factor, taps, out_status);
     int launched = 1;

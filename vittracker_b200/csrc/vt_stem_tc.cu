@@ -283,15 +283,18 @@ static int run_tc_conv(const uint8_t* in, int n, const uint8_t* wt, const float*
                        int tok_stride_rows, int tok_off, cudaStream_t st) {
     using K = TcConv<CCH, COUT, NPAD, WOUT, BR>;
     auto kern = conv_s2_tc_kernel<CCH, COUT, NPAD, WOUT, BR, HSWISH, OUT_PLANES, NEXT_CCH>;
-    static int grid_cap = 0;
-    if (grid_cap == 0) {
+    static int grid_caps[kMaxDevices] = {};                          // per device ordinal: the opt-in and the SM count are per device
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+    if (grid_caps[dev] == 0) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::kSmemBytes) != cudaSuccess) return -1;
-        int dev = 0, sms = 0, per_sm = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+        int sms = 0, per_sm = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K::kThreads, K::kSmemBytes) != cudaSuccess || per_sm < 1) return -1;
         const int tmem_limit = 512 / K::kTmemCols;                  // resident CTAs also share the SM's 512 TMEM columns
-        grid_cap = sms * (per_sm < tmem_limit ? per_sm : tmem_limit);
+        grid_caps[dev] = sms * (per_sm < tmem_limit ? per_sm : tmem_limit);
     }
+    const int grid_cap = grid_caps[dev];
     const long long items = (long long)n * (WOUT / K::kBR);
     if (items > 0x7fffffffLL) return -1;
     const int grid = items < grid_cap ? (int)items : grid_cap;

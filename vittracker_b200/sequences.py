@@ -258,9 +258,18 @@ class MultiSequenceRunner:
             active = [i for i in active if self.slots[i].seq is not None]      # minus the sequences whose frame could not be read
             self._prefetch_next(active)                                        # decode step t + 1 while the device runs step t
             boxes = self.backend.step(images)
-            dt = time.time() - t0
+            # `time`: the reference records the wall time of one sequence's track() call (tracker.py:139-146); a batched step
+            # advances every running sequence at once, so each is charged its share of the step - sum(time) over all sequences
+            # is the wall time spent tracking, and the printed FPS is this sequence's share of the batched throughput
+            dt = (time.time() - t0) / max(1, len(active))
             for i in active:
                 slot = self.slots[i]
+                if boxes[i, 4] < 0:
+                    # per-track failure flagged by vt_tracks_step (confidence -1, state kept: crop too small / outside the image /
+                    # numeric range): the reference's track() would have raised and run_sequence dropped the sequence (running.py:135-142)
+                    print(f"{slot.seq.name}: tracking failed at frame {slot.next_frame} (track status != 0), sequence dropped")
+                    self._drop(slot)
+                    continue
                 slot.output["target_bbox"].append([float(v) for v in boxes[i, :4]])
                 slot.output["time"].append(dt)
                 slot.next_frame += 1

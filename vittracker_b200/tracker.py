@@ -122,6 +122,11 @@ class Vit_dist(BaseTracker):
         self._upload(image, box, self.params.template_factor)
         self._set_box(box)
         status = self.engine.tracks_init(self._frame_dev, self._off_dev, self._hw_dev, self._box_dev, first=0)
+        # the reference keeps the uint8 template crop (vit_dist.py:55-57, self.z_patch_arr); the crop runs now (the frame buffer is
+        # reused by the next frame), the device -> host copy only when the attribute is read
+        self._z_patch_dev = self.engine.crop_normalize(self._frame_dev, self._off_dev, self._hw_dev, self._box_dev,
+                                                       self.params.template_factor, self.params.template_size, want_u8=True)["u8"]
+        self._z_patch_arr = None
         st = int(status.item())
         if st == 1:
             raise Exception('Too small bounding box.')
@@ -130,6 +135,15 @@ class Vit_dist(BaseTracker):
         self.state = info['init_bbox']
         self.frame_id = 0
         return None
+
+    @property
+    def z_patch_arr(self) -> np.ndarray:
+        """uint8 [template_size, template_size, 3] template crop, as ``sample_target`` returned it (vit_dist.py:55-57)."""
+        if self._z_patch_arr is None:
+            if getattr(self, "_z_patch_dev", None) is None:
+                raise AttributeError("z_patch_arr is set by initialize()")
+            self._z_patch_arr = self._z_patch_dev[0].cpu().numpy()
+        return self._z_patch_arr
 
     def track(self, image, info: dict = None):
         self.frame_id += 1
@@ -140,16 +154,21 @@ class Vit_dist(BaseTracker):
         self.engine.tracks_step(self._frame_dev, self._off_dev, self._hw_dev, first=0, n=1, out_boxes=self._out_boxes,
                                 out_detail=self._out_detail, update_state=False, detail=True)
         self._out_pin.copy_(self._out_dev, non_blocking=True)
+        # `confidence` is a 0-dim tensor on the model's device, as the reference's `score_map.max()` is (vit_dist.py:147-148)
+        confidence = self._out_dev[4].to(torch.float32)
         torch.cuda.current_stream(self._dev).synchronize()
         out = self._out_pin.tolist()
         if int(out[11]) == 1:
             raise Exception('Too small bounding box.')
+        if int(out[11]) == 3:
+            raise FloatingPointError("an activation left the fp16 operand range of the tensor-core path (or was non-finite): result "
+                                     "withheld; construct the tracker with params.blocks_impl = 'simt' for these weights")
         if int(out[11]) != 0:
             raise ValueError("search crop lies outside the image (undefined behaviour in the reference)")
         pred_box = out[5:9]                                      # (cx, cy, w, h) as `.tolist()` of the fp32 tensor
         self.state = clip_box(self.map_box_back(pred_box, resize_factor), H, W, margin=10)
         self.last_detail = {"argmax": int(out[10]), "resize_factor": out[9], "window_max": out[12], "device_box": out[0:4]}
-        return {"target_bbox": self.state, "confidence": torch.tensor(out[4], dtype=torch.float32)}
+        return {"target_bbox": self.state, "confidence": confidence}
 
     def map_box_back(self, pred_box: list, resize_factor: float):
         """lib/test/tracker/vit_dist.py:150-156."""
