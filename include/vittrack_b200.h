@@ -151,7 +151,10 @@ int vt_tracks_init(VtHandle h, const uint8_t* frames, const int64_t* frame_offse
  *   out_detail [n][8] float64 or NULL: pred cx, cy, w, h (the fp32 `pred_box` of vit_dist.py:
  *              108-109 before map_box_back), resize_factor, arg-max index of the windowed
  *              response, VT_TRACK_* status, windowed maximum
- *   update_state != 0 writes the new box back as the track state (closed loop). */
+ *   update_state != 0 writes the new box back as the track state (closed loop).
+ * Of a track's frame only rows [max(0, y1), min(H, y1 + crop_sz)) are read (crop_sz = ceil(sqrt(w h) search_factor),
+ * y1 = round(y + h/2 - crop_sz/2) of its current state): a caller may upload just those rows, and frame_offsets[i]
+ * may point before its buffer as long as the rows that are read lie inside it. */
 int vt_tracks_step(VtHandle h, const uint8_t* frames, const int64_t* frame_offsets,
                    const int32_t* frame_hw, int32_t first, int32_t n, double* out_boxes,
                    double* out_detail, int32_t update_state, void* stream);

@@ -353,6 +353,11 @@ class OracleModel:
         self.C = self.sd["pos_embed_x"].shape[-1]
         self.feat_sz = FEAT_SZ
 
+    def to(self, device) -> "OracleModel":
+        """Move the parameters (bench.py's `gpu_eager` baseline leg: the same stock torch ops, dispatched to the GPU)."""
+        self.sd = {k: v.to(device) for k, v in self.sd.items()}
+        return self
+
     # -- R7: LevitPatchEmbedding (vit_dist.py:36-54) ------------------------------------------
     def patch_embed(self, img: torch.Tensor, taps: Optional[dict] = None, tag: str = "") -> torch.Tensor:
         x = img

@@ -54,7 +54,9 @@ def test_secondary_figures_are_json_safe_and_sane():
     r = bench.hbm_rooflines(O.synth_boxes(1024, bench.FRAME_H, bench.FRAME_W, seed=3000), stages, bench.measured_peaks())
     json.dumps(r)
     for k in ("stem", "head"):
-        assert r[k]["bound"] == "hbm" and 0 < r[k]["frac"] < 1 and abs(r[k]["frac"] - r[k]["achieved"] / r[k]["peak"]) < 1e-12
+        assert 0 < r[k]["frac"] < 1 and abs(r[k]["frac"] - r[k]["achieved"] / r[k]["peak"]) < 1e-12
+    assert r["stem"]["bound"] == "hbm" and r["stem"]["unit"] == "GB/s"
+    assert r["head"]["bound"] == "tensor" and r["head"]["unit"] == "TFLOP/s" and 0 < r["head"]["hbm_frac"] < 1      # latency-bound: labelled as such
     # a 720p crop reads at most 4 S^2 pixels x 3 bytes, and the tokens are 48 KB
     assert 49152 * 1024 < r["stem"]["algorithmic_bytes_per_launch"] <= (3 * 4 * 256 * 256 + 49152) * 1024
     assert r["stem"]["traffic"] > r["stem"]["algorithmic_bytes_per_launch"]

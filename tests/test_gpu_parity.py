@@ -279,18 +279,22 @@ def test_batched_open_loop_argmax_and_boxes_against_oracle(cfg, blocks, n):
     assert close(maps["score_map"][5].flatten().cpu().numpy(), want[5]["score"], atol=1e-4)
 
 
-def test_argmax_bit_exact_on_10k_frames():
-    """North-star gate: Hann-weighted arg-max index identical to the reference algorithm on 10 240 synthetic frames
-    (ties = oracle top-1 - top-2 < 1e-5 excepted and counted), decoded boxes within 1e-2 abs / 1e-3 rel."""
+@pytest.mark.parametrize("weights,n", [("default", 3414), ("stress1", 3413), ("stress2", 3413)])
+def test_argmax_bit_exact_on_10k_frames(weights, n):
+    """North-star gate on the benchmarked workload shape: Hann-weighted arg-max index identical to the reference algorithm on
+    10 240 synthetic 720 x 1280 frames (64 distinct, half smooth / half white noise) split over three weight sets - default-init
+    and two stress-init seeds - ties (oracle top-1 - top-2 < 1e-5) excepted and counted, decoded boxes within 1e-2 abs / 1e-3 rel.
+    (tools/argmax_parity.py runs 10 240 frames per weight set; its records are under profiles/.)"""
     import os
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     import argmax_parity
     torch.set_num_threads(os.cpu_count() or 1)
-    res = argmax_parity.run(n=10240, blocks="tcgen05")
+    res = argmax_parity.run(n=n, blocks="tcgen05", weights=weights)
     print(res)
     assert res["argmax_flips"] == 0, res
     assert res["boxes_outside_tolerance"] == 0, res
+    assert res["status_nonzero"] == 0, res
     assert res["ties_excluded"] < 0.01 * res["frames"], res
 
 

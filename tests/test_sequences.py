@@ -119,6 +119,31 @@ def test_threaded_frame_ingest_from_image_files(tmp_path):
     assert [e[3] for e in be.log if e[0] == "frame" and e[2] == 2] == [1, 2, 3]
 
 
+def test_crop_rows_cover_what_sample_target_reads():
+    """Row staging uploads rows [ya, yb) of a frame: exactly the slice sample_target takes (processing_utils.py:34-48)."""
+    from oracle import vt_oracle as O
+    from vittracker_b200.sequences import crop_rows
+    H, W = 240, 320
+    rng = np.random.default_rng(3)
+    im = rng.integers(1, 255, size=(H, W, 3), dtype=np.uint8)
+    for _ in range(300):
+        w, h = rng.uniform(2, 200), rng.uniform(2, 200)
+        box = [rng.uniform(-20, W), rng.uniform(-40, H + 20), w, h]
+        if rng.random() < 0.2:
+            box = [float(round(v)) for v in box]                      # .5 rounding cases
+        r = crop_rows(box, 4.0, H)
+        if not O.crop_in_domain(box, 4.0, H, W):
+            continue
+        assert r is not None
+        ya, yb = r
+        masked = np.zeros_like(im)
+        masked[ya:yb] = im[ya:yb]                                     # rows outside the ROI never matter
+        a = O.sample_target_cv(im, box, 4.0, 256)[0]
+        b = O.sample_target_cv(masked, box, 4.0, 256)[0]
+        assert np.array_equal(a, b), (box, r)
+    assert crop_rows([10, 10, 0, 0], 4.0, H) is None
+
+
 def test_save_tracker_output_truncates_like_astype_int(tmp_path):
     s = Sequence("q", _frames(2, 0), [1, 2, 3, 4])
     save_tracker_output(str(tmp_path), s, {"target_bbox": [[1.9, 2.1, 3.999, 4.5], [10.2, -0.5, 7.7, 8.0]], "time": [0.25, 0.5]})

@@ -371,7 +371,10 @@ crop_taps_kernel(const int32_t* __restrict__ frame_hw, const double* __restrict_
     const double scale = s_scale;
     if (tid > S) return;
     const int d = tid - 1;
-    int4 tc = make_int4(0, 0, 0, 1), tr = make_int4(0, 0, 0, 1);
+    // Padding rows are read with weight 0 (branch-free gather); they read the crop's first in-image row rather than row 0 of the frame, so
+    // that a track never touches frame rows outside [max(0, y1), min(H, y1 + crop_sz)) - callers may upload only those rows.
+    const int anchor = g.status == 0 ? min(max(g.y1, 0), max(H - 2, 0)) * W * 3 : 0;
+    int4 tc = make_int4(0, 0, 0, 1), tr = make_int4(anchor, anchor, 0, 1);
     if (d >= 0 && g.status == 0) {
         {
             int s0, s1, a0, a1; bool w0, w1;
@@ -388,7 +391,7 @@ crop_taps_kernel(const int32_t* __restrict__ frame_hw, const double* __restrict_
             tap_y(d, scale, g.crop_sz, r0, r1, b0, b1, w0, w1);
             const int iy0 = g.y1 + r0, iy1 = g.y1 + r1;
             const bool v0 = iy0 >= 0 && iy0 <= H - 2, v1 = iy1 >= 0 && iy1 <= H - 2;
-            tr = make_int4(v0 ? iy0 * W * 3 : 0, v1 ? iy1 * W * 3 : 0, (v0 ? b0 : 0) | ((v1 ? b1 : 0) << 16), 0);
+            tr = make_int4(v0 ? iy0 * W * 3 : anchor, v1 ? iy1 * W * 3 : anchor, (v0 ? b0 : 0) | ((v1 ? b1 : 0) << 16), 0);
         }
     }
     taps[((size_t)item * 2 + 0) * kTapPitch + tid] = tc;

@@ -10,6 +10,7 @@ with the init box as entry 0 - and ``save_tracker_output`` writes the same ``<se
 (running.py:14-102), so the analysis tooling reads them unchanged."""
 from __future__ import annotations
 
+import math
 import os
 import time
 from concurrent.futures import Future, ThreadPoolExecutor
@@ -75,44 +76,92 @@ class _Slot:
         self.prefetch_idx = -1
 
 
+def crop_rows(box, factor: float, H: int) -> Optional[tuple]:
+    """Rows [ya, yb) of an H-row frame that sample_target(im, box, factor, .) can read (processing_utils.py:30-48: crop_sz =
+    ceil(sqrt(w h) factor), y1 = round(y + h/2 - crop_sz/2) with Python's round); None when the crop is degenerate."""
+    x, y, w, h = [float(v) for v in box]
+    if not (w * h >= 0):
+        return None
+    crop_sz = math.ceil(math.sqrt(w * h) * factor)
+    if crop_sz < 1:
+        return None
+    y1 = round(y + 0.5 * h - crop_sz * 0.5)
+    ya, yb = max(0, y1), min(H, y1 + crop_sz)
+    return (ya, yb) if yb > ya else None
+
+
 class BatchedBackend:
     """The device side of the driver: per-slot initialise, one step for a prefix of slots.  Split from the scheduler so
-    that the scheduling logic is testable without a GPU."""
+    that the scheduling logic is testable without a GPU.
 
-    def __init__(self, cfg, state_dict, slots: int, device: Optional[int] = None, blocks_impl: str = "tcgen05"):
+    Uploads are ROW-STAGED like the batch-1 tracker's (tracker.py `_upload`): a step sends, per slot, only the frame rows its search
+    crop can read (the state is known on the host: it is what the previous step returned), packed back to back in one pinned buffer
+    and moved with one copy.  The kernels address a frame by a byte offset, so a slot's offset simply points `ya` rows BEFORE its
+    packed rows - rows outside [ya, yb) are never read.  Packing runs on a small thread pool (NumPy copies release the GIL)."""
+
+    _PAD = 256           # bytes between packed regions: the gather reads aligned words around a tap (< 16 bytes past a row's end)
+
+    def __init__(self, cfg, state_dict, slots: int, device: Optional[int] = None, blocks_impl: str = "tcgen05", stage_workers: int = 8,
+                 row_staging: bool = True):
         import torch
         from .batched import BatchedTracker
         self.torch = torch
         self.bt = BatchedTracker(cfg, state_dict, max_tracks=slots, device=device, blocks_impl=blocks_impl)
         self.dev = self.bt.device
         self.slots = slots
+        self.search_factor = float(cfg.TEST.SEARCH_FACTOR)
+        self.row_staging = row_staging
         self._cap = 0
         self._pin = None
         self._devbuf = None
         self._hw = torch.zeros((slots, 2), dtype=torch.int32)
         self._off = torch.zeros((slots,), dtype=torch.int64)
         self._out_pin = torch.zeros((slots, 5), dtype=torch.float64).pin_memory()
+        self._state: List[Optional[list]] = [None] * slots          # host copy of every slot's box (what the device holds)
+        self._pool = ThreadPoolExecutor(max_workers=stage_workers, thread_name_prefix="vt-stage") if stage_workers > 0 else None
+        self.bytes_uploaded = 0
         # idle slots keep tracking a small black frame so that a step can always cover a contiguous slot range
         self._dummy = np.zeros((64, 64, 3), dtype=np.uint8)
         self._dummy_box = [24.0, 24.0, 16.0, 16.0]
 
-    def _stage(self, frames: List[np.ndarray]):
-        """Pack the frames into one pinned buffer, upload with one copy; returns per-frame byte offsets."""
+    def _stage(self, frames: List[np.ndarray], rois: Optional[List[Optional[tuple]]] = None):
+        """Pack the frames (or, with `rois`, the rows [ya, yb) of each) into one pinned buffer, upload with one copy; returns per-frame
+        byte offsets of the (virtual) frame starts inside the device buffer."""
         torch = self.torch
-        sizes = [f.size for f in frames]
-        total = int(sum(sizes))
+        spans = []
+        o = self._PAD
+        for i, f in enumerate(frames):
+            H, W = f.shape[0], f.shape[1]
+            ya, yb = (0, H) if rois is None or rois[i] is None else rois[i]
+            nbytes = (yb - ya) * W * 3
+            spans.append((o, ya, yb, nbytes))
+            o += (nbytes + self._PAD + 15) // 16 * 16
+        total = o
         if total > self._cap:
             self._cap = int(total * 1.25) + 1024
             self._pin = torch.empty((self._cap,), dtype=torch.uint8).pin_memory()
             self._devbuf = torch.empty((self._cap,), dtype=torch.uint8, device=self.dev)
-        offs, o = [], 0
+            self._devbuf.zero_()
         pin = self._pin.numpy()
-        for f, n in zip(frames, sizes):
-            pin[o:o + n] = np.ascontiguousarray(f).reshape(-1)
-            offs.append(o)
-            o += n
+
+        def pack(i):
+            o, ya, yb, nbytes = spans[i]
+            pin[o:o + nbytes] = np.ascontiguousarray(frames[i][ya:yb]).reshape(-1)
+
+        if self._pool is not None and len(frames) > 1:
+            list(self._pool.map(pack, range(len(frames))))
+        else:
+            for i in range(len(frames)):
+                pack(i)
         self._devbuf[:total].copy_(self._pin[:total], non_blocking=True)
-        return offs
+        self.bytes_uploaded += total
+        # virtual frame start: `ya` rows before the packed rows (never dereferenced outside [ya, yb)); may be negative
+        return [o - ya * frames[i].shape[1] * 3 for i, (o, ya, yb, _) in enumerate(spans)]
+
+    def close(self) -> None:
+        if self._pool is not None:
+            self._pool.shutdown(wait=False)
+            self._pool = None
 
     def initialize(self, slot: int, image: np.ndarray, box) -> None:
         torch = self.torch
@@ -128,6 +177,7 @@ class BatchedBackend:
             raise Exception("Too small bounding box.")                 # processing_utils.py:32-33
         if code != 0:
             raise ValueError("crop lies outside the image (undefined in the reference)")
+        self._state[slot] = [float(v) for v in box]
 
     def park(self, slot: int) -> None:
         """Give an idle slot a valid template / state on the dummy frame."""
@@ -138,7 +188,10 @@ class BatchedBackend:
         torch = self.torch
         n = len(images)
         frames = [self._dummy if im is None else im for im in images]
-        offs = self._stage(frames)
+        rois = None
+        if self.row_staging:
+            rois = [crop_rows(self._state[i], self.search_factor, f.shape[0]) if self._state[i] is not None else None for i, f in enumerate(frames)]
+        offs = self._stage(frames, rois)
         for i, f in enumerate(frames):
             self._hw[i, 0], self._hw[i, 1] = f.shape[0], f.shape[1]
             self._off[i] = offs[i]
@@ -147,7 +200,11 @@ class BatchedBackend:
         out = self.bt.engine.tracks_step(self._devbuf, off, hw, first=0, n=n, update_state=True)
         self._out_pin[:n].copy_(out, non_blocking=True)
         torch.cuda.current_stream(self.dev).synchronize()
-        return self._out_pin[:n].numpy().copy()
+        res = self._out_pin[:n].numpy().copy()
+        for i in range(n):
+            if res[i, 4] >= 0:                                         # a flagged track keeps its state on the device too
+                self._state[i] = res[i, :4].tolist()
+        return res
 
 
 class MultiSequenceRunner:
@@ -279,12 +336,13 @@ class MultiSequenceRunner:
 
 
 def run_sequences(sequences: Seq[Sequence], cfg, state_dict, slots: int = 64, results_dir: Optional[str] = None,
-                  device: Optional[int] = None, blocks_impl: str = "tcgen05", **kw) -> Dict[str, dict]:
+                  device: Optional[int] = None, blocks_impl: str = "tcgen05", row_staging: bool = True, **kw) -> Dict[str, dict]:
     """Track every sequence; ``slots`` run concurrently on one GPU."""
     slots = max(1, min(slots, len(sequences)))
-    backend = BatchedBackend(cfg, state_dict, slots, device=device, blocks_impl=blocks_impl)
+    backend = BatchedBackend(cfg, state_dict, slots, device=device, blocks_impl=blocks_impl, row_staging=row_staging)
     runner = MultiSequenceRunner(backend, slots, results_dir=results_dir, **kw)
     try:
         return runner.run(sequences)
     finally:
         runner.close()
+        backend.close()

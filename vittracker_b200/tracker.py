@@ -79,14 +79,21 @@ class Vit_dist(BaseTracker):
         self._hw = (-1, -1)
         self._hw_dev = torch.zeros((1, 2), dtype=torch.int32, device=dev)
         self._off_dev = torch.zeros((1,), dtype=torch.int64, device=dev)
-        self._box_pin = torch.zeros((1, 4), dtype=torch.float64).pin_memory()
+        self._box_pin = self._pinned(torch.zeros((1, 4), dtype=torch.float64))
         self._box_dev = torch.zeros((1, 4), dtype=torch.float64, device=dev)
         self._out_dev = torch.zeros((13,), dtype=torch.float64, device=dev)
-        self._out_pin = torch.zeros((13,), dtype=torch.float64).pin_memory()
+        self._out_pin = self._pinned(torch.zeros((13,), dtype=torch.float64))
         self._out_boxes = self._out_dev[:5].view(1, 5)
         self._out_detail = self._out_dev[5:].view(1, 8)
 
     # ------------------------------------------------------------------------------------------
+    def _pinned(self, t: torch.Tensor) -> torch.Tensor:
+        return t.pin_memory() if self._dev.type == "cuda" else t
+
+    def _sync(self) -> None:
+        if self._dev.type == "cuda":
+            torch.cuda.current_stream(self._dev).synchronize()
+
     def _upload(self, image: np.ndarray, box, factor: float):
         """Stage the rows of ``image`` the crop will read into the device frame buffer."""
         if image.dtype != np.uint8 or image.ndim != 3 or image.shape[2] != 3:
@@ -95,7 +102,7 @@ class Vit_dist(BaseTracker):
         H, W, _ = image.shape
         if (H, W) != self._hw:
             self._frame_dev = torch.empty((H * W * 3,), dtype=torch.uint8, device=self._dev)
-            self._frame_pin = torch.empty((H * W * 3,), dtype=torch.uint8).pin_memory()
+            self._frame_pin = self._pinned(torch.empty((H * W * 3,), dtype=torch.uint8))
             self._hw_dev.copy_(torch.tensor([[H, W]], dtype=torch.int32))
             self._hw = (H, W)
         x, y, w, h = [float(v) for v in box]
@@ -156,7 +163,7 @@ class Vit_dist(BaseTracker):
         self._out_pin.copy_(self._out_dev, non_blocking=True)
         # `confidence` is a 0-dim tensor on the model's device, as the reference's `score_map.max()` is (vit_dist.py:147-148)
         confidence = self._out_dev[4].to(torch.float32)
-        torch.cuda.current_stream(self._dev).synchronize()
+        self._sync()
         out = self._out_pin.tolist()
         if int(out[11]) == 1:
             raise Exception('Too small bounding box.')
