@@ -13,8 +13,9 @@ for tool in $TOOLS; do
     extra=""
     [ "$tool" = "racecheck" ] && extra="--racecheck-report all"
     [ "$tool" = "initcheck" ] && extra="--track-unused-memory no"
-    /usr/bin/time -f "wall %e s" timeout 900 compute-sanitizer --tool $tool $extra --print-limit 30 python tools/sanitize_target.py $part > $log 2>&1
-    echo "exit $?" >> $log
+    t0=$SECONDS
+    timeout 900 compute-sanitizer --tool $tool $extra --print-limit 30 python tools/sanitize_target.py $part > $log 2>&1
+    echo "exit $? wall $((SECONDS - t0)) s" >> $log
     echo "== $tool $part: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|exit |wall ' $log | tr '\n' ' ')"
   done
 done

@@ -30,6 +30,14 @@ extern "C" int vt_head_trace_read(long long* host) { cudaDeviceSynchronize(); re
 #define HEAD_TRACE(i) do {} while (0)
 #endif
 
+// max that keeps NaN (fmaxf returns the other operand): the ReLUs and the running maximum of the tensor-core epilogues must not
+// squash a NaN born from an overflowed fp16 operand or weight into a plausible number - the range guard has to see it
+__device__ __forceinline__ float max_nan(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+
 constexpr int kHeadThreads = 256;
 constexpr int kPlane = 18 * 18;                      // zero-bordered 16x16 plane
 constexpr int kWChunk = 3456;                        // floats per streamed weight chunk
@@ -423,8 +431,8 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
                         float t2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[j]), 1);   // T_2[y][x+1]
                         if (px == 0) t0 = 0.f;
                         if (px == 15) t2 = 0.f;
-                        v[j] = fmaxf((t0 + __uint_as_float(r1[j])) + t2 + sb[h * 48 + c0 + j], 0.f);
-                        vmax = fmaxf(vmax, v[j]);
+                        v[j] = max_nan((t0 + __uint_as_float(r1[j])) + t2 + sb[h * 48 + c0 + j], 0.f);
+                        vmax = max_nan(vmax, v[j]);
                     }
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
@@ -494,8 +502,8 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
                 float t2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[j]), 1);
                 if (px == 0) t0 = 0.f;
                 if (px == 15) t2 = 0.f;
-                v[j] = fmaxf((t0 + __uint_as_float(r1[j])) + t2 + sb[96 + tw * 16 + j], 0.f);
-                vmax = fmaxf(vmax, v[j]);
+                v[j] = max_nan((t0 + __uint_as_float(r1[j])) + t2 + sb[96 + tw * 16 + j], 0.f);
+                vmax = max_nan(vmax, v[j]);
             }
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -552,7 +560,9 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
                 float t2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[j]), 1);
                 if (px == 0) t0 = 0.f;
                 if (px == 15) t2 = 0.f;
-                op[(tw * 8 + j) * kPlane] = fmaxf((t0 + __uint_as_float(r1[j])) + t2 + sb[144 + tw * 8 + j], 0.f);
+                const float o3 = max_nan((t0 + __uint_as_float(r1[j])) + t2 + sb[144 + tw * 8 + j], 0.f);
+                op[(tw * 8 + j) * kPlane] = o3;
+                vmax = max_nan(vmax, o3 < INFINITY ? 0.f : o3);          // conv3's operands were fp16 too: a non-finite result (inf or NaN) is an overflow
             }
         }
     }
