@@ -491,6 +491,15 @@ int vt_finalize_weights(VtHandle h, void* stream) {
                                  });
         }
     }
+    // ---- stem conv1 for the fused tensor-core front (vt_stem_fused.cu): pixel normalisation folded into the weights / border-variant biases
+    const size_t s1_w = slot(kStem1TcWBytes / 4), s1_p = slot(kStem1TcParFloats);
+    stem1_tc_pack(&pk.buf[stem_w[0]], &pk.buf[stem_b[0]], reinterpret_cast<uint8_t*>(&pk.buf[s1_w]), &pk.buf[s1_p],
+                  [](float v, uint16_t* hi, uint16_t* lo) {
+                      const __half h2 = __float2half_rn(v);
+                      const __half l2 = __float2half_rn(v - __half2float(h2));
+                      memcpy(hi, &h2, 2);
+                      memcpy(lo, &l2, 2);
+                  });
     // ---- blocks: Linear weights [out][in] -> K-major [in][out]
     struct BOff { size_t ln1g, ln1b, wqkv, bqkv, wproj, bproj, ln2g, ln2b, wfc1, bfc1, wfc2, bfc2; } bo[kDepth];
     auto copyv = [&](size_t o, const float* src, size_t n) { if (src) memcpy(&pk.buf[o], src, n * sizeof(float)); };
@@ -691,6 +700,7 @@ int vt_finalize_weights(VtHandle h, void* stream) {
     m.head_tc_w2 = reinterpret_cast<const uint8_t*>(base + o_htc2);
     m.head_tc_w3 = reinterpret_cast<const uint8_t*>(base + o_htc3);
     for (int i = 0; i < 3; ++i) { m.stem_tc_w[i] = reinterpret_cast<const uint8_t*>(base + stc_w[i]); m.stem_tc_b[i] = base + stc_b[i]; }
+    m.stem1_tc_w = reinterpret_cast<const uint8_t*>(base + s1_w); m.stem1_tc_par = base + s1_p;
     m.hann = base + o_hann; m.lut = base + o_lut;
     h->finalized = true;
     return VT_OK;

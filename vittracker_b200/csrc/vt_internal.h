@@ -103,6 +103,8 @@ constexpr int kTcWbBytes = 2 * (192 * 48 * 2) + 2 * (48 * 192 * 2);     // W1 hi
 constexpr int kHeadTcPieceBytes = 2 * (48 * 48 * 2);       // one (half, ky, K step) piece of head conv1: hi | lo, N = 144 (kx, co), K = 16 -> 9216
 constexpr int kHeadTcW3Bytes = 3 * 2 * (48 * 32 * 2);      // head conv3: 3 tower blobs of hi | lo, N = 32 (kx, co; 24 used), K = 48 -> 18432
 constexpr int kHeadTcW2Bytes = 9 * 2 * (96 * 16 * 2);      // head conv2: 3 tower blobs of hi | lo, N = 48 (kx, co), K = 96 -> 55296
+constexpr int kStem1TcWBytes = 4 * 512;     // fused stem, conv1 on tcgen05 (vt_stem_fused.cu): [variant 2][K step 2] x (2 chunks x 16 n x 16 B)
+constexpr int kStem1TcParFloats = 40;       // bias[4 border variants][8], 2^-s at [32]
 constexpr int kTcParFloats = 624;   // ln1_g 48 | ln1_b 48 | bq 48 | bk 48 | Wproj bv 48 | bproj 48 | ln2_g 48 | ln2_b 48 | bfc1 192 | bfc2 48
 struct BlockTcW {
     const uint8_t* wa;     // kTcWaBytes
@@ -119,6 +121,8 @@ struct ModelW {
     HeadW head;
     const uint8_t* stem_tc_w[3];   // stem conv2 / conv3 / conv4 for tcgen05 (vt_stem_tc.cu): fp16 hi | lo blobs in K-step order
     const float* stem_tc_b[3];     // biases
+    const uint8_t* stem1_tc_w;     // stem conv1 for tcgen05 with the pixel normalisation folded in (vt_stem_fused.cu: stem1_tc_pack)
+    const float* stem1_tc_par;     // its border-variant biases and scale
     const uint8_t* head_tc_w1;     // head conv1 for tcgen05: 18 pieces (half h, ky, K step) x [hi | lo] x K-major [2 chunks][n = kx*48 + co][8]
     const uint8_t* head_tc_w3;     // head conv3 for tcgen05: 3 blobs (tower) x [hi | lo] x K-major [k/8][n = kx*8 + co, 32][8], k = ky*16 + ci
     const uint8_t* head_tc_w2;     // head conv2 for tcgen05: 3 blobs (tower) x [hi | lo] x K-major [k/8][n = kx*16 + co][8], k = ky*32 + ci
@@ -163,6 +167,29 @@ inline bool ensure_dyn_smem(DeviceOnce& once, Kern kern, size_t bytes) {
     return true;
 }
 
+// Resident CTAs per SM of a persistent kernel, from the kernel's own resource use and the device limits (registers are allocated per
+// warp in units of 256; 1 KB of shared memory per CTA is reserved by the driver; TMEM has 512 columns per SM).  Computed by hand:
+// cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for these kernels on this driver although two (or more) CTAs are resident
+// (Nsight Compute's launch limits agree with the arithmetic below) - and a persistent grid sized from it ran one CTA per SM.
+template <typename Kern>
+inline int resident_ctas_per_sm(Kern kern, int threads, size_t dyn_smem, int tmem_cols, int dev) {
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess) return 1;
+    int regs_sm = 65536, smem_sm = 233472, thr_sm = 2048, blk_sm = 32;
+    cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    cudaDeviceGetAttribute(&thr_sm, cudaDevAttrMaxThreadsPerMultiProcessor, dev);
+    cudaDeviceGetAttribute(&blk_sm, cudaDevAttrMaxBlocksPerMultiprocessor, dev);
+    const int warps = (threads + 31) / 32;
+    const int regs_warp = (fa.numRegs * 32 + 255) / 256 * 256;
+    int k = blk_sm;
+    if (regs_warp > 0) k = min(k, regs_sm / (regs_warp * warps));
+    k = min(k, (int)(smem_sm / (dyn_smem + fa.sharedSizeBytes + 1024)));
+    k = min(k, thr_sm / (warps * 32));
+    if (tmem_cols > 0) k = min(k, 512 / tmem_cols);
+    return k < 1 ? 1 : k;
+}
+
 // RAII: make `device` current for the duration of a C-ABI call and restore the caller's device afterwards (the host
 // language's runtime - PyTorch - keeps its own notion of the current device).
 struct DeviceGuard {
@@ -195,6 +222,13 @@ int launch_stem234_tc(const uint8_t* planes2, int n, const ModelW& w, uint8_t* p
 __host__ __device__ constexpr size_t tc_planes_bytes_per_track() {
     return tc_planes_bytes(kConv2Cch, kConv2Wout) + tc_planes_bytes(kConv3Cch, kConv3Wout) + tc_planes_bytes(kConv4Cch, kConv4Wout);
 }
+// conv3 + conv4 only (the fused front kernel has written planes3)
+int launch_stem34_tc(const uint8_t* planes3, int n, const ModelW& w, uint8_t* planes4, float* tokens, int tok_stride_rows, int tok_off,
+                     cudaStream_t st);
+// Fused front of the search-branch stem (vt_stem_fused.cu): tap tables + crop gather -> conv1 -> conv2 on tcgen05 -> planes3
+int launch_crop_stem12_fused(const uint8_t* frames, const int64_t* frame_offsets, const int32_t* frame_hw, const double* boxes, double factor,
+                             int n, const ModelW& w, int32_t* out_status, void* tap_tables, uint8_t* planes3, cudaStream_t st);
+void stem1_tc_pack(const float* wf, const float* bf, uint8_t* blob, float* par, void (*split)(float, uint16_t*, uint16_t*));
 size_t stem_tc_weight_bytes(int layer);
 void stem_tc_pack_weights(int cin, int cch, int cout, int npad, const float* wf, uint8_t* hi8, uint8_t* lo8,
                           void (*split)(float, uint16_t*, uint16_t*));
