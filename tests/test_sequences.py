@@ -119,6 +119,45 @@ def test_threaded_frame_ingest_from_image_files(tmp_path):
     assert [e[3] for e in be.log if e[0] == "frame" and e[2] == 2] == [1, 2, 3]
 
 
+def test_read_image_branches_match_the_reference_reader(tmp_path, monkeypatch):
+    """read_image = Tracker._read_image (tracker.py:282-289): path -> cv.imread + BGR2RGB; [lmdb_file, key] -> LMDB value ->
+    cv.imdecode + BGR2RGB (lmdb_utils.py:23-30).  lmdb is not in this image: the lookup runs against an in-memory stand-in module."""
+    cv = pytest.importorskip("cv2")
+    import sys
+    import types
+    from vittracker_b200 import sequences as S
+    rng = np.random.default_rng(1)
+    rgb = rng.integers(0, 256, size=(12, 20, 3), dtype=np.uint8)
+    path = str(tmp_path / "f.png")
+    assert cv.imwrite(path, rgb[..., ::-1])
+    assert np.array_equal(S.read_image(path), rgb)
+    ok, enc = cv.imencode(".png", rgb[..., ::-1])
+    assert ok and np.array_equal(S.read_image(enc.tobytes()), rgb)
+    store = {"seq/0001.png": enc.tobytes()}
+    opened = []
+
+    class _Txn:
+        def get(self, key):
+            return store.get(key.decode())
+
+    class _Env:
+        def begin(self, write=False):
+            return _Txn()
+
+    fake = types.ModuleType("lmdb")
+    fake.open = lambda name, **kw: (opened.append((name, kw)), _Env())[1]
+    monkeypatch.setitem(sys.modules, "lmdb", fake)
+    S._LMDB_HANDLES.clear()
+    assert np.array_equal(S.read_image(["db.lmdb", "seq/0001.png"]), rgb)
+    assert np.array_equal(S.read_image(["db.lmdb", "seq/0001.png"]), rgb) and len(opened) == 1      # the handle is cached (lmdb_utils.py:11-20)
+    assert opened[0][1] == dict(readonly=True, lock=False, readahead=False, meminit=False)
+    with pytest.raises(FileNotFoundError):
+        S.read_image(["db.lmdb", "missing"])
+    with pytest.raises(ValueError):
+        S.read_image(42)
+    S._LMDB_HANDLES.clear()
+
+
 def test_crop_rows_cover_what_sample_target_reads():
     """Row staging uploads rows [ya, yb) of a frame: exactly the slice sample_target takes (processing_utils.py:34-48)."""
     from oracle import vt_oracle as O

@@ -47,6 +47,17 @@ namespace {
 #define VT_TC_NS 6
 #endif
 constexpr int kNS = VT_TC_NS;                  // 3 or 6
+// Split terms of the score contraction S = q k^T:  3 = hi*hi + lo*hi + hi*lo (as every other contraction), 2 = without hi*lo (K at fp16),
+// 1 = hi*hi only (single-pass fp16).  The per-contraction precision budget (tools/precision_budget.py, profiles/r02_precision_budget*.json:
+// oracle-side emulation of this kernel's operand rounding on 3 x 10^4 frames, two weight sets) shows the scores are the one contraction whose
+// low-order terms do not reach the arg-max: S feeds a softmax (a perturbation of S scales P by 1 + dS, and the row normalisation removes
+// its common part), |dS| ~ 2^-12 |q||k| / sqrt(48) ~ 1e-5 here.  Dropping either term of q k^T: 0 flips, score-map error 1e-6 (the noise
+// floor of the three-term scheme is 8e-7); every other contraction flips the arg-max when it loses a term (errors 2e-5 .. 1.5e-4).
+#ifndef VT_TC_SCORES_TERMS
+#define VT_TC_SCORES_TERMS 1
+#endif
+constexpr int kScoresTerms = VT_TC_SCORES_TERMS;
+static_assert(kScoresTerms >= 1 && kScoresTerms <= 3, "scores terms");
 constexpr int kEpiWarps = 4 * kNS;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kTcThreads = kEpiThreads + 32;   // + the control warp
@@ -311,9 +322,9 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
                     const uint32_t off = ks * 2 * (kN * 16) + half * 160 * 16;
                     const uint64_t bh = smem_desc(sbase + kSmKhi + off, kN * 16, 128);
                     const uint64_t bl = smem_desc(sbase + kSmKlo + off, kN * 16, 128);
-                    mma_ts_elect(d, a + 8 * ks, bh, id160, ks > 0);
-                    mma_ts_elect(d, a + 24 + 8 * ks, bh, id160, true);
-                    mma_ts_elect(d, a + 8 * ks, bl, id160, true);
+                    mma_ts_elect(d, a + 8 * ks, bh, id160, ks > 0);                               // q_hi k_hi
+                    if (kScoresTerms >= 2) mma_ts_elect(d, a + 24 + 8 * ks, bh, id160, true);     // q_lo k_hi
+                    if (kScoresTerms >= 3) mma_ts_elect(d, a + 8 * ks, bl, id160, true);          // q_hi k_lo
                 }
             };
             // O' = P V' accumulated in the tile's (now dead) q slot: P in TMEM (16-key group g: hi cols 16g.., lo cols 16g+8..),
@@ -474,7 +485,7 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
 #pragma unroll
                             for (int j = 0; j < 4; ++j) split_pack2(v[2 * (c + j)] * scale, v[2 * (c + j) + 1] * scale, hi[j], lo[j]);
                             tmem_st4(e.taddr(kColOpa + 48 * t + qkv_off / 2 + c), hi);
-                            tmem_st4(e.taddr(kColOpa + 48 * t + 24 + qkv_off / 2 + c), lo);
+                            if (kScoresTerms >= 2) tmem_st4(e.taddr(kColOpa + 48 * t + 24 + qkv_off / 2 + c), lo);
                         }
                     } else {
                         // K: K-major [k/8][key][8]   V: MN-major [f/8][key/8][key%8][f%8]  (both: chunk * 320*16 + key*16)
@@ -486,7 +497,8 @@ blocks_tc_kernel(const float* __restrict__ tok_z, int z_stride_rows, const float
 #pragma unroll
                             for (int j = 0; j < 4; ++j) split_pack2(v[8 * c + 2 * j], v[8 * c + 2 * j + 1], hi[j], lo[j]);
                             *reinterpret_cast<uint4*>(hi_base + c * (kN * 16)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                            *reinterpret_cast<uint4*>(lo_base + c * (kN * 16)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                            if (qkv_part == 2 || kScoresTerms >= 3)                    // K's low-order half is read by the q_hi k_lo term only
+                                *reinterpret_cast<uint4*>(lo_base + c * (kN * 16)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                         }
                     }
                 };

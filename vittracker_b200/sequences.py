@@ -18,7 +18,7 @@ from typing import Callable, Dict, List, Optional, Sequence as Seq, Union
 
 import numpy as np
 
-Frame = Union[np.ndarray, str, Callable[[], np.ndarray]]
+Frame = Union[np.ndarray, str, bytes, list, Callable[[], np.ndarray]]
 
 
 class Sequence:
@@ -35,12 +35,41 @@ class Sequence:
         return {"init_bbox": list(self.init_bbox)}
 
 
+_LMDB_HANDLES: Dict[str, object] = {}
+
+
+def decode_image(buf) -> np.ndarray:
+    """Encoded image bytes -> HxWx3 uint8 RGB: the decode step of lib/utils/lmdb_utils.py:23-30 (cv.imdecode + BGR2RGB)."""
+    import cv2 as cv
+    im = cv.imdecode(np.frombuffer(buf, np.uint8), cv.IMREAD_COLOR)
+    if im is None:
+        raise ValueError("image bytes could not be decoded")
+    return cv.cvtColor(im, cv.COLOR_BGR2RGB)
+
+
 def read_image(frame: Frame) -> np.ndarray:
-    """HxWx3 uint8 RGB, as Tracker._read_image delivers it (tracker.py:282-289: cv.imread + BGR2RGB)."""
+    """HxWx3 uint8 RGB, as Tracker._read_image delivers it (lib/test/evaluation/tracker.py:282-289): a path goes through cv.imread +
+    BGR2RGB; a two-element list [lmdb_file, key] through the LMDB lookup + cv.imdecode of lib/utils/lmdb_utils.py:11-30.  Also accepted:
+    an array (used as is), a zero-argument loader, and encoded image bytes (the LMDB value itself)."""
     if isinstance(frame, np.ndarray):
         return frame
     if callable(frame):
         return frame()
+    if isinstance(frame, (bytes, bytearray, memoryview)):
+        return decode_image(frame)
+    if isinstance(frame, (list, tuple)) and len(frame) == 2:
+        import lmdb                                                     # the reference's dependency for this branch; not bundled
+        name, key = frame
+        handle = _LMDB_HANDLES.get(name)
+        if handle is None:
+            env = lmdb.open(name, readonly=True, lock=False, readahead=False, meminit=False)
+            handle = _LMDB_HANDLES[name] = env.begin(write=False)
+        buf = handle.get(key.encode())
+        if buf is None:
+            raise FileNotFoundError(f"{name}: no LMDB entry {key!r}")
+        return decode_image(buf)
+    if not isinstance(frame, str):
+        raise ValueError("type of image_file should be str or list")        # tracker.py:289
     import cv2 as cv
     im = cv.imread(frame)
     if im is None:

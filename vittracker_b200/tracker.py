@@ -85,6 +85,7 @@ class Vit_dist(BaseTracker):
         self._out_pin = self._pinned(torch.zeros((13,), dtype=torch.float64))
         self._out_boxes = self._out_dev[:5].view(1, 5)
         self._out_detail = self._out_dev[5:].view(1, 8)
+        self._graph, self._graph_key = None, None
 
     # ------------------------------------------------------------------------------------------
     def _pinned(self, t: torch.Tensor) -> torch.Tensor:
@@ -157,9 +158,7 @@ class Vit_dist(BaseTracker):
         H, W, crop_sz = self._upload(image, self.state, self.params.search_factor)
         resize_factor = self.params.search_size / crop_sz       # processing_utils.py:67
         self._set_box(self.state)
-        self.engine.tracks_set_state(self._box_dev, first=0)
-        self.engine.tracks_step(self._frame_dev, self._off_dev, self._hw_dev, first=0, n=1, out_boxes=self._out_boxes,
-                                out_detail=self._out_detail, update_state=False, detail=True)
+        self._step_device()
         self._out_pin.copy_(self._out_dev, non_blocking=True)
         # `confidence` is a 0-dim tensor on the model's device, as the reference's `score_map.max()` is (vit_dist.py:147-148)
         confidence = self._out_dev[4].to(torch.float32)
@@ -176,6 +175,37 @@ class Vit_dist(BaseTracker):
         self.state = clip_box(self.map_box_back(pred_box, resize_factor), H, W, margin=10)
         self.last_detail = {"argmax": int(out[10]), "resize_factor": out[9], "window_max": out[12], "device_box": out[0:4]}
         return {"target_bbox": self.state, "confidence": confidence}
+
+    def _step_device(self) -> None:
+        """State upload + one tracking step for the single track.  Every buffer involved is allocated once (frame buffer, box, frame
+        size, outputs), so after the first frames the kernel sequence is captured in a CUDA graph and replayed: one graph launch
+        instead of a device copy + the step's kernel launches.  params.cuda_graph = False keeps plain launches."""
+        def launch():
+            self.engine.tracks_set_state(self._box_dev, first=0)
+            self.engine.tracks_step(self._frame_dev, self._off_dev, self._hw_dev, first=0, n=1, out_boxes=self._out_boxes,
+                                    out_detail=self._out_detail, update_state=False, detail=True)
+        use_graph = self._dev.type == "cuda" and getattr(self.params, "cuda_graph", True)
+        key = (self._hw, self._frame_dev.data_ptr() if self._frame_dev is not None else 0)
+        if use_graph and getattr(self, "_graph_key", None) == key and self._graph is not None:
+            self._graph.replay()
+            return
+        launch()
+        if not use_graph or getattr(self, "_graph_failed", False):
+            return
+        # capture after a warm frame on these buffers (lazy one-off configuration inside the library has happened by then)
+        self._graph_warm = getattr(self, "_graph_warm", 0) + 1 if getattr(self, "_graph_warm_key", None) == key else 1
+        self._graph_warm_key = key
+        if self._graph_warm < 2:
+            return
+        try:
+            torch.cuda.current_stream(self._dev).synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                launch()
+            self._graph, self._graph_key = g, key
+        except Exception:
+            self._graph, self._graph_key, self._graph_failed = None, None, True
+            torch.cuda.synchronize(self._dev)
 
     def map_box_back(self, pred_box: list, resize_factor: float):
         """lib/test/tracker/vit_dist.py:150-156."""
