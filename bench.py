@@ -532,7 +532,7 @@ def main():
     ap.add_argument("--config", default="vit_48_h32_noKD", choices=["vit_48_h32_noKD", WIDEST["name"]])
     ap.add_argument("--frames", type=int, default=64, help="distinct frames resident per GPU")
     ap.add_argument("--chunk", type=int, default=0, help="tracks per internal pass (default 1024; 32 for the widest config)")
-    ap.add_argument("--blocks", default="tcgen05", choices=["simt", "tcgen05"])
+    ap.add_argument("--blocks", default="tcgen05", choices=["simt", "tcgen05", "tcgen05_3term"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true")
@@ -690,7 +690,7 @@ def main():
     timed_s = ms / 1e3
     burst = timed_s < 1.0
     peak_tf = peaks["bf16_tflops"] if burst else peaks["bf16_tflops_sustained"]
-    kernel = "gemm_tc_kernel (blocks + head stage of the generic path)" if widest else ("blocks_simt_kernel" if args.blocks == "simt" else "blocks_tc_kernel")
+    kernel = "gemm_tc_kernel (blocks + head stage of the generic path)" if widest else {"simt": "blocks_simt_kernel", "tcgen05": "blocks_tc_kernel<1>", "tcgen05_3term": "blocks_tc_kernel<3>"}[args.blocks]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if args.total_tracks > 0 else "weak", "vs_baseline": None,

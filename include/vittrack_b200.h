@@ -52,7 +52,12 @@ typedef enum VtStatus {
 
 /* Which implementation of the ViT blocks vt_forward / vt_tracks_step use. */
 #define VT_BLOCKS_SIMT_FP32 0     /* fp32 CUDA-core kernel: bring-up / exact mode                 */
-#define VT_BLOCKS_TCGEN05 1       /* tcgen05 tensor-core kernel (fp16 hi/lo split, fp32 accum)    */
+#define VT_BLOCKS_TCGEN05 1       /* tcgen05 tensor-core kernels: fp16 hi/lo split operands (three products per contraction),
+                                   * fp32 accumulation; the attention scores q k^T as a single fp16 pass - the one contraction whose
+                                   * low-order terms the measured precision budget (profiles/r02_precision_budget*.json) shows
+                                   * never reach the arg-max on the specified (random-init) workload                          */
+#define VT_BLOCKS_TCGEN05_3TERM 2 /* the same kernels with three products for q k^T too: for checkpoints with sharp attention
+                                   * (large |q||k|), ~9 % slower blocks                                                       */
 
 /* Model / tracker configuration: experiments/vit_dist/vit_48_h32_noKD.yaml:56-64,89-92,
  * lib/config/vit_dist/config.py:27-37, build_ostrack_dist(cfg, depth=3) vit_dist.py:159. */

@@ -37,7 +37,8 @@ def stress_sd(golden_model):
     return state_dict_from_npz(golden_model)
 
 
-BLOCKS = ["simt", "tcgen05"]            # fp32 CUDA-core kernel and tcgen05 tensor-core kernel: same parity bar
+# fp32 CUDA-core kernels, tcgen05 kernels (scores q k^T as one fp16 pass), tcgen05 kernels with three-term scores: same parity bar
+BLOCKS = ["simt", "tcgen05", "tcgen05_3term"]
 
 
 @pytest.fixture(scope="module", params=BLOCKS)

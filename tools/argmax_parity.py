@@ -110,7 +110,7 @@ def run(n=10240, blocks="tcgen05", H=720, W=1280, F=64, seed=0, chunk=1024, weig
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=10240)
-    ap.add_argument("--blocks", default="tcgen05", choices=["tcgen05", "simt"])
+    ap.add_argument("--blocks", default="tcgen05", choices=["tcgen05", "tcgen05_3term", "simt"])
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--weights", default="all", choices=["all", *WEIGHT_SETS])
     ap.add_argument("--hw", default="720x1280")

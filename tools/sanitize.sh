@@ -12,7 +12,6 @@ for tool in $TOOLS; do
     log=$O/${T}_sanitizer_${tool}_${part}.txt
     extra=""
     [ "$tool" = "racecheck" ] && extra="--racecheck-report all"
-    [ "$tool" = "initcheck" ] && extra="--track-unused-memory no"
     t0=$SECONDS
     timeout 900 compute-sanitizer --tool $tool $extra --print-limit 30 python tools/sanitize_target.py $part > $log 2>&1
     echo "exit $? wall $((SECONDS - t0)) s" >> $log

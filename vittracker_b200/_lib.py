@@ -14,6 +14,7 @@ from . import build as _build
 VT_OK = 0
 VT_BLOCKS_SIMT_FP32 = 0
 VT_BLOCKS_TCGEN05 = 1
+VT_BLOCKS_TCGEN05_3TERM = 2
 VT_TRACK_OK, VT_TRACK_TOO_SMALL, VT_TRACK_OUT_OF_DOMAIN, VT_TRACK_NUMERIC_RANGE = 0, 1, 2, 3
 
 STATUS_NAMES = {0: "VT_OK", -1: "VT_ERR_INVALID_ARG", -2: "VT_ERR_CUDA", -3: "VT_ERR_WEIGHTS", -4: "VT_ERR_STATE",

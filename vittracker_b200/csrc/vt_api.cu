@@ -194,7 +194,7 @@ int run_blocks(VtHandle h, const float* tokz, int zs, const float* tokx, int xs,
                size_t tap_stride, cudaStream_t st) {
     if (h->cfg.blocks_impl == VT_BLOCKS_SIMT_FP32)
         return launch_blocks_simt(tokz, zs, tokx, xs, out, n, h->mw, taps, tap_stride, st);
-    return launch_blocks_tc(tokz, zs, tokx, xs, out, n, h->mw, taps, tap_stride, h->num_sms, st);
+    return launch_blocks_tc(tokz, zs, tokx, xs, out, n, h->mw, taps, tap_stride, h->num_sms, h->cfg.blocks_impl == VT_BLOCKS_TCGEN05_3TERM ? 3 : 1, st);
 }
 
 
@@ -346,7 +346,7 @@ int vt_create(const VtConfig* cfg, VtHandle* out) {
                     "num_heads, 1 <= depth <= %d)", kGenMaxDepth);
     if (cfg->max_tracks < 1 || !(cfg->template_factor > 0) || !(cfg->search_factor > 0))
         return fail(nullptr, VT_ERR_INVALID_ARG, "vt_create: max_tracks >= 1 and positive crop factors required");
-    if (cfg->blocks_impl != VT_BLOCKS_SIMT_FP32 && cfg->blocks_impl != VT_BLOCKS_TCGEN05)
+    if (cfg->blocks_impl != VT_BLOCKS_SIMT_FP32 && cfg->blocks_impl != VT_BLOCKS_TCGEN05 && cfg->blocks_impl != VT_BLOCKS_TCGEN05_3TERM)
         return fail(nullptr, VT_ERR_INVALID_ARG, "vt_create: unknown blocks_impl %d", cfg->blocks_impl);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -372,7 +372,7 @@ int vt_create(const VtConfig* cfg, VtHandle* out) {
     if (fast) {
         A((void**)&h->d_scratch, ch * stem_scratch_floats(kSx) * sizeof(float));
         A((void**)&h->d_taps, crop_taps_bytes((int)ch));
-        if (cfg->blocks_impl == VT_BLOCKS_TCGEN05) {
+        if (cfg->blocks_impl != VT_BLOCKS_SIMT_FP32) {
             const size_t pb = ch * tc_planes_bytes_per_track();
             A((void**)&h->d_planes, pb);
             if (e == cudaSuccess) e = cudaMemset(h->d_planes, 0, pb);
@@ -766,7 +766,7 @@ int vt_forward(VtHandle h, const float* z, const float* x, int32_t n, float* pre
         a.size_map = size_map ? size_map + (size_t)first * 512 : nullptr;
         a.offset_map = offset_map ? offset_map + (size_t)first * 512 : nullptr;
         a.tokens_norm = taps ? taps + (size_t)(kDepth + 1) * tap_stride + (size_t)first * kN * kC : nullptr;
-        a.use_tc = h->cfg.blocks_impl == VT_BLOCKS_TCGEN05;
+        a.use_tc = h->cfg.blocks_impl != VT_BLOCKS_SIMT_FP32;
         VT_LAUNCH(h, VT_STAGE_HEAD, m, st, "vt_forward/head", launch_head(a, h->mw, st));
     }
     return VT_OK;
@@ -880,7 +880,7 @@ int vt_tracks_step(VtHandle h, const uint8_t* frames, const int64_t* frame_offse
         a.out_detail = out_detail;
         a.update_state = update_state;
         a.search_factor = h->cfg.search_factor;
-        a.use_tc = h->cfg.blocks_impl == VT_BLOCKS_TCGEN05;
+        a.use_tc = h->cfg.blocks_impl != VT_BLOCKS_SIMT_FP32;
         VT_LAUNCH(h, VT_STAGE_HEAD, m, st, "vt_tracks_step/head", launch_head(a, h->mw, st));
     }
     h->last_first = first; h->last_n = n;

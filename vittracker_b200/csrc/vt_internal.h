@@ -246,7 +246,7 @@ int launch_blocks_simt(const float* tok_z, int z_stride_rows, const float* tok_x
 
 // ViT blocks on the tcgen05 tensor cores (fp16 hi/lo split operands, fp32 accumulation in TMEM).
 int launch_blocks_tc(const float* tok_z, int z_stride_rows, const float* tok_x, int x_stride_rows,
-                     float* out, int n, const ModelW& w, float* taps, size_t tap_stride, int num_sms, cudaStream_t st);
+                     float* out, int n, const ModelW& w, float* taps, size_t tap_stride, int num_sms, int scores_terms, cudaStream_t st);
 
 struct HeadArgs {
     const float* tokens;      // [n][320][48] block output (pre final-norm)

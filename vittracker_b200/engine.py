@@ -34,7 +34,7 @@ class Engine:
         self.device_index = torch.cuda.current_device() if device is None else int(device)
         self.device = torch.device("cuda", self.device_index)
         self.cfg = cfg
-        impl = {"simt": _lib.VT_BLOCKS_SIMT_FP32, "tcgen05": _lib.VT_BLOCKS_TCGEN05}[blocks_impl]
+        impl = {"simt": _lib.VT_BLOCKS_SIMT_FP32, "tcgen05": _lib.VT_BLOCKS_TCGEN05, "tcgen05_3term": _lib.VT_BLOCKS_TCGEN05_3TERM}[blocks_impl]
         c = _lib.VtConfig(
             embed_dim=int(cfg.MODEL.BACKBONE.CHANNELS), num_heads=int(cfg.MODEL.BACKBONE.HEADS), depth=int(depth),
             mlp_ratio=4, head_channels=int(cfg.MODEL.HEAD.NUM_CHANNELS), stride=int(cfg.MODEL.BACKBONE.STRIDE),
