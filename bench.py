@@ -711,6 +711,9 @@ def main():
                 "h2d_cap_gbs": float(sum(cap_ranks)), "h2d_cap_gbs_per_rank": cap_ranks,
                 "h2d_cap_frames_per_s": float(sum(cap_ranks)) * 1e9 / (h2d / n),
                 "frac_of_h2d_cap": e2e_value / (float(sum(cap_ranks)) * 1e9 / (h2d / n)),
+                # every rank moves the same bytes per step and the step time is the max over ranks: the slowest rank's link sets the pace
+                "h2d_cap_frames_per_s_at_slowest_rank": world * min(cap_ranks) * 1e9 / (h2d / n),
+                "frac_of_slowest_rank_cap": e2e_value / (world * min(cap_ranks) * 1e9 / (h2d / n)),
                 "binding": binding,
                 "note": "per step: H2D of all %d frames + boxes from pinned host memory (upload of step t+1 overlaps compute "
                         "of step t on a copy stream), step, D2H of the boxes; h2d_cap_gbs = pinned host -> HBM bandwidth measured in this run "
