@@ -11,8 +11,9 @@ from oracle import vt_oracle as O
 pytestmark = pytest.mark.gpu
 
 ABS_TOL, REL_TOL, TIE_GAP = 1e-2, 1e-3, 1e-5
+# "img": the smallest member that takes the split-image GEMM route (C a multiple of 128), ragged row tiles included
 CONFIGS = {"small": dict(C=96, heads=3, depth=2, hc=64), "odd": dict(C=40, heads=5, depth=1, hc=24),
-           "widest": dict(C=768, heads=12, depth=12, hc=256)}
+           "img": dict(C=128, heads=2, depth=2, hc=64), "widest": dict(C=768, heads=12, depth=12, hc=256)}
 
 
 def make_cfg(C, heads, depth, hc):
@@ -58,7 +59,7 @@ def test_generic_forward_against_oracle(name):
     assert torch.isfinite(got["taps"]).all()
 
 
-@pytest.mark.parametrize("name", ["small", "widest"])
+@pytest.mark.parametrize("name", ["small", "img", "widest"])
 def test_generic_batched_tracking_against_oracle(name):
     """vt_tracks_init + closed-loop vt_tracks_step through the generic path vs the oracle tracker (reference state machine)."""
     from vittracker_b200 import BatchedTracker, FramePool

@@ -31,13 +31,16 @@ if which in ("all", "fast"):
         print("fast path", blocks, "OK", out[0].tolist())
         del bt
 if which in ("all", "generic"):
-    cfg = load_cfg()
-    cfg.MODEL.BACKBONE.CHANNELS, cfg.MODEL.BACKBONE.HEADS, cfg.MODEL.BACKBONE.DEPTH, cfg.MODEL.HEAD.NUM_CHANNELS = 96, 3, 2, 64
-    sd = O.make_state_dict(seed=21, stress=True, C=96, depth=2, head_ch=64)
-    bt = BatchedTracker(cfg, sd, max_tracks=3, chunk_tracks=2, depth=2)
-    pool = FramePool(frames, bt.device)
-    assert int(bt.initialize(pool, torch.zeros(3, dtype=torch.int64), boxes[:3]).abs().sum()) == 0
-    out = bt.track(pool, torch.ones(3, dtype=torch.int64), update_state=True)
-    torch.cuda.synchronize()
-    assert torch.isfinite(out).all()
-    print("generic path OK", out[0].tolist())
+    # C = 96: converting GEMM (gemm_tc_kernel) + CUDA-core GEMM;  C = 128: split-image GEMM (gemm_img_kernel, layernorm_img, im2col_img)
+    for C, heads in ((96, 3), (128, 2)):
+        cfg = load_cfg()
+        cfg.MODEL.BACKBONE.CHANNELS, cfg.MODEL.BACKBONE.HEADS, cfg.MODEL.BACKBONE.DEPTH, cfg.MODEL.HEAD.NUM_CHANNELS = C, heads, 2, 64
+        sd = O.make_state_dict(seed=21, stress=True, C=C, depth=2, head_ch=64)
+        bt = BatchedTracker(cfg, sd, max_tracks=3, chunk_tracks=2, depth=2)
+        pool = FramePool(frames, bt.device)
+        assert int(bt.initialize(pool, torch.zeros(3, dtype=torch.int64), boxes[:3]).abs().sum()) == 0
+        out = bt.track(pool, torch.ones(3, dtype=torch.int64), update_state=True)
+        torch.cuda.synchronize()
+        assert torch.isfinite(out).all()
+        print("generic path C =", C, "OK", out[0].tolist())
+        del bt

@@ -263,6 +263,19 @@ int finalize_generic(VtHandle h, cudaStream_t st) {
                                 (size_t)C, (size_t)C, (size_t)hid * C, (size_t)hid, (size_t)C * hid, (size_t)C};
         for (int i = 0; i < 12; ++i) bo[b].v[i] = put(T(p + names[i]), cnt[i]);
     }
+    // split images of the blocks' Linear weights for the bulk-copy GEMM (same bytes as the fp32 matrices; packed on a few host threads)
+    struct IO { size_t v[4]; };
+    std::vector<IO> io(c.depth);
+    if (h->gw.use_img) {
+        const int wi[4] = {2, 4, 8, 10};                                       // qkv, proj, fc1, fc2 in `names`
+        const int wn[4] = {3 * C, C, hid, C}, wk[4] = {C, C, C, hid};
+        for (int b = 0; b < c.depth; ++b)
+            for (int j = 0; j < 4; ++j) io[b].v[j] = pk.alloc(gen_img_bytes(wn[j], wk[j]) / 4);
+        if (missing.empty())
+            for (int b = 0; b < c.depth; ++b)
+                for (int j = 0; j < 4; ++j)
+                    gen_pack_weight_image(&pk.buf[bo[b].v[wi[j]]], wn[j], wk[j], reinterpret_cast<uint8_t*>(&pk.buf[io[b].v[j]]));
+    }
     const size_t o_ng = put(T("norm.weight"), C), o_nb = put(T("norm.bias"), C);
     const size_t o_pz = put(T("pos_embed_z"), (size_t)kNz * C), o_px = put(T("pos_embed_x"), (size_t)kNx * C);
     // head: layer 1 merged over the towers (ctr | offset | size), layers 2-4 per tower, conv5 rows ctr, off x, off y, size w, size h
@@ -297,6 +310,18 @@ int finalize_generic(VtHandle h, cudaStream_t st) {
     if (!missing.empty()) return fail(h, VT_ERR_WEIGHTS, "missing tensors: %s", missing.c_str());
     const size_t o_hann = pk.alloc(256), o_lut = pk.alloc(768);
     fill_hann_and_lut(h, &pk.buf[o_hann], &pk.buf[o_lut]);
+    // split images of the folded convolution weights (K = 9 cin must be a whole number of 32-wide panels)
+    size_t isw[4] = {0, 0, 0, 0}, ihw1 = 0, ihw[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    auto conv_img = [&](size_t w_off, int co_n, int ci_n) -> size_t {
+        if (!h->gw.use_img || ci_n % 32 != 0) return 0;
+        const size_t o = pk.alloc(gen_img_bytes(co_n, 9 * ci_n) / 4);
+        gen_pack_weight_image(&pk.buf[w_off], co_n, 9 * ci_n, reinterpret_cast<uint8_t*>(&pk.buf[o]));
+        return o;
+    };
+    for (int l = 1; l < 4; ++l) isw[l] = conv_img(sw[l], ch[l + 1], ch[l]);
+    ihw1 = conv_img(o_w1, 3 * hc, C);
+    for (int t = 0; t < 3; ++t)
+        for (int l = 0; l < 3; ++l) ihw[t][l] = conv_img(hw[t][l], hch[l + 2], hch[l + 1]);
 
     if (h->d_weights && h->weights_floats < pk.buf.size()) { cudaFree(h->d_weights); h->d_weights = nullptr; }
     if (!h->d_weights) {
@@ -311,7 +336,12 @@ int finalize_generic(VtHandle h, cudaStream_t st) {
     for (int b = 0; b < c.depth; ++b) {
         const float* q[12];
         for (int i = 0; i < 12; ++i) q[i] = base + bo[b].v[i];
-        g.blk[b] = GenBlockW{q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8], q[9], q[10], q[11]};
+        g.blk[b] = GenBlockW{q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8], q[9], q[10], q[11], nullptr, nullptr, nullptr, nullptr};
+        if (g.use_img) {
+            const uint8_t* ib[4];
+            for (int j = 0; j < 4; ++j) ib[j] = reinterpret_cast<const uint8_t*>(base + io[b].v[j]);
+            g.blk[b].iwqkv = ib[0]; g.blk[b].iwproj = ib[1]; g.blk[b].iwfc1 = ib[2]; g.blk[b].iwfc2 = ib[3];
+        }
     }
     g.norm_g = base + o_ng; g.norm_b = base + o_nb; g.pos_z = base + o_pz; g.pos_x = base + o_px;
     g.head_w1 = base + o_w1; g.head_b1 = base + o_b1;
@@ -319,6 +349,11 @@ int finalize_generic(VtHandle h, cudaStream_t st) {
         for (int l = 0; l < 3; ++l) { g.head_w[t][l] = base + hw[t][l]; g.head_b[t][l] = base + hb[t][l]; }
     g.head_w5 = base + o_w5; g.head_b5 = base + o_b5;
     g.hann = base + o_hann;
+    auto imgp = [&](size_t o) { return o ? reinterpret_cast<const uint8_t*>(base + o) : nullptr; };
+    for (int l = 0; l < 4; ++l) g.istem_w[l] = imgp(isw[l]);
+    g.ihead_w1 = imgp(ihw1);
+    for (int t = 0; t < 3; ++t)
+        for (int l = 0; l < 3; ++l) g.ihead_w[t][l] = imgp(ihw[t][l]);
     h->mw.hann = base + o_hann; h->mw.lut = base + o_lut;         // the crop kernel reads the table through ModelW
     h->finalized = true;
     return VT_OK;
@@ -382,12 +417,15 @@ int vt_create(const VtConfig* cfg, VtHandle* out) {
         A((void**)&h->d_tok, mt * kN * kC * sizeof(float));
     } else {
         h->gw.C = cfg->embed_dim; h->gw.heads = cfg->num_heads; h->gw.depth = cfg->depth; h->gw.hc = cfg->head_channels;
-        size_t off[17];
+        h->gw.use_img = (cfg->blocks_impl != VT_BLOCKS_SIMT_FP32 && cfg->embed_dim % 128 == 0) ? 1 : 0;
+        size_t off[kGenWorkSlots];
         const size_t tot = gen_work_floats(h->gw, h->chunk, off);
         A((void**)&h->d_gwork, tot * sizeof(float));
-        float** members[17] = {&h->gws.crop, &h->gws.col, &h->gws.act1, &h->gws.act2, &h->gws.act3, &h->gws.tokz, &h->gws.tok, &h->gws.ln,
-                               &h->gws.qkv, &h->gws.scores, &h->gws.attn, &h->gws.hid, &h->gws.t1, &h->gws.t2, &h->gws.t3, &h->gws.t4, &h->gws.raw5};
-        for (int i = 0; i < 17; ++i) *members[i] = h->d_gwork ? h->d_gwork + off[i] : nullptr;
+        if (e == cudaSuccess) e = cudaMemset(h->d_gwork, 0, tot * sizeof(float));      // padding rows of the split images are read (and ignored)
+        float** members[kGenWorkSlots] = {&h->gws.crop, &h->gws.col, &h->gws.act1, &h->gws.act2, &h->gws.act3, &h->gws.tokz, &h->gws.tok, &h->gws.ln,
+                                          &h->gws.qkv, &h->gws.scores, &h->gws.attn, &h->gws.hid, &h->gws.t1, &h->gws.t2, &h->gws.t3, &h->gws.t4, &h->gws.raw5,
+                                          &h->gws.img_ln, &h->gws.img_attn, &h->gws.img_hid};
+        for (int i = 0; i < kGenWorkSlots; ++i) *members[i] = h->d_gwork ? h->d_gwork + off[i] : nullptr;
         h->gws.chunk = h->chunk;
     }
     A((void**)&h->d_state, mt * 4 * sizeof(double));

@@ -8,6 +8,14 @@
 // Convolutions are im2col (NHWC, k = (ky, kx, ci)) + one tiled GEMM with a fused bias / activation / residual epilogue;
 // attention is two batched GEMMs (batch = track x head) around a row softmax.  The decode is the code the fused head
 // kernels use (vt_decode.cuh).  This path favours coverage over speed; the tuned kernels are vit_48_h32's.
+#include <stdlib.h>
+#include <string.h>
+
+#include <thread>
+#include <vector>
+
+#include <cuda_fp16.h>
+
 #include "vt_decode.cuh"
 #include "vt_internal.h"
 #include "vt_tc.cuh"
@@ -28,6 +36,9 @@ struct GemmArgs {
     int rmod;            // > 0: residual row = m % rmod (broadcast over groups of rows, e.g. the positional embedding)
     float alpha;
     int act;
+    // optional: write the result as the split image of a matrix with img_K columns instead of C (tensor-core kernel only):
+    // element (m, n) of batch z lands at image row z1 * img_rows1 + m, column z2 * img_cols2 + n
+    uint8_t* Cimg; int img_K; long long img_rows1; int img_cols2;
 };
 
 constexpr int kBM = 64, kBN = 64, kBK = 16;
@@ -194,6 +205,21 @@ __global__ void __launch_bounds__(kTcGemmThreads) gemm_tc_kernel(GemmArgs g) {
             tc::tmem_ld16(ta + c0, r);
             tc::tc_wait_ld();
             if (m >= g.M) continue;
+            if (g.Cimg) {             // plain product (no bias / activation on this route) as a split image: 16 columns = two 8-wide chunks
+                const long long ir = (long long)z1 * g.img_rows1 + m;
+                const int ic = z2 * g.img_cols2 + n0 + c0;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (n0 + c0 + 8 * c >= g.N) break;
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        tc::split_pack2(__uint_as_float(r[8 * c + 2 * j]) * g.alpha, __uint_as_float(r[8 * c + 2 * j + 1]) * g.alpha, hi[j], lo[j]);
+                    *reinterpret_cast<uint4*>(g.Cimg + gen_img_offset(ir, ic / 8 + c, g.img_K, 0)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(g.Cimg + gen_img_offset(ir, ic / 8 + c, g.img_K, 1)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+                continue;
+            }
             float* cp = C + (size_t)m * g.ldc + n0 + c0;
             const float* rp = R ? R + (size_t)(g.rmod > 0 ? m % g.rmod : m) * g.ldr + n0 + c0 : nullptr;
 #pragma unroll
@@ -252,9 +278,205 @@ int launch_gemm_tc(const GemmArgs& g, int batch, cudaStream_t st) {
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
+// ---- split-image GEMM: C = act(A B^T + bias) + R with BOTH operands already in the tensor cores' shared-memory layout -------------------
+// A: image of [M][K] activations (written by layernorm_img_kernel or by a producing GEMM's epilogue), B: image of a [N][K] Linear weight
+// (packed once at vt_finalize_weights).  A pipeline stage is two 16 KB bulk copies (cp.async.bulk, one per operand) completing on an
+// mbarrier - no thread touches the operands; one warp issues the copies, one the MMAs (hi*hi + lo*hi + hi*lo, M = N = 128, K = 16), eight
+// warps run the epilogue.  Output: fp32 row-major (bias / activation / residual) and / or the split image of the result for the next GEMM.
+// Against gemm_tc_kernel this removes the fp32 -> fp16 hi/lo conversion of both operands from every tile of every GEMM (the A panel was
+// re-converted once per 128 output columns: 18 times for the QKV projection at C = 768).
+struct ImgGemmArgs {
+    const uint8_t* A; const uint8_t* B;
+    int M, N, K;
+    float* C; int ldc;
+    const float* bias; const float* R; int ldr;
+    int act;
+    uint8_t* Cimg;          // image of the result (K' = N), or null
+    int rmod;               // > 0: residual row = m % rmod (the positional embedding, broadcast over tracks)
+    int c_group, c_stride;  // c_group > 0: output row of m = (m / c_group) * c_stride + m % c_group (tokens of a track inside [320][C])
+};
+constexpr int kIgStages = 3;
+constexpr int kIgStageBytes = 2 * kImgBlockBytes;                                   // A block | B block
+constexpr int kIgSmem = kIgStages * kIgStageBytes + (2 * kIgStages + 1) * 8 + 16;   // 2 CTAs per SM
+constexpr int kIgThreads = 10 * 32;                                                 // warps 0-7 epilogue, 8 bulk copies, 9 MMA issue
+
+__global__ void __launch_bounds__(kIgThreads) gemm_img_kernel(ImgGemmArgs g) {
+    extern __shared__ __align__(128) uint8_t gsm[];
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(gsm + kIgStages * kIgStageBytes);
+    uint64_t* bar_empty = bar_full + kIgStages;
+    uint64_t* bar_acc = bar_empty + kIgStages;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acc + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128;
+    const int ksteps = g.K / 32;
+    if (warp == 9) tc::tmem_alloc(s_tmem, 128);
+    if (tid == 0) {
+        for (int i = 0; i < kIgStages; ++i) { tc::mbar_init(bar_full + i, 2); tc::mbar_init(bar_empty + i, 1); }
+        tc::mbar_init(bar_acc, 1);
+        tc::mbar_fence_init();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tbase = __shfl_sync(0xffffffffu, *s_tmem, 0);
+
+    if (warp == 8) {
+        // ---- bulk copies: block (row tile, K panel) of each operand, kIgStages in flight ----
+        const uint8_t* ab = g.A + (size_t)blockIdx.y * ksteps * kImgBlockBytes;
+        const uint8_t* bb = g.B + (size_t)blockIdx.x * ksteps * kImgBlockBytes;
+#pragma unroll 1
+        for (int ks = 0; ks < ksteps; ++ks) {
+            const int st = ks % kIgStages;
+            if (ks >= kIgStages) tc::mbar_wait(bar_empty + st, ((ks / kIgStages) - 1) & 1);
+            uint8_t* sp = gsm + st * kIgStageBytes;
+            tc::bulk_g2s_elect(sp, ab + (size_t)ks * kImgBlockBytes, kImgBlockBytes, bar_full + st);
+            tc::bulk_g2s_elect(sp + kImgBlockBytes, bb + (size_t)ks * kImgBlockBytes, kImgBlockBytes, bar_full + st);
+        }
+        __syncwarp();
+    } else if (warp == 9) {
+        // ---- MMA issue ----
+        const uint32_t sbase = tc::smem_u32(gsm);
+        const uint32_t idesc = tc::instr_desc_f16(128, 128, false);
+#pragma unroll 1
+        for (int ks = 0; ks < ksteps; ++ks) {
+            const int st = ks % kIgStages;
+            tc::mbar_wait(bar_full + st, (ks / kIgStages) & 1);
+            tc::tc_fence_after();
+            const uint32_t pa = sbase + st * kIgStageBytes, pb = pa + kImgBlockBytes;
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                const uint32_t off = kk * 2 * 2048;
+                const uint64_t ah = tc::smem_desc(pa + off, 2048, 128), al = tc::smem_desc(pa + 8192 + off, 2048, 128);
+                const uint64_t bh = tc::smem_desc(pb + off, 2048, 128), bl = tc::smem_desc(pb + 8192 + off, 2048, 128);
+                tc::mma_ss_elect(tbase, ah, bh, idesc, (ks | kk) != 0 ? 1u : 0u);
+                tc::mma_ss_elect(tbase, al, bh, idesc, 1u);
+                tc::mma_ss_elect(tbase, ah, bl, idesc, 1u);
+            }
+            tc::mma_commit_elect(bar_empty + st);
+        }
+        tc::mma_commit_elect(bar_acc);
+        __syncwarp();
+    } else {
+        // ---- epilogue: thread = output row (TMEM lane), warps 0-3 columns 0-63, warps 4-7 columns 64-127 ----
+        tc::mbar_wait(bar_acc, 0);
+        tc::tc_fence_after();
+        const int half = warp >> 2;
+        const int m = m0 + 32 * (warp & 3) + (tid & 31);
+        const uint32_t ta = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
+#pragma unroll 1
+        for (int c0 = 64 * half; c0 < 64 * half + 64; c0 += 16) {
+            uint32_t r[16];
+            tc::tmem_ld16(ta + c0, r);
+            tc::tc_wait_ld();
+            if (m >= g.M) continue;
+            if (n0 + c0 >= g.N) break;                       // N is a multiple of 16 (tail tile of a 128-column grid)
+            float v[16];
+            const float* rp = g.R ? g.R + (size_t)(g.rmod > 0 ? m % g.rmod : m) * g.ldr + n0 + c0 : nullptr;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float x = __uint_as_float(r[j]);
+                if (g.bias) x += __ldg(g.bias + n0 + c0 + j);
+                if (g.act == ACT_RELU) x = x < 0.f ? 0.f : x;
+                else if (g.act == ACT_HSWISH) x = hardswish_exact(x);
+                else if (g.act == ACT_GELU) x = 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+                if (rp) x += rp[j];
+                v[j] = x;
+            }
+            if (g.C) {
+                const size_t orow = g.c_group > 0 ? (size_t)(m / g.c_group) * g.c_stride + m % g.c_group : (size_t)m;
+                float4* cp = reinterpret_cast<float4*>(g.C + orow * g.ldc + n0 + c0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) cp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            if (g.Cimg) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) tc::split_pack2(v[8 * c + 2 * j], v[8 * c + 2 * j + 1], hi[j], lo[j]);
+                    *reinterpret_cast<uint4*>(g.Cimg + gen_img_offset(m, (n0 + c0) / 8 + c, g.N, 0)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(g.Cimg + gen_img_offset(m, (n0 + c0) / 8 + c, g.N, 1)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tc::tmem_dealloc(tbase, 128);
+}
+
+int run_gemm_img(const ImgGemmArgs& g, cudaStream_t st) {
+    if (g.M <= 0) return 0;
+    if (g.N % 16 != 0 || g.K % 32 != 0 || (g.C && (g.ldc % 4 != 0)) || (g.Cimg && g.N % 32 != 0)) return -1;
+    static DeviceOnce once;
+    if (!ensure_dyn_smem(once, gemm_img_kernel, kIgSmem)) return -1;
+    dim3 grid((g.N + 127) / 128, (g.M + 127) / 128);
+    gemm_img_kernel<<<grid, kIgThreads, kIgSmem, st>>>(g);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// LayerNorm over the last dim C (eps 1e-5), one warp per row (same arithmetic as layernorm_kernel), result written as a split image
+__global__ void __launch_bounds__(256) layernorm_img_kernel(const float* __restrict__ in, uint8_t* __restrict__ img, const float* __restrict__ g,
+                                                           const float* __restrict__ b, int rows, int C) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* x = in + (size_t)row * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += x[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)C;
+    float v = 0.f;
+    for (int c = lane; c < C; c += 32) { const float d = x[c] - mean; v = fmaf(d, d, v); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const float rstd = rsqrtf(v / (float)C + kLnEps);
+    for (int c8 = lane; c8 < C / 8; c8 += 32) {
+        const float4 x0 = *reinterpret_cast<const float4*>(x + 8 * c8), x1 = *reinterpret_cast<const float4*>(x + 8 * c8 + 4);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + 8 * c8)), g1 = __ldg(reinterpret_cast<const float4*>(g + 8 * c8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + 8 * c8)), b1 = __ldg(reinterpret_cast<const float4*>(b + 8 * c8 + 4));
+        const float y[8] = {(x0.x - mean) * rstd * g0.x + b0.x, (x0.y - mean) * rstd * g0.y + b0.y, (x0.z - mean) * rstd * g0.z + b0.z,
+                            (x0.w - mean) * rstd * g0.w + b0.w, (x1.x - mean) * rstd * g1.x + b1.x, (x1.y - mean) * rstd * g1.y + b1.y,
+                            (x1.z - mean) * rstd * g1.z + b1.z, (x1.w - mean) * rstd * g1.w + b1.w};
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tc::split_pack2(y[2 * j], y[2 * j + 1], hi[j], lo[j]);
+        *reinterpret_cast<uint4*>(img + gen_img_offset(row, c8, C, 0)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(img + gen_img_offset(row, c8, C, 1)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+int run_gemm(const GemmArgs& g, int batch, bool nn, cudaStream_t st);
+
+}  // namespace
+
+// Host: W[N][K] fp32 (torch Linear weight) -> split image (rows padded to 128 with zeros).  A few threads: 10^8 elements at C = 768.
+void gen_pack_weight_image(const float* w, int N, int K, uint8_t* img) {
+    const size_t bytes = gen_img_bytes(N, K);
+    memset(img, 0, bytes);
+    auto work = [&](int n_lo, int n_hi) {
+        for (int n = n_lo; n < n_hi; ++n)
+            for (int k = 0; k < K; ++k) {
+                const float v = w[(size_t)n * K + k];
+                const __half hi = __float2half_rn(v);
+                const __half lo = __float2half_rn(v - __half2float(hi));
+                const size_t off = gen_img_offset(n, k / 8, K, 0) + (k % 8) * 2;
+                memcpy(img + off, &hi, 2);
+                memcpy(img + off + 8192, &lo, 2);
+            }
+    };
+    const int nt = 8;
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) th.emplace_back(work, (int)((long long)N * t / nt), (int)((long long)N * (t + 1) / nt));
+    for (auto& t : th) t.join();
+}
+
+namespace {
+
 int run_gemm(const GemmArgs& g, int batch, bool nn, cudaStream_t st) {
     if (g.M <= 0 || g.N <= 0 || batch <= 0) return 0;
     if (gemm_tc_ok(g, nn)) return nn ? launch_gemm_tc<true>(g, batch, st) : launch_gemm_tc<false>(g, batch, st);
+    if (g.Cimg) return -1;                      // the image epilogue exists on the tensor-core kernel only
     dim3 grid((g.N + kBN - 1) / kBN, (g.M + kBM - 1) / kBM, batch);
     if (nn) sgemm_kernel<true><<<grid, 256, 0, st>>>(g);
     else sgemm_kernel<false><<<grid, 256, 0, st>>>(g);
@@ -287,6 +509,43 @@ __global__ void __launch_bounds__(256) im2col3x3_kernel(const float* __restrict_
             v = NCHW ? __ldg(in + ((b * Cin + ci) * H + y) * W + x) : __ldg(in + b * bstride + ((long long)y * W + x) * ld + choff + ci);
         out[i] = v;
     }
+}
+
+// The same patches written as the split image of the [rows][9 Cin] matrix (NHWC input, Cin a multiple of 8: a chunk of 8 consecutive k is
+// 8 consecutive channels of one tap): thread = (row, chunk), two 16-byte loads, one 16-byte store per precision.
+__global__ void __launch_bounds__(256) im2col3x3_img_kernel(const float* __restrict__ in, long long bstride, int ld, int choff, int Cin, int H, int W,
+                                                           int stride, int Ho, int Wo, uint8_t* __restrict__ img, long long rows) {
+    const int K = 9 * Cin, chunks = K / 8, cpt = Cin / 8;
+    const long long total = (rows + 127) / 128 * 128 * chunks;         // the index space covers whole 128-row tiles; rows beyond `rows` are skipped
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        // consecutive threads = consecutive rows of one chunk: the image stores of a warp are contiguous
+        const long long row = (i / (128LL * chunks)) * 128 + (i % 128);
+        const int kc = (int)((i / 128) % chunks);
+        if (row >= rows) continue;
+        const int tap = kc / cpt, ci = (kc % cpt) * 8, ky = tap / 3, kx = tap % 3;
+        const int ox = (int)(row % Wo), oy = (int)((row / Wo) % Ho);
+        const long long b = row / ((long long)Wo * Ho);
+        const int y = stride * oy + ky - 1, x = stride * ox + kx - 1;
+        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+        if (y >= 0 && y < H && x >= 0 && x < W) {
+            const float* p = in + b * bstride + ((long long)y * W + x) * ld + choff + ci;
+            v0 = __ldg(reinterpret_cast<const float4*>(p));
+            v1 = __ldg(reinterpret_cast<const float4*>(p + 4));
+        }
+        uint4 hi, lo;
+        gen_split8(v0, v1, hi, lo);
+        *reinterpret_cast<uint4*>(img + gen_img_offset(row, kc, K, 0)) = hi;
+        *reinterpret_cast<uint4*>(img + gen_img_offset(row, kc, K, 1)) = lo;
+    }
+}
+
+int run_im2col_img(const float* in, long long bstride, int ld, int choff, int Cin, int H, int stride, int n, uint8_t* img, cudaStream_t st) {
+    const int Ho = (H + 2 - 3) / stride + 1;
+    const long long rows = (long long)n * Ho * Ho, total = (rows + 127) / 128 * 128 * (9 * Cin / 8);
+    if (rows <= 0) return 0;
+    const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    im2col3x3_img_kernel<<<blocks, 256, 0, st>>>(in, bstride, ld, choff, Cin, H, H, stride, Ho, Ho, img, rows);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 int run_im2col(bool nchw, const float* in, long long bstride, int ld, int choff, int Cin, int H, int stride, int n, float* out, cudaStream_t st) {
@@ -383,15 +642,17 @@ __global__ void __launch_bounds__(256) gen_decode_kernel(const float* __restrict
 // workspace plan for `chunk` tracks; offsets[i] in floats, order = the pointer members of GenWork
 size_t gen_work_floats(const GenModelW& w, int chunk, size_t* off) {
     const size_t C = w.C, hc = w.hc, n = chunk;
-    const size_t sizes[17] = {
+    const size_t img_rows = ((n * kN + 127) / 128) * 128;
+    const size_t sizes[kGenWorkSlots] = {
         n * 3 * kSx * kSx,                                    // crop
         n * 4096 * 9 * (C / 8) > n * 256 * 9 * C ? n * 4096 * 9 * (C / 8) : n * 256 * 9 * C,   // col (largest: conv2 or head conv1; conv1 is 16384 x 27)
         n * 16384 * (C / 8), n * 4096 * (C / 4), n * 1024 * (C / 2),              // act1..3
         n * kNz * C, n * kN * C, n * kN * C, n * kN * 3 * C,                    // tokz, tok, ln, qkv
         n * w.heads * (size_t)kN * kN, n * kN * C, n * kN * 4 * C,              // scores, attn, hid
-        n * 256 * 3 * hc, n * 256 * 3 * (hc / 2), n * 256 * 3 * (hc / 4), n * 256 * 3 * (hc / 8), n * 256 * 5};   // t1..t4, raw5
+        n * 256 * 3 * hc, n * 256 * 3 * (hc / 2), n * 256 * 3 * (hc / 4), n * 256 * 3 * (hc / 8), n * 256 * 5,    // t1..t4, raw5
+        w.use_img ? img_rows * C : 0, w.use_img ? img_rows * C : 0, w.use_img ? img_rows * 4 * C : 0};           // split images: 4 bytes per element
     size_t tot = 0;
-    for (int i = 0; i < 17; ++i) {
+    for (int i = 0; i < kGenWorkSlots; ++i) {
         size_t s = sizes[i];
         if (i == 1 && s < n * 16384 * 27) s = n * 16384 * 27;
         off[i] = tot;
@@ -410,6 +671,22 @@ int gen_launch_stem(const float* img, int S, int n, const GenModelW& w, const Ge
     int H = S;
     for (int l = 0; l < 4; ++l) {
         const int Ho = H / 2, K = 9 * ch[l];
+        if (l > 0 && w.istem_w[l]) {
+            // patches written as a split image, weights pre-split: the bulk-copy GEMM (no per-tile operand conversion)
+            uint8_t* col_img = reinterpret_cast<uint8_t*>(ws.col);
+            GEN_TRY(run_im2col_img(acts[l - 1], (long long)H * H * ch[l], ch[l], 0, ch[l], H, 2, n, col_img, st));
+            ImgGemmArgs g{};
+            g.A = col_img; g.B = w.istem_w[l]; g.M = n * Ho * Ho; g.N = ch[l + 1]; g.K = K; g.bias = w.stem_b[l];
+            if (l < 3) { g.C = acts[l]; g.ldc = ch[l + 1]; g.act = ACT_HSWISH; }
+            else {
+                g.C = tokens + (size_t)tok_off * C; g.ldc = C; g.act = ACT_NONE;
+                g.R = (S == kSx) ? w.pos_x : w.pos_z; g.ldr = C; g.rmod = Ho * Ho;
+                g.c_group = Ho * Ho; g.c_stride = tok_stride_rows;
+            }
+            GEN_TRY(run_gemm_img(g, st));
+            H = Ho;
+            continue;
+        }
         if (l == 0) GEN_TRY(run_im2col(true, img, 0, 0, 0, 3, H, 2, n, ws.col, st));
         else GEN_TRY(run_im2col(false, acts[l - 1], (long long)H * H * ch[l], ch[l], 0, ch[l], H, 2, n, ws.col, st));
         if (l < 3) {
@@ -438,8 +715,55 @@ int gen_launch_blocks_head(float* tokens, int n, const GenModelW& w, const GenWo
         return cudaGetLastError() == cudaSuccess ? 1 : -1;
     };
     if (taps && cudaMemcpyAsync(taps, tokens, tok_bytes, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return -1;
+    uint8_t* img_ln = reinterpret_cast<uint8_t*>(ws.img_ln);
+    uint8_t* img_attn = reinterpret_cast<uint8_t*>(ws.img_attn);
+    uint8_t* img_hid = reinterpret_cast<uint8_t*>(ws.img_hid);
+    auto ln_img = [&](const float* in, const float* g, const float* b) {
+        layernorm_img_kernel<<<(rows + 7) / 8, 256, 0, st>>>(in, img_ln, g, b, rows, C);
+        return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    };
+    auto lin = [&](const uint8_t* a_img, const uint8_t* w_img, int N, int K, float* out, const float* bias, int act, const float* resid, uint8_t* out_img) {
+        ImgGemmArgs g{};
+        g.A = a_img; g.B = w_img; g.M = rows; g.N = N; g.K = K; g.C = out; g.ldc = N; g.bias = bias; g.R = resid; g.ldr = N; g.act = act; g.Cimg = out_img;
+        return run_gemm_img(g, st);
+    };
     for (int b = 0; b < w.depth; ++b) {
         const GenBlockW& B = w.blk[b];
+        if (w.use_img) {
+            // Linear layers on the split-image GEMM: LayerNorm and the producing epilogues write the next GEMM's A operand in its
+            // shared-memory layout; the attention products (6 % of the block's FLOPs) stay on the converting kernel
+            GEN_TRY(ln_img(tokens, B.ln1g, B.ln1b));
+            GEN_TRY(lin(img_ln, B.iwqkv, 3 * C, C, ws.qkv, B.bqkv, ACT_NONE, nullptr, nullptr));
+            {
+                GemmArgs g = gemm_args(ws.qkv, 3 * C, ws.qkv + C, 3 * C, ws.scores, kN, kN, kN, hd, nullptr, ACT_NONE);
+                g.nh = w.heads;
+                g.sa1 = g.sb1 = (long long)kN * 3 * C; g.sa2 = g.sb2 = hd;
+                g.sc1 = (long long)w.heads * kN * kN; g.sc2 = (long long)kN * kN;
+                g.alpha = 1.f / sqrtf((float)hd);
+                GEN_TRY(run_gemm(g, n * w.heads, false, st));
+            }
+            {
+                const long long srows = (long long)n * w.heads * kN;
+                softmax_rows_kernel<<<(unsigned)((srows + 7) / 8), 256, 0, st>>>(ws.scores, srows, kN);
+                if (cudaGetLastError() != cudaSuccess) return -1;
+                ++total;
+            }
+            {   // attn = P V straight into the image that the output projection reads
+                GemmArgs g = gemm_args(ws.scores, kN, ws.qkv + 2 * C, 3 * C, ws.attn, C, kN, hd, kN, nullptr, ACT_NONE);
+                g.nh = w.heads;
+                g.sa1 = (long long)w.heads * kN * kN; g.sa2 = (long long)kN * kN;
+                g.sb1 = (long long)kN * 3 * C; g.sb2 = hd;
+                g.sc1 = (long long)kN * C; g.sc2 = hd;
+                g.Cimg = img_attn; g.img_K = C; g.img_rows1 = kN; g.img_cols2 = hd;
+                GEN_TRY(run_gemm(g, n * w.heads, true, st));
+            }
+            GEN_TRY(lin(img_attn, B.iwproj, C, C, tokens, B.bproj, ACT_NONE, tokens, nullptr));
+            GEN_TRY(ln_img(tokens, B.ln2g, B.ln2b));
+            GEN_TRY(lin(img_ln, B.iwfc1, 4 * C, C, nullptr, B.bfc1, ACT_GELU, nullptr, img_hid));
+            GEN_TRY(lin(img_hid, B.iwfc2, C, 4 * C, tokens, B.bfc2, ACT_NONE, tokens, nullptr));
+            if (taps && cudaMemcpyAsync(taps + (size_t)(b + 1) * tap_stride, tokens, tok_bytes, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return -1;
+            continue;
+        }
         GEN_TRY(ln(tokens, ws.ln, B.ln1g, B.ln1b));
         GEN_TRY(run_gemm(gemm_args(ws.ln, C, B.wqkv, C, ws.qkv, 3 * C, rows, 3 * C, C, B.bqkv, ACT_NONE), 1, false, st));
         {   // scores[b][h] = (q k^T) * hd^-0.5, batch = track x head
@@ -484,12 +808,28 @@ int gen_launch_blocks_head(float* tokens, int n, const GenModelW& w, const GenWo
     // ---- CENTER head on the 16 x 16 search feature map (tokens 64..319 of every track, NHWC) ----
     const int hc = w.hc, prow = n * 256;
     const int co[5] = {C, hc, hc / 2, hc / 4, hc / 8};
-    GEN_TRY(run_im2col(false, ws.ln + (size_t)kNz * C, (long long)kN * C, C, 0, C, kFeat, 1, n, ws.col, st));
-    GEN_TRY(run_gemm(gemm_args(ws.col, 9 * C, w.head_w1, 9 * C, ws.t1, 3 * hc, prow, 3 * hc, 9 * C, w.head_b1, ACT_RELU), 1, false, st));
+    uint8_t* col_img = reinterpret_cast<uint8_t*>(ws.col);
+    auto conv_img = [&](const float* in, long long bstride, int ld, int choff, int ci, const uint8_t* wimg, const float* bias, float* out, int ldo, int cn) {
+        int r = run_im2col_img(in, bstride, ld, choff, ci, kFeat, 1, n, col_img, st);
+        if (r < 0) return r;
+        ImgGemmArgs g{};
+        g.A = col_img; g.B = wimg; g.M = prow; g.N = cn; g.K = 9 * ci; g.C = out; g.ldc = ldo; g.bias = bias; g.act = ACT_RELU;
+        const int r2 = run_gemm_img(g, st);
+        return r2 < 0 ? r2 : r + r2;
+    };
+    if (w.ihead_w1) GEN_TRY(conv_img(ws.ln + (size_t)kNz * C, (long long)kN * C, C, 0, C, w.ihead_w1, w.head_b1, ws.t1, 3 * hc, 3 * hc));
+    else {
+        GEN_TRY(run_im2col(false, ws.ln + (size_t)kNz * C, (long long)kN * C, C, 0, C, kFeat, 1, n, ws.col, st));
+        GEN_TRY(run_gemm(gemm_args(ws.col, 9 * C, w.head_w1, 9 * C, ws.t1, 3 * hc, prow, 3 * hc, 9 * C, w.head_b1, ACT_RELU), 1, false, st));
+    }
     float* tbuf[4] = {ws.t1, ws.t2, ws.t3, ws.t4};
     for (int l = 1; l < 4; ++l)
         for (int t = 0; t < 3; ++t) {
             const int ci = co[l], cn = co[l + 1];
+            if (w.ihead_w[t][l - 1] && cn % 16 == 0) {
+                GEN_TRY(conv_img(tbuf[l - 1], (long long)256 * 3 * ci, 3 * ci, t * ci, ci, w.ihead_w[t][l - 1], w.head_b[t][l - 1], tbuf[l] + t * cn, 3 * cn, cn));
+                continue;
+            }
             GEN_TRY(run_im2col(false, tbuf[l - 1], (long long)256 * 3 * ci, 3 * ci, t * ci, ci, kFeat, 1, n, ws.col, st));
             GEN_TRY(run_gemm(gemm_args(ws.col, 9 * ci, w.head_w[t][l - 1], 9 * ci, tbuf[l] + t * cn, 3 * cn, prow, cn, 9 * ci, w.head_b[t][l - 1], ACT_RELU), 1, false, st));
         }

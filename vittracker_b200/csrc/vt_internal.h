@@ -276,9 +276,20 @@ int launch_cal_bbox(const float* score, const float* size_map, const float* offs
 constexpr int kGenMaxDepth = 32;
 struct GenBlockW {
     const float *ln1g, *ln1b, *wqkv, *bqkv, *wproj, *bproj, *ln2g, *ln2b, *wfc1, *bfc1, *wfc2, *bfc2;
+    const uint8_t *iwqkv, *iwproj, *iwfc1, *iwfc2;           // split images of the four Linear weights (GenModelW::use_img), else null
 };
+// "Split image" of a K-major GEMM operand X[rows][K] (vt_generic.cu, gemm_img_kernel): fp16 hi | lo in the UMMA no-swizzle layout, one
+// contiguous 16 KB block per (128-row tile, 32-wide K panel) so that a pipeline stage is ONE bulk copy per operand:
+//   byte offset of (r, k, prec) = (((r / 128) * (K / 32) + k / 32) * 2 + prec) * 8192 + ((k / 8) % 4) * 2048 + (r % 128) * 16 + (k % 8) * 2
+constexpr int kImgBlockBytes = 2 * 4 * 128 * 16;
+__host__ __device__ inline size_t gen_img_bytes(long long rows, int K) { return (size_t)((rows + 127) / 128) * (K / 32) * kImgBlockBytes; }
+__host__ __device__ inline size_t gen_img_offset(long long r, int kchunk, int K, int prec) {      // kchunk = k / 8
+    return (((size_t)(r >> 7) * (K >> 5) + (kchunk >> 2)) * 2 + prec) * 8192 + (size_t)(kchunk & 3) * 2048 + (size_t)(r & 127) * 16;
+}
+void gen_pack_weight_image(const float* w, int N, int K, uint8_t* img);     // host: W[N][K] fp32 -> split image
 struct GenModelW {
     int C, heads, depth, hc;
+    int use_img;                                             // Linear layers of the blocks on the split-image GEMM (C % 128 == 0)
     const float* stem_w[4]; const float* stem_b[4];          // [cout][9 cin], [cout]
     GenBlockW blk[kGenMaxDepth];
     const float *norm_g, *norm_b, *pos_z, *pos_x;
@@ -286,12 +297,16 @@ struct GenModelW {
     const float* head_w[3][3]; const float* head_b[3][3];    // [tower][layer 2..4]: [co][9 ci], [co]
     const float* head_w5; const float* head_b5;              // [5][hc / 8] rows ctr, offset x, offset y, size w, size h; [5]
     const float* hann;
+    // split images of the convolution weights ([cout][9 cin] as a [N][K] matrix) for the layers whose cin is a multiple of 32, else null
+    const uint8_t* istem_w[4]; const uint8_t* ihead_w1; const uint8_t* ihead_w[3][3];
 };
 struct GenWork {             // device scratch for `chunk` tracks
     int chunk;
     float *crop, *col, *act1, *act2, *act3, *tokz, *tok, *ln, *qkv, *scores, *attn, *hid, *t1, *t2, *t3, *t4, *raw5;
+    float *img_ln, *img_attn, *img_hid;                      // split images (bytes = 4 per element, rows padded to 128) when use_img
 };
-size_t gen_work_floats(const GenModelW& w, int chunk, size_t* offsets /*[17]*/);
+constexpr int kGenWorkSlots = 20;
+size_t gen_work_floats(const GenModelW& w, int chunk, size_t* offsets /*[kGenWorkSlots]*/);
 // Stem of n images (NCHW fp32, side S) -> tokens[(b * tok_stride_rows + tok_off + t)][C] (+ pos)
 int gen_launch_stem(const float* img, int S, int n, const GenModelW& w, const GenWork& ws, float* tokens, int tok_stride_rows,
                     int tok_off, cudaStream_t st);
