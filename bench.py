@@ -531,7 +531,7 @@ def main():
     ap.add_argument("--total-tracks", type=int, default=0, help="strong sharding: this many tracks split over the GPUs (BASELINE configs[3]: 8192)")
     ap.add_argument("--config", default="vit_48_h32_noKD", choices=["vit_48_h32_noKD", WIDEST["name"]])
     ap.add_argument("--frames", type=int, default=64, help="distinct frames resident per GPU")
-    ap.add_argument("--chunk", type=int, default=0, help="tracks per internal pass (default 1024; 32 for the widest config)")
+    ap.add_argument("--chunk", type=int, default=0, help="tracks per internal pass (default 1024; 128 for the widest config)")
     ap.add_argument("--blocks", default="tcgen05", choices=["simt", "tcgen05", "tcgen05_3term"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
@@ -545,7 +545,7 @@ def main():
     if args.tracks <= 0:
         args.tracks = 512 if widest else 1024
     if args.chunk <= 0:
-        args.chunk = 32 if widest else 1024
+        args.chunk = 128 if widest else 1024
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

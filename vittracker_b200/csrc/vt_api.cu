@@ -397,7 +397,7 @@ int vt_create(const VtConfig* cfg, VtHandle* out) {
     h->cfg = *cfg;
     h->num_sms = prop.multiProcessorCount;
     h->generic = !fast;
-    h->chunk = cfg->chunk_tracks > 0 ? cfg->chunk_tracks : (fast ? 1024 : 8);
+    h->chunk = cfg->chunk_tracks > 0 ? cfg->chunk_tracks : (fast ? 1024 : 64);        // generic path: ~46 MB of workspace per track at C = 768
     if (h->chunk > cfg->max_tracks) h->chunk = cfg->max_tracks;
     DeviceGuard dg(cfg->device);                 // the caller's current device is restored on return
     if (dg.err != cudaSuccess) { delete h; return fail(nullptr, VT_ERR_CUDA, "cudaSetDevice failed"); }
