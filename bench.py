@@ -346,13 +346,15 @@ def bind_rank(local_rank, world):
     return info
 
 
-def h2d_cap(dev, world, mb=177, reps=6):
-    """Pinned host -> HBM copy bandwidth of this rank with EVERY rank copying at once (the e2e leg's limiter): per-rank GB/s."""
+def h2d_cap(dev, world, host_buf, reps=8):
+    """Pinned host -> HBM copy bandwidth of this rank with EVERY rank copying at once (the e2e leg's limiter): per-rank GB/s.
+    `host_buf`: one of the pinned frame pools the e2e leg itself uploads (same pages, same placement)."""
     import torch.distributed as dist
-    n = mb * 1024 * 1024
-    h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h = host_buf.reshape(-1)
+    n = h.numel()
     d = torch.empty(n, dtype=torch.uint8, device=dev)
-    d.copy_(h, non_blocking=True)
+    for _ in range(2):
+        d.copy_(h, non_blocking=True)
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
@@ -642,7 +644,7 @@ def main():
     h2d = F * FRAME_H * FRAME_W * 3 + n * 32
     d2h = host_out.numel() * 8
     # the limiter of that leg, measured: pinned host -> HBM bandwidth with every rank copying at once
-    cap = torch.tensor([h2d_cap(dev, world)], device=dev, dtype=torch.float64)
+    cap = torch.tensor([h2d_cap(dev, world, host_pools[0])], device=dev, dtype=torch.float64)
     cap_all = [torch.zeros_like(cap) for _ in range(world)]
     if world > 1:
         dist.all_gather(cap_all, cap)
