@@ -71,6 +71,29 @@ __device__ __forceinline__ void hardswish_exact_n(float (&v)[N]) {
         for (int i = 0; i < N; ++i) v[i] = __fdiv_rn(p[i], 6.f);
     }
 }
+
+// Hardswish of the tensor-core stem's epilogues: x * relu6(x + 3) * fl(1/6) - within one ulp of the exactly rounded quotient above (the
+// three-term fp16 products these epilogues follow carry 2^-22 already), at a third of the instructions: no correction step, no sign
+// fix-up, no branch.
+template <int N>
+__device__ __forceinline__ void hardswish_n(float (&v)[N]) {
+    static_assert(N % 2 == 0, "pairs");
+    const uint64_t k3 = 0x4040000040400000ull, kr = 0x3e2aaaab3e2aaaabull;   // {3, 3}, {fl(1/6)} x 2
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+        uint64_t x, t, pp;
+        float t0, t1;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(v[i]), "f"(v[i + 1]));
+        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(x), "l"(k3));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(t0), "=f"(t1) : "l"(t));
+        t0 = fminf(fmaxf(t0, 0.f), 6.f);
+        t1 = fminf(fmaxf(t1, 0.f), 6.f);
+        asm("mov.b64 %0, {%1, %2};" : "=l"(t) : "f"(t0), "f"(t1));
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(pp) : "l"(x), "l"(t));
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(pp) : "l"(pp), "l"(kr));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(v[i]), "=f"(v[i + 1]) : "l"(pp));
+    }
+}
 #endif
 
 // ---- packed weights (device, fp32) --------------------------------------------------------------

@@ -485,7 +485,7 @@ size_t stem_scratch_floats(int S) {
     return (size_t)6 * (S / 2) * (S / 2) + (size_t)12 * (S / 4) * (S / 4) + (size_t)24 * (S / 8) * (S / 8);
 }
 
-size_t crop_taps_bytes(int n) { return (size_t)n * 2 * kTapPitch * sizeof(int4); }
+size_t crop_taps_bytes(int n) { return (size_t)n * 2 * kTapPitch * sizeof(int4) + 256; }      // + the fused front's work counter
 
 template <int S, int TCOUT_CCH>
 static int run_crop_conv1(const uint8_t* frames, const int64_t* frame_offsets, const int32_t* frame_hw, const double* boxes,
@@ -494,7 +494,7 @@ static int run_crop_conv1(const uint8_t* frames, const int64_t* frame_offsets, c
     static DeviceOnce once;
     if (!ensure_dyn_smem(once, kern, kCc1SmemBytes)) return -1;
     constexpr int tiles = (S / 64) * (S / 64);
-    crop_taps_kernel<S><<<n, 288, 0, st>>>(frame_hw, boxes, factor, taps, out_status);
+    crop_taps_kernel<S><<<n, 288, 0, st>>>(frame_hw, boxes, factor, taps, out_status, nullptr, 0);
     int launched = 1;
     for (int first = 0; first < n; first += 32768) {
         const int m = min(32768, n - first);

@@ -35,6 +35,19 @@ namespace vt {
 
 using namespace tc;
 
+// Optional cycle trace of one worker thread of CTA 0 (development aid): -DVT_FUSED_TRACE, read back with vt_fused_trace_read().
+#ifdef VT_FUSED_TRACE
+__device__ long long g_fused_trace[8192];
+__device__ int g_fused_trace_n;
+__device__ long long g_fused_cta[1024][4];      // per CTA: globaltimer at kernel entry, loop start, loop end; SM id
+#define FUSED_TRACE()                                                                                                   \
+    do {                                                                                                                \
+        if (blockIdx.x == 0 && threadIdx.x == 511) { int k__ = g_fused_trace_n; if (k__ < 8192) { g_fused_trace[k__] = clock64(); g_fused_trace_n = k__ + 1; } } \
+    } while (0)
+#else
+#define FUSED_TRACE() do {} while (0)
+#endif
+
 namespace {
 
 constexpr int kFThreads = 512;
@@ -44,6 +57,7 @@ template <int BR2>
 struct Fused {
     using C2 = TcConv<kConv2Cch, 12, 16, kConv2Wout, BR2>;       // conv2: band geometry (A operand planes) and weight blob
     static constexpr int kBands = kConv2Wout / BR2;
+    static constexpr int kUnitBands = 4;                          // consecutive bands of one track a CTA takes at a time (work unit)
     static constexpr int kIRows = 4 * BR2 + 3;                    // resized-crop rows of a band
     static constexpr int kA1Rows = 2 * BR2 + 1;                   // conv1 output rows of a band
     static constexpr int kOffI = 0;
@@ -56,7 +70,8 @@ struct Fused {
     static constexpr int kPasses = (C2::kTiles + 1) / 2;
     static constexpr int kXchgFloats = kPasses * 2 * 2 * 2 * 8;   // [pass][tile of the pair][channel half][image row of the tile][8]
     static constexpr int kOffBar = (kOffXchg + kXchgFloats * 4 + 7) / 8 * 8;
-    static constexpr int kSmemBytes = kOffBar + 3 * 8;            // bar1, bar2, TMEM base
+    static constexpr int kSmemBytes = kOffBar + 4 * 8;            // bar1, bar2, TMEM base, next item [2]
+    static_assert(kBands % kUnitBands == 0 && kUnitBands >= 2, "work units");
     static constexpr int kCol2 = kA1Rows * 16;                    // conv2's accumulators follow conv1's
     static constexpr int kCols = kCol2 + C2::kTiles * 32;
     static constexpr int kTmemCols = kCols <= 128 ? 128 : kCols <= 256 ? 256 : 512;
@@ -65,19 +80,22 @@ struct Fused {
 };
 
 // One resized-crop pixel (3 channels) from its 2 x 2 source taps, exactly cv::resize's 8U bilinear (HResize: 11-bit weights, then
-// VResizeLinear) - the arithmetic of crop_conv1_kernel / crop_normalize_kernel - with 0x6400 added: the result is the bit pattern of the
-// fp16 number 1024 + v.  wd: three aligned words per tap row covering the pixel pair's six bytes; sh: byte misalignment * 8.
-__device__ __forceinline__ void bilinear_px3(const uint32_t (&wd)[6], unsigned sh0, unsigned sh1, unsigned wx, int bz, int (&px)[3]) {
+// VResizeLinear: ((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2) - the arithmetic of crop_conv1_kernel /
+// crop_normalize_kernel - with 0x6400 added: the result is the bit pattern of the fp16 number 1024 + v.
+// wd: three aligned words per tap row covering the pixel pair's six bytes; sh: byte misalignment * 8; b0 / b1: the row weights.
+// One permute serves two channels: R0 R1 G0 G1 in one word feeds dp2a.lo (red) and dp2a.hi (green).  (tools/ubench/gather_arith.cu: this
+// arrangement costs 44 issue cycles per pixel and warp against 49 with a permute per channel; multiply-high forms of the vertical
+// pass - (b * (h >> 4)) >> 16 == hi32((h & ~15) * (b << 12)) - are slower, 52 - 69: IMAD.HI is not a full-rate instruction.)
+__device__ __forceinline__ void bilinear_px3(const uint32_t (&wd)[6], unsigned sh0, unsigned sh1, unsigned wx, int b0, int b1, int (&px)[3]) {
     const uint32_t u0 = __funnelshift_r(wd[0], wd[1], sh0), u1 = __funnelshift_r(wd[1], wd[2], sh0);   // R0 G0 B0 R1 | G1 B1 . .
     const uint32_t t0 = __funnelshift_r(wd[3], wd[4], sh1), t1 = __funnelshift_r(wd[4], wd[5], sh1);
-    const int b0 = bz & 0xffff, b1 = (unsigned)bz >> 16;
+    const uint32_t urg = __byte_perm(u0, u1, 0x4130), ubb = __byte_perm(u0, u1, 0x0052);                // R0 R1 G0 G1 | B0 B1 . .
+    const uint32_t trg = __byte_perm(t0, t1, 0x4130), tbb = __byte_perm(t0, t1, 0x0052);
+    const int h0[3] = {(int)__dp2a_lo(wx, urg, 0u), (int)__dp2a_hi(wx, urg, 0u), (int)__dp2a_lo(wx, ubb, 0u)};
+    const int h1[3] = {(int)__dp2a_lo(wx, trg, 0u), (int)__dp2a_hi(wx, trg, 0u), (int)__dp2a_lo(wx, tbb, 0u)};
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-        const unsigned sel = ch == 0 ? 0x0030u : ch == 1 ? 0x0041u : 0x0052u;                           // (first, second) pixel's byte
-        const int h0 = (int)__dp2a_lo(wx, __byte_perm(u0, u1, sel), 0u);
-        const int h1 = (int)__dp2a_lo(wx, __byte_perm(t0, t1, sel), 0u);
-        px[ch] = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + (2 + (0x6400 << 2))) >> 2;       // v + 0x6400, v in [0, 255]
-    }
+    for (int ch = 0; ch < 3; ++ch)
+        px[ch] = (((b0 * (h0[ch] >> 4)) >> 16) + ((b1 * (h1[ch] >> 4)) >> 16) + (2 + (0x6400 << 2))) >> 2;   // v + 0x6400, v in [0, 255]
 }
 // two values (each 0x6400 + v) -> packed fp16 {v_lo, v_hi}: (1024 + v) - 1024 is exact
 __device__ __forceinline__ uint32_t pack_u8_f16x2(int a, int b) {
@@ -92,16 +110,25 @@ template <int BR2>
 __global__ void __launch_bounds__(kFThreads, Fused<BR2>::kCtasPerSm)
 stem12_fused_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict__ frame_offsets, const int4* __restrict__ taps,
                     const uint8_t* __restrict__ w1g, const float* __restrict__ par1g, const uint8_t* __restrict__ w2g,
-                    const float* __restrict__ bias2g, uint8_t* __restrict__ planes3, int n_items) {
+                    const float* __restrict__ bias2g, uint8_t* __restrict__ planes3, int n_units, int* __restrict__ work_counter) {
     using F = Fused<BR2>;
     using C2 = typename F::C2;
     extern __shared__ __align__(128) uint8_t sm[];
+#ifdef VT_FUSED_TRACE
+    if (threadIdx.x == 0 && blockIdx.x < 1024) {
+        long long t; unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_fused_cta[blockIdx.x][0] = t; g_fused_cta[blockIdx.x][3] = smid;
+    }
+#endif
     float* sPar = reinterpret_cast<float*>(sm + F::kOffPar);
     float* sB2 = sPar + kStem1TcParFloats;
     float* sXchg = reinterpret_cast<float*>(sm + F::kOffXchg);
     uint64_t* bar1 = reinterpret_cast<uint64_t*>(sm + F::kOffBar);
     uint64_t* bar2 = bar1 + 1;
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar1 + 2);
+    volatile int* s_next = reinterpret_cast<volatile int*>(bar1 + 3);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // one-off: the zero chunks of the row slots (the whole region is cleared; data chunks are rewritten per item), weights, parameters
@@ -124,60 +151,84 @@ stem12_fused_kernel(const uint8_t* __restrict__ frames, const int64_t* __restric
     const uint32_t sbase = smem_u32(sm);
     const float inv_scale = sPar[32];
 
-    auto gather = [&](int item) {
+    // reuse: the item is the band below the one whose rows are in the slots - its first three rows are that band's last three
+    auto gather = [&](int item, bool reuse) {
         const int b = item / F::kBands, oy0 = (item % F::kBands) * BR2;
         const int i0 = 4 * oy0 - 3;                                   // resized-crop row held by slot 0
         const uint8_t* __restrict__ im = frames + frame_offsets[b];
         const int4* __restrict__ tcol = taps + (size_t)b * 2 * kTapPitch + 1;    // record of resized-crop column d at [d]
         const int4* __restrict__ trow = tcol + kTapPitch;
-        // ---- 1. gather: thread = pixel-pair column x, rows slot = ph, ph + 4, ...; two rows per batch, every load in flight before use
+        // ---- 1. gather: thread = pixel-pair column x, rows slot = s0 + ph + 4 j (j = 0 .. 4).  The rows go through two register sets as a
+        // rolling pipeline - the loads of row j + 2 are issued as soon as row j has been consumed - so a thread always has one row of taps
+        // in flight while it does the arithmetic of the other, instead of waiting out a full memory round trip per batch.
         {
             const int x = tid & 127, ph = tid >> 7;
             const int4 c0 = __ldg(tcol + 2 * x), c1 = __ldg(tcol + 2 * x + 1);
-            const uint8_t* __restrict__ colp0 = im + c0.x;
-            const uint8_t* __restrict__ colp1 = im + c1.x;
+            // byte offsets are taken from the frame's word-aligned base: address = one wide multiply-add, misalignment = the offset's low bits
+            const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(im) & 3u);
+            const uint32_t* __restrict__ imw = reinterpret_cast<const uint32_t*>(im - mis);
+            const unsigned colx[2] = {(unsigned)c0.x + mis, (unsigned)c1.x + mis};
             const unsigned wx0 = (unsigned)c0.y, wx1 = (unsigned)c1.y;
             uint8_t* dst = sm + F::kOffI + 16 * (x + 1);
-#pragma unroll 1
-            for (int s = ph; s < F::kIRows; s += 8) {
-                uint32_t wd[2][2][6];
-                unsigned sh[2][2][2];
-                int bz[2];
-                bool live[2];
+            if (reuse && ph > 0)      // slot 15 + ph moves to slot ph - 1; the same thread rewrites slot 15 + ph afterwards (program order)
+                *reinterpret_cast<uint4*>(dst + (ph - 1) * kIPitch) = *reinterpret_cast<const uint4*>(dst + (15 + ph) * kIPitch);
+            struct Row {
+                uint32_t wd[2][6];
+                unsigned sh[2][2];
+                unsigned bz;
+            };
+            auto live = [&](int slot) { return slot < F::kIRows && i0 + slot >= 0; };     // warp-uniform
+            auto load = [&](Row& r, int slot) {
+                if (live(slot)) {
+                    const int4 rt = __ldg(trow + i0 + slot);
+                    r.bz = (unsigned)rt.z;
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const int slot = s + 4 * k;
-                    live[k] = slot < F::kIRows && i0 + slot >= 0;                         // warp-uniform
-                    if (live[k]) {
-                        const int4 rt = __ldg(trow + i0 + slot);
-                        bz[k] = rt.z;
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const uint8_t* cp = j == 0 ? colp0 : colp1;
-                            const uintptr_t q0 = reinterpret_cast<uintptr_t>(cp + (unsigned)rt.x);
-                            const uintptr_t q1 = reinterpret_cast<uintptr_t>(cp + (unsigned)rt.y);
-                            const uint32_t* p0 = reinterpret_cast<const uint32_t*>(q0 & ~static_cast<uintptr_t>(3));
-                            const uint32_t* p1 = reinterpret_cast<const uint32_t*>(q1 & ~static_cast<uintptr_t>(3));
-                            wd[k][j][0] = __ldg(p0); wd[k][j][1] = __ldg(p0 + 1); wd[k][j][2] = __ldg(p0 + 2);
-                            wd[k][j][3] = __ldg(p1); wd[k][j][4] = __ldg(p1 + 1); wd[k][j][5] = __ldg(p1 + 2);
-                            sh[k][j][0] = (unsigned)q0 << 3; sh[k][j][1] = (unsigned)q1 << 3;   // the funnel shift takes the amount mod 32
-                        }
+                    for (int j = 0; j < 2; ++j) {
+                        const unsigned q0 = colx[j] + (unsigned)rt.x, q1 = colx[j] + (unsigned)rt.y;
+                        const uint32_t* p0 = imw + (q0 >> 2);
+                        const uint32_t* p1 = imw + (q1 >> 2);
+                        r.wd[j][0] = __ldg(p0); r.wd[j][1] = __ldg(p0 + 1); r.wd[j][2] = __ldg(p0 + 2);
+                        r.wd[j][3] = __ldg(p1); r.wd[j][4] = __ldg(p1 + 1); r.wd[j][5] = __ldg(p1 + 2);
+                        r.sh[j][0] = q0 << 3; r.sh[j][1] = q1 << 3;                       // the funnel shift takes the amount mod 32
                     }
                 }
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const int slot = s + 4 * k;
-                    if (live[k]) {
-                        int pa[3], pb[3];
-                        bilinear_px3(wd[k][0], sh[k][0][0], sh[k][0][1], wx0, bz[k], pa);
-                        bilinear_px3(wd[k][1], sh[k][1][0], sh[k][1][1], wx1, bz[k], pb);
-                        *reinterpret_cast<uint4*>(dst + slot * kIPitch) =
-                            make_uint4(pack_u8_f16x2(pa[0], pa[1]), pack_u8_f16x2(pa[2], pb[0]), pack_u8_f16x2(pb[1], pb[2]), 0u);
-                    } else if (slot < F::kIRows && i0 + slot == -1) {
-                        *reinterpret_cast<uint4*>(dst + slot * kIPitch) = make_uint4(0u, 0u, 0u, 0u);     // the convolution's zero row above the crop
-                    }
+            };
+            auto finish = [&](const Row& r, int slot) {
+                if (live(slot)) {
+                    int pa[3], pb[3];
+                    const int b0 = (int)(r.bz & 0xffffu), b1 = (int)(r.bz >> 16);
+                    bilinear_px3(r.wd[0], r.sh[0][0], r.sh[0][1], wx0, b0, b1, pa);
+                    bilinear_px3(r.wd[1], r.sh[1][0], r.sh[1][1], wx1, b0, b1, pb);
+                    *reinterpret_cast<uint4*>(dst + slot * kIPitch) =
+                        make_uint4(pack_u8_f16x2(pa[0], pa[1]), pack_u8_f16x2(pa[2], pb[0]), pack_u8_f16x2(pb[1], pb[2]), 0u);
+                } else if (slot < F::kIRows && i0 + slot == -1) {
+                    *reinterpret_cast<uint4*>(dst + slot * kIPitch) = make_uint4(0u, 0u, 0u, 0u);         // the convolution's zero row above the crop
                 }
-            }
+            };
+            static_assert(F::kIRows <= 20, "five rows per thread");
+            const int s0 = (reuse ? 3 : 0) + ph;
+            Row ra, rb;
+            load(ra, s0);
+            load(rb, s0 + 4);
+            finish(ra, s0);
+            load(ra, s0 + 8);
+            finish(rb, s0 + 4);
+            load(rb, s0 + 12);
+            finish(ra, s0 + 8);
+            load(ra, s0 + 16);
+            finish(rb, s0 + 12);
+            finish(ra, s0 + 16);
+        }
+    };
+    // The tap records of a later item, pulled into L1 one phase ahead: the gather's first two loads (column record, row record) head a
+    // dependent chain (record -> pixel addresses -> pixels) that every warp of the CTA walks at the same time.
+    auto prefetch_taps = [&](int item) {
+        if (tid >= 32 && tid < 72) {
+            const int b = item / F::kBands, oy0 = (item % F::kBands) * BR2;
+            const int4* tcol = taps + (size_t)b * 2 * kTapPitch;
+            const int l = tid - 32;
+            const int4* p = l < 34 ? tcol + 8 * l : tcol + kTapPitch + max(4 * oy0 - 3, 0) + 8 * (l - 34);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
         }
     };
     auto issue_conv1 = [&](int item) {
@@ -219,7 +270,7 @@ stem12_fused_kernel(const uint8_t* __restrict__ frames, const int64_t* __restric
                 float v[6];
 #pragma unroll
                 for (int c = 0; c < 6; ++c) v[c] = fmaf(__uint_as_float(acc[c]) + __uint_as_float(acc[8 + c]), inv_scale, bv[c]);
-                hardswish_exact_n<6>(v);
+                hardswish_n<6>(v);
                 uint32_t hi[4], lo[4];
 #pragma unroll
                 for (int j = 0; j < 3; ++j) split_pack2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
@@ -309,7 +360,7 @@ stem12_fused_kernel(const uint8_t* __restrict__ frames, const int64_t* __restric
                     if (ox == 0) tb = 0.f;
                     v[j] = __uint_as_float(ra[pass][j]) + tb + sB2[8 * half + j];
                 }
-                hardswish_exact_n<8>(v);
+                hardswish_n<8>(v);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     if (8 * half + j >= 12) v[j] = 0.f;                             // padding channels stay exactly zero
@@ -327,46 +378,84 @@ stem12_fused_kernel(const uint8_t* __restrict__ frames, const int64_t* __restric
     // Hazards (program order per thread + the two barriers): conv2's accumulators of i - 1 are read (E2) before the barrier that precedes
     // conv2(i); conv1's accumulators are read (E1) before the barrier that precedes conv1(i + 1); the row slots are rewritten (G(i + 1)) after
     // every thread has waited for conv1(i); the plane image is rewritten (E1(i + 1)) after every thread has waited for conv2(i).
+    // Work distribution: a unit = kUnitBands consecutive bands of one track.  CTAs take their first unit by index and every further one from
+    // a global counter (crop_taps_kernel resets it to gridDim.x): items differ in cost with the crop's scale and position, and a static
+    // round-robin leaves the slowest CTA 10 % behind the mean.  The successor of the NEXT item is fetched by one thread during the gather
+    // phase, so the atomic's round trip is never waited for.
+    auto successor = [&](int x) -> int {
+        if (x < 0) return -1;
+        if (x % F::kUnitBands != F::kUnitBands - 1) return x + 1;
+        const int u = atomicAdd(work_counter, 1);
+        return u < n_units ? u * F::kUnitBands : -1;
+    };
     int it = 0, prev = -1;
-    if ((int)blockIdx.x < n_items) gather(blockIdx.x);
+    int item = (int)blockIdx.x < n_units ? (int)blockIdx.x * F::kUnitBands : -1;
+#ifdef VT_FUSED_TRACE
+    if (threadIdx.x == 0 && blockIdx.x < 1024) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_fused_cta[blockIdx.x][1] = t; }
+#endif
+    if (tid == 480) s_next[0] = successor(item);
+    if (item >= 0) gather(item, false);
 #pragma unroll 1
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    for (; item >= 0; ++it) {
+        FUSED_TRACE();
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
+        FUSED_TRACE();
+        const int nxt = s_next[it & 1];
         issue_conv1(item);
+        if (nxt >= 0) prefetch_taps(nxt);
         if (prev >= 0) {
             mbar_wait(bar2, (it - 1) & 1);
             tc_fence_after();
+            FUSED_TRACE();
             epilogue2(prev);
+        } else {
+            FUSED_TRACE();
         }
+        FUSED_TRACE();
         mbar_wait(bar1, it & 1);
         tc_fence_after();
+        FUSED_TRACE();
         epilogue1(item);
+        FUSED_TRACE();
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
+        FUSED_TRACE();
         issue_conv2();
-        if (item + (int)gridDim.x < n_items) gather(item + gridDim.x);
+        if (tid == 480) s_next[(it + 1) & 1] = successor(nxt);
+        if (nxt >= 0) gather(nxt, nxt == item + 1 && nxt % F::kBands != 0);
+        FUSED_TRACE();
         prev = item;
+        item = nxt;
     }
     if (prev >= 0) {
         mbar_wait(bar2, (it - 1) & 1);
         tc_fence_after();
         epilogue2(prev);
     }
+#ifdef VT_FUSED_TRACE
+    if (threadIdx.x == 0 && blockIdx.x < 1024) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_fused_cta[blockIdx.x][2] = t; }
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tbase, F::kTmemCols);
 }
 
-template <int BR2>
-static int run_fused(const uint8_t* frames, const int64_t* frame_offsets, const int4* taps, int n, const ModelW& w, uint8_t* planes3,
-                     cudaStream_t st) {
-    using F = Fused<BR2>;
-    auto kern = stem12_fused_kernel<BR2>;
+#ifndef VT_FUSED_BR
+#define VT_FUSED_BR 4
+#endif
+
+// Search crop of n tracks straight from the raw frames -> conv3's operand image (planes3): tap tables + the fused kernel.
+// tap_tables: crop_taps_bytes(n) bytes; the fused kernel's work counter sits behind the n tables.
+int launch_crop_stem12_fused(const uint8_t* frames, const int64_t* frame_offsets, const int32_t* frame_hw, const double* boxes, double factor,
+                             int n, const ModelW& w, int32_t* out_status, void* tap_tables, uint8_t* planes3, cudaStream_t st) {
+    if (n <= 0) return 0;
+    using F = Fused<VT_FUSED_BR>;
+    auto kern = stem12_fused_kernel<VT_FUSED_BR>;
     static int grid_caps[kMaxDevices] = {};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
@@ -376,27 +465,17 @@ static int run_fused(const uint8_t* frames, const int64_t* frame_offsets, const 
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
         grid_caps[dev] = sms * resident_ctas_per_sm(kern, kFThreads, F::kSmemBytes, F::kTmemCols, dev);
     }
-    const long long items = (long long)n * F::kBands;
-    if (items > 0x7fffffffLL) return -1;
-    const int grid = items < grid_caps[dev] ? (int)items : grid_caps[dev];
-    kern<<<grid, kFThreads, F::kSmemBytes, st>>>(frames, frame_offsets, taps, w.stem1_tc_w, w.stem1_tc_par, w.stem_tc_w[0], w.stem_tc_b[0],
-                                                 planes3, (int)items);
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
-}
-
-#ifndef VT_FUSED_BR
-#define VT_FUSED_BR 4
-#endif
-
-// Search crop of n tracks straight from the raw frames -> conv3's operand image (planes3): tap tables + the fused kernel.
-int launch_crop_stem12_fused(const uint8_t* frames, const int64_t* frame_offsets, const int32_t* frame_hw, const double* boxes, double factor,
-                             int n, const ModelW& w, int32_t* out_status, void* tap_tables, uint8_t* planes3, cudaStream_t st) {
-    if (n <= 0) return 0;
+    const long long units = (long long)n * (F::kBands / F::kUnitBands);
+    if (units * F::kUnitBands > 0x7fffffffLL) return -1;
+    const int n_units = (int)units;
+    const int grid = n_units < grid_caps[dev] ? n_units : grid_caps[dev];
     int4* taps = reinterpret_cast<int4*>(tap_tables);
-    crop_taps_kernel<kSx><<<n, 288, 0, st>>>(frame_hw, boxes, factor, taps, out_status);
+    int* work_counter = reinterpret_cast<int*>(taps + (size_t)n * 2 * kTapPitch);
+    crop_taps_kernel<kSx><<<n, 288, 0, st>>>(frame_hw, boxes, factor, taps, out_status, work_counter, grid);
     if (cudaGetLastError() != cudaSuccess) return -1;
-    const int r = run_fused<VT_FUSED_BR>(frames, frame_offsets, taps, n, w, planes3, st);
-    return r < 0 ? r : r + 1;
+    kern<<<grid, kFThreads, F::kSmemBytes, st>>>(frames, frame_offsets, taps, w.stem1_tc_w, w.stem1_tc_par, w.stem_tc_w[0], w.stem_tc_b[0],
+                                                 planes3, n_units, work_counter);
+    return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }
 
 // Host side: conv1's folded weights [ci][ky][kx][co] (BatchNorm folded, fp32) + bias -> the kernel's operands.
@@ -452,6 +531,18 @@ void stem1_tc_pack(const float* wf, const float* bf, uint8_t* blob, float* par, 
     par[32] = (float)ldexp(1.0, -s);
     for (int i = 33; i < kStem1TcParFloats; ++i) par[i] = 0.f;
 }
+
+#ifdef VT_FUSED_TRACE
+extern "C" int vt_fused_trace_read(long long* host, int* n) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(n, g_fused_trace_n, sizeof(int));
+    cudaMemcpyFromSymbol(host, g_fused_trace, sizeof(long long) * 8192);
+    cudaMemcpyFromSymbol(host + 8192, g_fused_cta, sizeof(long long) * 4096);
+    int zero = 0;
+    cudaMemcpyToSymbol(g_fused_trace_n, &zero, sizeof zero);
+    return 0;
+}
+#endif
 
 }  // namespace vt
 

@@ -168,7 +168,7 @@ conv_s2_tc_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wt
                         if (ox == 0) tb = 0.f;
                         v[j] = __uint_as_float(ra[j]) + tb + sBias[chb + c0 + j];
                     }
-                    if (HSWISH) hardswish_exact_n<8>(v);
+                    if (HSWISH) hardswish_n<8>(v);
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         if (chb + c0 + j >= COUT) v[j] = 0.f;                           // padding channels stay exactly zero
