@@ -23,6 +23,7 @@
 //   3. epilogue 1: (hi + lo) * 2^-s + bias variant, Hardswish, fp16 hi/lo split -> conv2's parity-plane operand image in shared memory.
 //   4. conv2 + epilogue 2: as conv_s2_tc_kernel (vt_stem_tc.cu), reading that image; writes conv3's operand image to global memory.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "vt_geom.cuh"
@@ -57,7 +58,7 @@ template <int BR2>
 struct Fused {
     using C2 = TcConv<kConv2Cch, 12, 16, kConv2Wout, BR2>;       // conv2: band geometry (A operand planes) and weight blob
     static constexpr int kBands = kConv2Wout / BR2;
-    static constexpr int kUnitBands = 4;                          // consecutive bands of one track a CTA takes at a time (work unit)
+    static constexpr int kUnitBands = 4;                          // consecutive bands of one track a CTA takes at a time (work unit), at most
     static constexpr int kIRows = 4 * BR2 + 3;                    // resized-crop rows of a band
     static constexpr int kA1Rows = 2 * BR2 + 1;                   // conv1 output rows of a band
     static constexpr int kOffI = 0;
@@ -110,7 +111,8 @@ template <int BR2>
 __global__ void __launch_bounds__(kFThreads, Fused<BR2>::kCtasPerSm)
 stem12_fused_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict__ frame_offsets, const int4* __restrict__ taps,
                     const uint8_t* __restrict__ w1g, const float* __restrict__ par1g, const uint8_t* __restrict__ w2g,
-                    const float* __restrict__ bias2g, uint8_t* __restrict__ planes3, int n_units, int* __restrict__ work_counter) {
+                    const float* __restrict__ bias2g, uint8_t* __restrict__ planes3, int n_units, int unit_bands,
+                    int* __restrict__ work_counter) {
     using F = Fused<BR2>;
     using C2 = typename F::C2;
     extern __shared__ __align__(128) uint8_t sm[];
@@ -378,18 +380,18 @@ stem12_fused_kernel(const uint8_t* __restrict__ frames, const int64_t* __restric
     // Hazards (program order per thread + the two barriers): conv2's accumulators of i - 1 are read (E2) before the barrier that precedes
     // conv2(i); conv1's accumulators are read (E1) before the barrier that precedes conv1(i + 1); the row slots are rewritten (G(i + 1)) after
     // every thread has waited for conv1(i); the plane image is rewritten (E1(i + 1)) after every thread has waited for conv2(i).
-    // Work distribution: a unit = kUnitBands consecutive bands of one track.  CTAs take their first unit by index and every further one from
+    // Work distribution: a unit = unit_bands (a power of two <= kUnitBands) consecutive bands of one track.  CTAs take their first unit by index and every further one from
     // a global counter (crop_taps_kernel resets it to gridDim.x): items differ in cost with the crop's scale and position, and a static
     // round-robin leaves the slowest CTA 10 % behind the mean.  The successor of the NEXT item is fetched by one thread during the gather
     // phase, so the atomic's round trip is never waited for.
     auto successor = [&](int x) -> int {
         if (x < 0) return -1;
-        if (x % F::kUnitBands != F::kUnitBands - 1) return x + 1;
+        if ((x & (unit_bands - 1)) != unit_bands - 1) return x + 1;
         const int u = atomicAdd(work_counter, 1);
-        return u < n_units ? u * F::kUnitBands : -1;
+        return u < n_units ? u * unit_bands : -1;
     };
     int it = 0, prev = -1;
-    int item = (int)blockIdx.x < n_units ? (int)blockIdx.x * F::kUnitBands : -1;
+    int item = (int)blockIdx.x < n_units ? (int)blockIdx.x * unit_bands : -1;
 #ifdef VT_FUSED_TRACE
     if (threadIdx.x == 0 && blockIdx.x < 1024) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_fused_cta[blockIdx.x][1] = t; }
 #endif
@@ -465,8 +467,12 @@ int launch_crop_stem12_fused(const uint8_t* frames, const int64_t* frame_offsets
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
         grid_caps[dev] = sms * resident_ctas_per_sm(kern, kFThreads, F::kSmemBytes, F::kTmemCols, dev);
     }
-    const long long units = (long long)n * (F::kBands / F::kUnitBands);
-    if (units * F::kUnitBands > 0x7fffffffLL) return -1;
+    // few tracks (the batch-1 latency path): single bands, so that a track spreads over kBands CTAs instead of kBands / kUnitBands
+    static const int forced = [] { const char* e = getenv("VT_FUSED_UNIT_BANDS"); return e ? atoi(e) : 0; }();      // A / B aid: 1, 2 or 4
+    const int unit_bands = (forced == 1 || forced == 2 || forced == 4) ? forced
+                           : (long long)n * (F::kBands / F::kUnitBands) >= 2LL * grid_caps[dev] ? F::kUnitBands : 1;
+    const long long units = (long long)n * (F::kBands / unit_bands);
+    if (units * unit_bands > 0x7fffffffLL) return -1;
     const int n_units = (int)units;
     const int grid = n_units < grid_caps[dev] ? n_units : grid_caps[dev];
     int4* taps = reinterpret_cast<int4*>(tap_tables);
@@ -474,7 +480,7 @@ int launch_crop_stem12_fused(const uint8_t* frames, const int64_t* frame_offsets
     crop_taps_kernel<kSx><<<n, 288, 0, st>>>(frame_hw, boxes, factor, taps, out_status, work_counter, grid);
     if (cudaGetLastError() != cudaSuccess) return -1;
     kern<<<grid, kFThreads, F::kSmemBytes, st>>>(frames, frame_offsets, taps, w.stem1_tc_w, w.stem1_tc_par, w.stem_tc_w[0], w.stem_tc_b[0],
-                                                 planes3, n_units, work_counter);
+                                                 planes3, n_units, unit_bands, work_counter);
     return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }
 
