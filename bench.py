@@ -831,7 +831,8 @@ def latency_b1(cfg, sd, frames_n=8, iters=10000, burst=8):
         lat.append(time.perf_counter() - t0)
     lat = np.array(lat[20:]) * 1e3
     out = {"p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)), "frames": iters,
-           "path": "Vit_dist.track(): host frame rows H2D + crop + forward + decode + D2H, blocking"}
+           "path": "Vit_dist.track(): host frame rectangle H2D + crop + forward + decode + D2H, blocking",
+           "cuda_graph": getattr(trk, "_graph", None) is not None}
     n_bursts = iters // 40
     if n_bursts > 0 and burst > 0:
         try:

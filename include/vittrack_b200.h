@@ -190,6 +190,17 @@ int64_t vt_launch_count(VtHandle h);
 int vt_profile_enable(VtHandle h, int32_t enable);
 int vt_profile_read(VtHandle h, double* stage_ms, int64_t* stage_launches, int64_t* stage_items);
 
+/* Host frame -> device frame buffer, only the rectangle a crop reads.  `image` is a host HxWx3 uint8 frame (pageable memory is
+ * fine), `frame_dev` the device buffer holding the frame at the same layout (byte offset (y * W + x) * 3), `staging` a pinned host
+ * buffer and `staging_dev` a device buffer (may be NULL: one strided host -> device copy instead, at about half the rate) of at
+ * least (y1 - y0) * (x1 - x0) * 3 bytes each.  Rows [y0, y1) x columns [x0, x1) are packed into `staging` by a few host threads, cross
+ * the link as one contiguous copy and are spread over the frame's rows on the device, all on `stream`.  The rest of `frame_dev` is
+ * left as it is: sample_target (lib/train/data/processing_utils.py:34-48) slices im[y1:y2, x1:x2] and reads nothing else, and the
+ * crop kernels read nothing else with a non-zero weight (vt_tracks_step's row guarantee, plus columns [x0, x1) and the first two
+ * pixels of a row, whose weight is zero).  `staging` and `staging_dev` may be reused once `stream` has passed the copies. */
+int vt_upload_frame_rect(const uint8_t* image, int32_t H, int32_t W, int32_t y0, int32_t y1, int32_t x0, int32_t x1,
+                         uint8_t* staging, uint8_t* staging_dev, uint8_t* frame_dev, void* stream);
+
 /* Development aid: which profiled stage launches (vt_profile_enable) have started / finished.  Non-blocking;
  * meant for a watchdog thread while the owning thread waits in a synchronisation (tools/hang_probe.py,
  * tests/test_gpu_soak.py).  out[i] = stage * 4 + (started ? 1 : 0) + (finished ? 2 : 0); returns the count. */

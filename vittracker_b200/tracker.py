@@ -80,6 +80,7 @@ class Vit_dist(BaseTracker):
         self._hw_dev = torch.zeros((1, 2), dtype=torch.int32, device=dev)
         self._off_dev = torch.zeros((1,), dtype=torch.int64, device=dev)
         self._box_pin = self._pinned(torch.zeros((1, 4), dtype=torch.float64))
+        self._box_np = self._box_pin.numpy()                      # the same memory, written without tensor indexing
         self._box_dev = torch.zeros((1, 4), dtype=torch.float64, device=dev)
         self._out_dev = torch.zeros((13,), dtype=torch.float64, device=dev)
         self._out_pin = self._pinned(torch.zeros((13,), dtype=torch.float64))
@@ -102,27 +103,40 @@ class Vit_dist(BaseTracker):
         image = np.ascontiguousarray(image)
         H, W, _ = image.shape
         if (H, W) != self._hw:
-            self._frame_dev = torch.empty((H * W * 3,), dtype=torch.uint8, device=self._dev)
+            # zero-filled: the crop kernels read the first pixels of a row with weight 0 for taps in the padding
+            self._frame_dev = torch.zeros((H * W * 3,), dtype=torch.uint8, device=self._dev)
             self._frame_pin = self._pinned(torch.empty((H * W * 3,), dtype=torch.uint8))
+            self._frame_stage = torch.empty((H * W * 3,), dtype=torch.uint8, device=self._dev)
             self._hw_dev.copy_(torch.tensor([[H, W]], dtype=torch.int32))
             self._hw = (H, W)
         x, y, w, h = [float(v) for v in box]
         crop_sz = math.ceil(math.sqrt(w * h) * factor)          # processing_utils.py:30
         if crop_sz < 1:
             raise Exception('Too small bounding box.')          # processing_utils.py:32-33
+        # only the rectangle sample_target slices (processing_utils.py:34-48: im[y1:y2, x1:x2]) is staged and sent; one spare column
+        # on either side keeps the host's and the device's rounding of x1 from ever disagreeing about a boundary pixel
+        x1 = round(x + 0.5 * w - crop_sz * 0.5)
         y1 = round(y + 0.5 * h - crop_sz * 0.5)
         ya, yb = max(0, y1), min(H, y1 + crop_sz)
-        if yb <= ya:
+        xa, xb = max(0, x1 - 1), min(W, x1 + crop_sz + 1)
+        if yb <= ya or xb <= xa:
             raise ValueError("crop lies outside the image (undefined in the reference)")
-        a, b = ya * W * 3, yb * W * 3
-        self._frame_pin[a:b].copy_(torch.from_numpy(image.reshape(-1)[a:b]))
-        self._frame_dev[a:b].copy_(self._frame_pin[a:b], non_blocking=True)
+        if self._dev.type == "cuda":
+            with torch.cuda.device(self._dev):
+                rc = self.engine.lib.vt_upload_frame_rect(image.ctypes.data, H, W, ya, yb, xa, xb, self._frame_pin.data_ptr(),
+                                                          self._frame_stage.data_ptr(), self._frame_dev.data_ptr(),
+                                                          torch.cuda.current_stream(self._dev).cuda_stream)
+            if rc != 0:
+                raise RuntimeError(f"vt_upload_frame_rect failed ({rc})")
+        else:
+            a, b = ya * W * 3, yb * W * 3
+            self._frame_dev[a:b].copy_(torch.from_numpy(image.reshape(-1)[a:b]))
         return H, W, crop_sz
 
-    def _set_box(self, box):
-        for i in range(4):
-            self._box_pin[0, i] = float(box[i])
-        self._box_dev.copy_(self._box_pin, non_blocking=True)
+    def _set_box(self, box, upload: bool = True):
+        self._box_np[0, :] = [float(v) for v in box]
+        if upload:
+            self._box_dev.copy_(self._box_pin, non_blocking=True)
 
     # ------------------------------------------------------------------------------------------
     def initialize(self, image, info: dict):
@@ -157,12 +171,12 @@ class Vit_dist(BaseTracker):
         self.frame_id += 1
         H, W, crop_sz = self._upload(image, self.state, self.params.search_factor)
         resize_factor = self.params.search_size / crop_sz       # processing_utils.py:67
-        self._set_box(self.state)
+        self._set_box(self.state, upload=False)
         self._step_device()
-        self._out_pin.copy_(self._out_dev, non_blocking=True)
-        # `confidence` is a 0-dim tensor on the model's device, as the reference's `score_map.max()` is (vit_dist.py:147-148)
-        confidence = self._out_dev[4].to(torch.float32)
         self._sync()
+        # `confidence` is a 0-dim tensor on the model's device, as the reference's `score_map.max()` is (vit_dist.py:147-148); the
+        # conversion is queued behind the step and never waited for
+        confidence = self._out_dev[4].to(torch.float32)
         out = self._out_pin.tolist()
         if int(out[11]) == 1:
             raise Exception('Too small bounding box.')
@@ -177,13 +191,16 @@ class Vit_dist(BaseTracker):
         return {"target_bbox": self.state, "confidence": confidence}
 
     def _step_device(self) -> None:
-        """State upload + one tracking step for the single track.  Every buffer involved is allocated once (frame buffer, box, frame
-        size, outputs), so after the first frames the kernel sequence is captured in a CUDA graph and replayed: one graph launch
-        instead of a device copy + the step's kernel launches.  params.cuda_graph = False keeps plain launches."""
+        """State upload + one tracking step + result download for the single track.  Every buffer involved is allocated once (frame
+        buffer, pinned box, frame size, outputs, pinned result), so after the first frames the whole sequence - box H2D, the step's
+        kernels, result D2H - is captured in a CUDA graph and replayed: one graph launch per frame.
+        params.cuda_graph = False keeps plain launches."""
         def launch():
+            self._box_dev.copy_(self._box_pin, non_blocking=True)
             self.engine.tracks_set_state(self._box_dev, first=0)
             self.engine.tracks_step(self._frame_dev, self._off_dev, self._hw_dev, first=0, n=1, out_boxes=self._out_boxes,
                                     out_detail=self._out_detail, update_state=False, detail=True)
+            self._out_pin.copy_(self._out_dev, non_blocking=True)
         use_graph = self._dev.type == "cuda" and getattr(self.params, "cuda_graph", True)
         key = (self._hw, self._frame_dev.data_ptr() if self._frame_dev is not None else 0)
         if use_graph and getattr(self, "_graph_key", None) == key and self._graph is not None:
