@@ -154,3 +154,31 @@ def test_run_sequences_against_oracle_tracker(tmp_path):
         on_disk = np.loadtxt(os.path.join(str(tmp_path), s.name + ".txt"), delimiter="\t")
         want_int = np.array(want).astype(int)
         assert on_disk.shape == want_int.shape and np.abs(on_disk - want_int).max() <= 1       # truncation of boxes within 1e-2 px
+
+
+def test_upload_frame_rect_writes_the_rectangle_and_nothing_else():
+    """vt_upload_frame_rect (the batch-1 tracker's frame staging): rows x columns of a pageable host frame land at their place in the device
+    frame buffer - through the device-side spread and through the strided fallback - and every other byte keeps its value; bad
+    rectangles are refused."""
+    from vittracker_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(12)
+    st = torch.cuda.current_stream().cuda_stream
+    for (H, W) in ((720, 1280), (333, 501)):
+        img = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+        pin = torch.empty(H * W * 3, dtype=torch.uint8).pin_memory()
+        stage = torch.empty(H * W * 3, dtype=torch.uint8, device="cuda")
+        rects = [(0, H, 0, W), (5, H - 7, 3, W - 9), (H // 3, H // 3 + 1, 10, 11), (0, H, W - 1, W), (17, 300, 40, 460), (1, 2, 0, W)]
+        for use_stage in (True, False):
+            for (ya, yb, xa, xb) in rects:
+                dev = torch.full((H, W, 3), 7, dtype=torch.uint8, device="cuda")
+                rc = lib.vt_upload_frame_rect(img.ctypes.data, H, W, ya, yb, xa, xb, pin.data_ptr(), stage.data_ptr() if use_stage else None,
+                                              dev.data_ptr(), st)
+                assert rc == 0
+                torch.cuda.synchronize()
+                want = np.full((H, W, 3), 7, dtype=np.uint8)
+                want[ya:yb, xa:xb] = img[ya:yb, xa:xb]
+                assert np.array_equal(dev.cpu().numpy(), want), (H, W, ya, yb, xa, xb, use_stage)
+        dev = torch.zeros((H, W, 3), dtype=torch.uint8, device="cuda")
+        for bad in ((5, 5, 0, W), (0, H + 1, 0, W), (-1, 4, 0, W), (0, H, 9, 9), (0, H, 0, W + 1)):
+            assert lib.vt_upload_frame_rect(img.ctypes.data, H, W, *bad, pin.data_ptr(), stage.data_ptr(), dev.data_ptr(), st) != 0

@@ -139,12 +139,14 @@ class BatchedBackend:
         self.dev = self.bt.device
         self.slots = slots
         self.search_factor = float(cfg.TEST.SEARCH_FACTOR)
+        self.template_factor = float(cfg.TEST.TEMPLATE_FACTOR)
         self.row_staging = row_staging
         self._cap = 0
         self._pin = None
         self._devbuf = None
-        self._hw = torch.zeros((slots, 2), dtype=torch.int32)
-        self._off = torch.zeros((slots,), dtype=torch.int64)
+        self._hw = torch.zeros((slots, 2), dtype=torch.int32).pin_memory()
+        self._off = torch.zeros((slots,), dtype=torch.int64).pin_memory()
+        self._hw_np, self._off_np = self._hw.numpy(), self._off.numpy()        # the same memory, written without tensor indexing
         self._out_pin = torch.zeros((slots, 5), dtype=torch.float64).pin_memory()
         self._state: List[Optional[list]] = [None] * slots          # host copy of every slot's box (what the device holds)
         self._pool = ThreadPoolExecutor(max_workers=stage_workers, thread_name_prefix="vt-stage") if stage_workers > 0 else None
@@ -167,22 +169,37 @@ class BatchedBackend:
             o += (nbytes + self._PAD + 15) // 16 * 16
         total = o
         if total > self._cap:
-            self._cap = int(total * 1.25) + 1024
+            # sized for every slot holding a whole frame of the largest size seen: pinned allocations cost ~0.4 ms per MB, so the buffers
+            # should be allocated once, not grown step by step as more slots fill up
+            largest = max(f.shape[0] * f.shape[1] * 3 for f in frames)
+            self._cap = max(int(total * 1.25), self.slots * (largest + 2 * self._PAD)) + 1024
             self._pin = torch.empty((self._cap,), dtype=torch.uint8).pin_memory()
             self._devbuf = torch.empty((self._cap,), dtype=torch.uint8, device=self.dev)
             self._devbuf.zero_()
         pin = self._pin.numpy()
 
-        def pack(i):
-            o, ya, yb, nbytes = spans[i]
-            pin[o:o + nbytes] = np.ascontiguousarray(frames[i][ya:yb]).reshape(-1)
+        def pack(lo, hi):
+            for i in range(lo, hi):
+                o, ya, yb, nbytes = spans[i]
+                pin[o:o + nbytes] = np.ascontiguousarray(frames[i][ya:yb]).reshape(-1)
 
-        if self._pool is not None and len(frames) > 1:
-            list(self._pool.map(pack, range(len(frames))))
-        else:
-            for i in range(len(frames)):
-                pack(i)
-        self._devbuf[:total].copy_(self._pin[:total], non_blocking=True)
+        n = len(frames)
+        workers = self._pool._max_workers if self._pool is not None else 1
+        # Up to four groups of frames, >= 8 MB each: a group is packed by all workers (one task per worker - a task per frame costs more in
+        # hand-over than the copy of a small ROI; NumPy's copy releases the GIL) and its bytes cross the link while the next group is packed.
+        groups = max(1, min(4, total // (8 << 20), n))
+        g0 = 0
+        for g in range(groups):
+            g1 = n if g == groups - 1 else max(g0 + 1, (n * (g + 1)) // groups)
+            if workers > 1 and g1 - g0 > 1:
+                per = (g1 - g0 + workers - 1) // workers
+                list(self._pool.map(lambda lo: pack(lo, min(g1, lo + per)), range(g0, g1, per)))
+            else:
+                pack(g0, g1)
+            b0 = 0 if g == 0 else spans[g0][0]
+            b1 = total if g == groups - 1 else spans[g1][0]
+            self._devbuf[b0:b1].copy_(self._pin[b0:b1], non_blocking=True)
+            g0 = g1
         self.bytes_uploaded += total
         # virtual frame start: `ya` rows before the packed rows (never dereferenced outside [ya, yb)); may be negative
         return [o - ya * frames[i].shape[1] * 3 for i, (o, ya, yb, _) in enumerate(spans)]
@@ -192,21 +209,64 @@ class BatchedBackend:
             self._pool.shutdown(wait=False)
             self._pool = None
 
-    def initialize(self, slot: int, image: np.ndarray, box) -> None:
-        torch = self.torch
+    @staticmethod
+    def _check_image(image) -> None:
         if image.dtype != np.uint8 or image.ndim != 3 or image.shape[2] != 3:
             raise ValueError("image must be HxWx3 uint8")
-        offs = self._stage([image])
-        hw = torch.tensor([[image.shape[0], image.shape[1]]], dtype=torch.int32, device=self.dev)
-        off = torch.tensor(offs, dtype=torch.int64, device=self.dev)
-        b = torch.tensor([list(box)], dtype=torch.float64, device=self.dev)
-        status = self.bt.engine.tracks_init(self._devbuf, off, hw, b, first=slot)
-        code = int(status.cpu()[0])
-        if code == 1:
-            raise Exception("Too small bounding box.")                 # processing_utils.py:32-33
-        if code != 0:
-            raise ValueError("crop lies outside the image (undefined in the reference)")
-        self._state[slot] = [float(v) for v in box]
+
+    def initialize_many(self, items) -> List[Optional[Exception]]:
+        """items = [(slot, image, box), ...] -> per item None or the exception the reference's initialize() would have raised.  One staging
+        pass + upload for all of them (only the rows the template crop reads, like a step) and one vt_tracks_init per run of consecutive
+        slots, instead of a staging pass, a launch and a blocking status read per sequence."""
+        torch = self.torch
+        errors: List[Optional[Exception]] = [None] * len(items)
+        ok = []
+        for k, (slot, image, box) in enumerate(items):
+            try:
+                self._check_image(image)
+                ok.append(k)
+            except Exception as e:
+                errors[k] = e
+        if not ok:
+            return errors
+        ok.sort(key=lambda k: items[k][0])
+        frames = [items[k][1] for k in ok]
+        rois = None
+        if self.row_staging:
+            rois = [crop_rows(items[k][2], self.template_factor, items[k][1].shape[0]) for k in ok]
+        offs = self._stage(frames, rois)
+        m = len(ok)
+        meta = np.zeros((m, 7), dtype=np.float64)               # H, W, offset (exact in fp64: < 2^53), box
+        for j, k in enumerate(ok):
+            f = frames[j]
+            meta[j, 0], meta[j, 1], meta[j, 2] = f.shape[0], f.shape[1], offs[j]
+            meta[j, 3:7] = [float(v) for v in items[k][2]]
+        hw = torch.from_numpy(meta[:, 0:2].astype(np.int32)).to(self.dev)
+        off = torch.from_numpy(meta[:, 2].astype(np.int64)).to(self.dev)
+        bx = torch.from_numpy(np.ascontiguousarray(meta[:, 3:7])).to(self.dev)
+        status = torch.empty((m,), dtype=torch.int32, device=self.dev)
+        j = 0
+        while j < m:                                             # runs of consecutive slots
+            e = j + 1
+            while e < m and items[ok[e]][0] == items[ok[e - 1]][0] + 1:
+                e += 1
+            status[j:e] = self.bt.engine.tracks_init(self._devbuf, off[j:e], hw[j:e], bx[j:e], first=items[ok[j]][0])
+            j = e
+        codes = status.cpu().numpy()
+        for j, k in enumerate(ok):
+            code = int(codes[j])
+            if code == 1:
+                errors[k] = Exception("Too small bounding box.")            # processing_utils.py:32-33
+            elif code != 0:
+                errors[k] = ValueError("crop lies outside the image (undefined in the reference)")
+            else:
+                self._state[items[k][0]] = [float(v) for v in items[k][2]]
+        return errors
+
+    def initialize(self, slot: int, image: np.ndarray, box) -> None:
+        err = self.initialize_many([(slot, image, box)])[0]
+        if err is not None:
+            raise err
 
     def park(self, slot: int) -> None:
         """Give an idle slot a valid template / state on the dummy frame."""
@@ -221,18 +281,21 @@ class BatchedBackend:
         if self.row_staging:
             rois = [crop_rows(self._state[i], self.search_factor, f.shape[0]) if self._state[i] is not None else None for i, f in enumerate(frames)]
         offs = self._stage(frames, rois)
+        hw_np, off_np = self._hw_np, self._off_np
         for i, f in enumerate(frames):
-            self._hw[i, 0], self._hw[i, 1] = f.shape[0], f.shape[1]
-            self._off[i] = offs[i]
+            hw_np[i, 0], hw_np[i, 1] = f.shape[0], f.shape[1]
+        off_np[:n] = offs
         hw = self._hw[:n].to(self.dev, non_blocking=True)
         off = self._off[:n].to(self.dev, non_blocking=True)
         out = self.bt.engine.tracks_step(self._devbuf, off, hw, first=0, n=n, update_state=True)
         self._out_pin[:n].copy_(out, non_blocking=True)
         torch.cuda.current_stream(self.dev).synchronize()
         res = self._out_pin[:n].numpy().copy()
+        boxes = res[:, :4].tolist()
+        good = (res[:, 4] >= 0).tolist()
         for i in range(n):
-            if res[i, 4] >= 0:                                         # a flagged track keeps its state on the device too
-                self._state[i] = res[i, :4].tolist()
+            if good[i]:                                                # a flagged track keeps its state on the device too
+                self._state[i] = boxes[i]
         return res
 
 
@@ -316,18 +379,43 @@ class MultiSequenceRunner:
         pending.reverse()
         results: Dict[str, dict] = {}
         while True:
-            # (re)fill free slots; a sequence whose initialisation fails is reported and skipped (running.py:135-142)
-            for i, slot in enumerate(self.slots):
-                while slot.seq is None and pending:
+            # (re)fill free slots; a sequence whose initialisation fails is reported and skipped (running.py:135-142).  The slots that
+            # are free at this point are initialised together when the backend can do that (one staging pass, one upload).
+            while pending:
+                free = [i for i, slot in enumerate(self.slots) if slot.seq is None]
+                if not free:
+                    break
+                batch = []
+                t0 = time.time()
+                for i in free:
+                    if not pending:
+                        break
                     seq = pending.pop()
-                    t0 = time.time()
                     try:
-                        self.backend.initialize(i, read_image(seq.frames[0]), seq.init_bbox)
+                        batch.append((i, seq, read_image(seq.frames[0])))
                     except Exception as e:
                         print(e)
+                if not batch:
+                    continue
+                many = getattr(self.backend, "initialize_many", None)
+                if many is not None:
+                    errors = many([(i, im, seq.init_bbox) for (i, seq, im) in batch])
+                else:
+                    errors = []
+                    for (i, seq, im) in batch:
+                        try:
+                            self.backend.initialize(i, im, seq.init_bbox)
+                            errors.append(None)
+                        except Exception as e:
+                            errors.append(e)
+                dt = (time.time() - t0) / len(batch)
+                for (i, seq, im), err in zip(batch, errors):
+                    if err is not None:
+                        print(err)
                         continue
+                    slot = self.slots[i]
                     slot.seq, slot.next_frame = seq, 1
-                    slot.output = {"target_bbox": [list(seq.init_bbox)], "time": [time.time() - t0]}
+                    slot.output = {"target_bbox": [list(seq.init_bbox)], "time": [dt]}
                     self._parked[i] = False
                     if len(seq.frames) == 1:
                         self._finish(slot, results)
