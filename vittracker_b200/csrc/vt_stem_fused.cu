@@ -111,7 +111,7 @@ template <int BR2>
 __global__ void __launch_bounds__(kFThreads, Fused<BR2>::kCtasPerSm)
 stem12_fused_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict__ frame_offsets, const int4* __restrict__ taps,
                     const uint8_t* __restrict__ w1g, const float* __restrict__ par1g, const uint8_t* __restrict__ w2g,
-                    const float* __restrict__ bias2g, uint8_t* __restrict__ planes3, int n_units, int unit_bands,
+                    const float* __restrict__ bias2g, uint8_t* __restrict__ planes3, int n_units, int n_big, int unit_bands,
                     int* __restrict__ work_counter) {
     using F = Fused<BR2>;
     using C2 = typename F::C2;
@@ -380,18 +380,26 @@ stem12_fused_kernel(const uint8_t* __restrict__ frames, const int64_t* __restric
     // Hazards (program order per thread + the two barriers): conv2's accumulators of i - 1 are read (E2) before the barrier that precedes
     // conv2(i); conv1's accumulators are read (E1) before the barrier that precedes conv1(i + 1); the row slots are rewritten (G(i + 1)) after
     // every thread has waited for conv1(i); the plane image is rewritten (E1(i + 1)) after every thread has waited for conv2(i).
-    // Work distribution: a unit = unit_bands (a power of two <= kUnitBands) consecutive bands of one track.  CTAs take their first unit by index and every further one from
-    // a global counter (crop_taps_kernel resets it to gridDim.x): items differ in cost with the crop's scale and position, and a static
-    // round-robin leaves the slowest CTA 10 % behind the mean.  The successor of the NEXT item is fetched by one thread during the gather
-    // phase, so the atomic's round trip is never waited for.
+    // Work distribution: a unit = consecutive bands of one track (the row reuse above works inside a unit): the first n_big units have
+    // unit_bands bands, the remaining ones a single band - the queue ends in small pieces, so that the last CTA finishes one band, not one
+    // unit, after the others.  CTAs take their first unit by index and every further one from a global counter (crop_taps_kernel resets
+    // it to gridDim.x): items differ in cost with the crop's scale and position, and a static round-robin leaves the slowest CTA 10 %
+    // behind the mean.  The successor of the NEXT item is fetched by one thread during the gather phase, so the atomic's round trip is
+    // never waited for.
+    int unit_last = -1;                              // last item of the unit the newest item belongs to (meaningful in thread 480)
+    auto unit_first = [&](int u) -> int {
+        if (u >= n_units) return -1;
+        if (u < n_big) { unit_last = (u + 1) * unit_bands - 1; return u * unit_bands; }
+        unit_last = n_big * unit_bands + (u - n_big);
+        return unit_last;
+    };
     auto successor = [&](int x) -> int {
         if (x < 0) return -1;
-        if ((x & (unit_bands - 1)) != unit_bands - 1) return x + 1;
-        const int u = atomicAdd(work_counter, 1);
-        return u < n_units ? u * unit_bands : -1;
+        if (x < unit_last) return x + 1;
+        return unit_first(atomicAdd(work_counter, 1));
     };
     int it = 0, prev = -1;
-    int item = (int)blockIdx.x < n_units ? (int)blockIdx.x * unit_bands : -1;
+    int item = unit_first((int)blockIdx.x);
 #ifdef VT_FUSED_TRACE
     if (threadIdx.x == 0 && blockIdx.x < 1024) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_fused_cta[blockIdx.x][1] = t; }
 #endif
@@ -469,18 +477,24 @@ int launch_crop_stem12_fused(const uint8_t* frames, const int64_t* frame_offsets
     }
     // few tracks (the batch-1 latency path): single bands, so that a track spreads over kBands CTAs instead of kBands / kUnitBands
     static const int forced = [] { const char* e = getenv("VT_FUSED_UNIT_BANDS"); return e ? atoi(e) : 0; }();      // A / B aid: 1, 2 or 4
+    // few tracks (the batch-1 latency path): single bands, so that a track spreads over kBands CTAs instead of kBands / kUnitBands
     const int unit_bands = (forced == 1 || forced == 2 || forced == 4) ? forced
                            : (long long)n * (F::kBands / F::kUnitBands) >= 2LL * grid_caps[dev] ? F::kUnitBands : 1;
-    const long long units = (long long)n * (F::kBands / unit_bands);
-    if (units * unit_bands > 0x7fffffffLL) return -1;
-    const int n_units = (int)units;
+    const long long bands = (long long)n * F::kBands;
+    if (bands > 0x7fffffffLL) return -1;
+    // the last sixteenth of the bands (at least two rounds of the grid) is handed out band by band
+    long long small = bands / 16;
+    if (small < 2LL * grid_caps[dev]) small = 2LL * grid_caps[dev];
+    if (small > bands || unit_bands == 1) small = bands;
+    const int n_big = (int)((bands - small) / unit_bands);
+    const int n_units = n_big + (int)(bands - (long long)n_big * unit_bands);
     const int grid = n_units < grid_caps[dev] ? n_units : grid_caps[dev];
     int4* taps = reinterpret_cast<int4*>(tap_tables);
     int* work_counter = reinterpret_cast<int*>(taps + (size_t)n * 2 * kTapPitch);
     crop_taps_kernel<kSx><<<n, 288, 0, st>>>(frame_hw, boxes, factor, taps, out_status, work_counter, grid);
     if (cudaGetLastError() != cudaSuccess) return -1;
     kern<<<grid, kFThreads, F::kSmemBytes, st>>>(frames, frame_offsets, taps, w.stem1_tc_w, w.stem1_tc_par, w.stem_tc_w[0], w.stem_tc_b[0],
-                                                 planes3, n_units, unit_bands, work_counter);
+                                                 planes3, n_units, n_big, unit_bands, work_counter);
     return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }
 
