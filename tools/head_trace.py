@@ -12,7 +12,14 @@ z = torch.randn(148, 3, 128, 128); x = torch.randn(148, 3, 256, 256)
 lib = _lib.load(); buf = (C.c_longlong * 32)()
 for _ in range(3):
     e.forward(z, x); lib.vt_head_trace_read(buf)
-t = np.frombuffer(buf, dtype=np.int64)[:7]
-names = ["zero+LN+A", "conv1", "conv2", "conv3", "conv4", "conv5+argmax"]
-for i, n in enumerate(names): print(f"{n:14s} {t[i+1]-t[i]:8d} cycles")
+t = np.frombuffer(buf, dtype=np.int64)
+names = ["prologue+LN -> A image", "conv1 (MMA + 2 epilogues)", "conv2 (MMA + epilogue)", "conv3 (MMA + epilogue)", "conv4 (CUDA cores)", "conv5 + arg-max + decode"]
+for i, n in enumerate(names): print(f"{n:28s} {t[i+1]-t[i]:8d} cycles")
 print("total", t[6] - t[0])
+if t[10] > 0:          # head_tc_kernel's finer stamps
+    print("  prologue (zero rows, biases, TMEM alloc, barriers, sync)", t[10] - t[0])
+    print("  LayerNorm rows -> operand image                         ", t[11] - t[10])
+    print("  barrier                                                 ", t[1] - t[11])
+    print("  conv1 half 0: MMAs (wait)", t[12] - t[1], " epilogue", t[13] - t[12])
+    print("  conv1 half 1: MMAs (wait)", t[15] - t[13], " epilogue", t[16] - t[15], " (barriers included in the waits)")
+    print("  conv2: MMAs (wait)", t[18] - t[2], " zeroing + epilogue", t[3] - t[18])

@@ -67,7 +67,9 @@ constexpr int kT_Bias = kT_R1 + 2 * kT_R1Half;
 constexpr int kT_Maps = kT_Bias + 256 * 4;
 constexpr int kT_Red = kT_Maps + 6 * 256 * 4;
 constexpr int kT_Bar = kT_Red + 32 * 4;                 // loaded[slots], consumed[slots], acc_ready, w2_loaded, acc2_ready, tmem base
-constexpr size_t kHeadTcSmemBytes = kT_Bar + (2 * kT_RingSlots + 6) * 8;
+constexpr size_t kHeadTcSmemBytes = kT_Bar + (2 * kT_RingSlots + 9) * 8;
+constexpr int kT_TokBytes = 256 * kC * 4;               // a track's search tokens, staged in R1 (dead until conv1's first epilogue) for the LayerNorm
+static_assert(kT_TokBytes <= 2 * kT_R1Half, "token staging");
 constexpr int kT_Issue1 = 2, kT_Issue2 = 6;             // warps issuing conv1's (one per M tile) and conv2's (one per tower x M tile) MMAs
 constexpr int kT_W2Bytes = 3 * 2 * 12 * 48 * 16;        // conv2 weights: (tower) x [hi | lo] x K-major [12 chunks][n = kx*16 + co][8] = 55296
 static_assert(kT_W2Bytes <= kT_R0Bytes && kT_Out4 + 12 * kPlane * 4 <= kT_R0 + kT_R0Bytes && kT_W3 + kHeadTcW3Bytes <= kT_R1 && kT_W3 % 128 == 0, "head tc smem plan");
@@ -159,13 +161,23 @@ __device__ __forceinline__ void head_conv(const float* in, float* outp, const fl
 // `bad` is raised when the row holds a non-finite value (an fp16-range overflow anywhere upstream on the tensor-core path ends as
 // inf / NaN in the residual stream: K / V' / q / P poison every query row of their track, the MLP its own row) or when the
 // normalised row itself would not fit the fp16 operand range.
-__device__ __forceinline__ void head_norm_row(const HeadArgs& a, const ModelW& w, int trk, int row, float (&y)[kC], int& bad) {
-    const float* src = a.tokens + ((size_t)trk * kN + row) * kC;
+// `staged`: the row in shared memory (head_tc_kernel stages a track's search tokens with one bulk copy); null = read it from global memory.
+__device__ __forceinline__ void head_norm_row(const HeadArgs& a, const ModelW& w, int trk, int row, float (&y)[kC], int& bad,
+                                              const float* staged = nullptr) {
     float x[kC];
+    if (staged) {
 #pragma unroll
-    for (int k = 0; k < kC; k += 4) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(src + k));
-        x[k] = v.x; x[k + 1] = v.y; x[k + 2] = v.z; x[k + 3] = v.w;
+        for (int k = 0; k < kC; k += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(staged + k);
+            x[k] = v.x; x[k + 1] = v.y; x[k + 2] = v.z; x[k + 3] = v.w;
+        }
+    } else {
+        const float* src = a.tokens + ((size_t)trk * kN + row) * kC;
+#pragma unroll
+        for (int k = 0; k < kC; k += 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(src + k));
+            x[k] = v.x; x[k + 1] = v.y; x[k + 2] = v.z; x[k + 3] = v.w;
+        }
     }
     float mean = 0.f;
 #pragma unroll
@@ -307,6 +319,8 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
     uint64_t* bar_w3 = bar_acc + 3;
     uint64_t* bar_acc3 = bar_acc + 4;
     uint32_t* tc_tmem = reinterpret_cast<uint32_t*>(bar_acc + 5);
+    uint64_t* bar_tok = bar_acc + 6;
+    uint64_t* bar_w2t = bar_acc + 7;        // [2] conv2's weights of towers 1 and 2 (tower 0: bar_w2), so that a tower starts when ITS weights are in
     const int trk = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int py = tid >> 4, px = tid & 15;
@@ -314,11 +328,21 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
     float vmax = 0.f;            // largest value this thread hands to a tensor-core operand image
 
     HEAD_TRACE(0);
-    // zero rows 0 and 17 of every chunk image (the vertical zero padding of both tensor-core convolutions)
-    for (int i = tid; i < 36 * 2 * 16; i += kHeadThreads) {
-        const int cimg = i / 32, rsel = (i / 16) & 1, q = i & 15;          // 12 + 24 chunk images (hi and lo), row 0 / 17, 16 px
-        const int base = cimg < 12 ? kT_R0 + cimg * kTcAChunk : kT_R1 + (cimg - 12) * kTcAChunk;
-        *reinterpret_cast<float4*>(sm8 + base + (rsel ? 17 * 256 : 0) + q * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+    // The track's 256 search tokens (48 KB, contiguous) come in with ONE bulk copy, issued before anything else and landing under the rest
+    // of the prologue: read row by row from global memory (a thread per token, 192-byte stride between lanes) they cost every load 32
+    // sectors and the LayerNorm 8 k cycles.  They are staged where conv1's output image will be, which nothing touches before conv1's
+    // first epilogue.
+    if (tid == 0) {
+        tc::mbar_init(bar_tok, 1);
+        tc::mbar_fence_init();
+        tc::mbar_arrive_expect_tx(bar_tok, kT_TokBytes);
+        tc::bulk_g2s(sm8 + kT_R1, a.tokens + ((size_t)trk * kN + kNz) * kC, kT_TokBytes, bar_tok);
+    }
+    // zero rows 0 and 17 of conv1's chunk images (the vertical zero padding); conv2's / conv3's images - the staging area now - get theirs
+    // while conv1's first MMAs run
+    for (int i = tid; i < 12 * 2 * 16; i += kHeadThreads) {
+        const int cimg = i / 32, rsel = (i / 16) & 1, q = i & 15;          // 12 chunk images (hi and lo), row 0 / 17, 16 px
+        *reinterpret_cast<float4*>(sm8 + kT_R0 + cimg * kTcAChunk + (rsel ? 17 * 256 : 0) + q * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (tid < 96) sb[tid] = w.head.b1[tid];
     if (tid < 48) sb[96 + tid] = w.head.b2[tid];
@@ -331,22 +355,26 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
         for (int i = 0; i < kT_RingSlots; ++i) { tc::mbar_init(bar_loaded + i, 1); tc::mbar_init(bar_consumed + i, kT_Issue1); }
         tc::mbar_init(bar_acc, kT_Issue1);
         tc::mbar_init(bar_w2, 1);
+        tc::mbar_init(bar_w2t, 1);
+        tc::mbar_init(bar_w2t + 1, 1);
         tc::mbar_init(bar_acc2, kT_Issue2);
         tc::mbar_init(bar_w3, 1);
         tc::mbar_init(bar_acc3, kT_Issue2);
         tc::mbar_fence_init();
     }
     __syncthreads();
+    HEAD_TRACE(10);
     // the first conv1 weight pieces stream in underneath the LayerNorm
     if (warp == 0) {
 #pragma unroll
-        for (int p = 0; p < kT_RingSlots - 1; ++p)
+        for (int p = 0; p < kT_RingSlots; ++p)
             tc::bulk_g2s_elect(sm8 + kT_Ring + p * kT_PieceBytes, w.head_tc_w1 + (size_t)p * kT_PieceBytes, kT_PieceBytes, bar_loaded + p);
     }
     // ---- final LayerNorm -> conv1's operand image (fp16 hi | lo, 8-channel chunks) ----------------------------------
     {
         float y[kC];
-        head_norm_row(a, w, trk, kNz + tid, y, bad);
+        tc::mbar_wait(bar_tok, 0);
+        head_norm_row(a, w, trk, kNz + tid, y, bad, reinterpret_cast<const float*>(sm8 + kT_R1) + tid * kC);
         uint8_t* ab = sm8 + kT_R0 + ((py + 1) * 16 + px) * 16;
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
@@ -358,6 +386,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
         }
         if (a.tokens_norm && tid < kNz) { float yz[kC]; int unused = 0; head_norm_row(a, w, trk, tid, yz, unused); }
     }
+    HEAD_TRACE(11);
     tc::fence_async_smem();
     tc::tc_fence_before();
     __syncthreads();
@@ -385,9 +414,11 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
 #pragma unroll 1
                 for (int q = 0; q < 9; ++q) {
                     const int p = 9 * h + q, ky = q / 3, ks = q % 3;
-                    if (warp == 0 && p + kT_RingSlots - 1 < 18) {
-                        if (p >= 1) tc::mbar_wait(bar_consumed + (p - 1) % kT_RingSlots, ((p - 1) / kT_RingSlots) & 1);    // ring slot of piece p-1 is free
-                        load_piece(p + kT_RingSlots - 1);
+                    // refill: the slot of piece p - 2 (both tiles' MMAs on it have had a piece's time to complete - waiting for piece p - 1
+                    // instead would hold this warp, and with it this tile's share of the tensor pipe, until the MMAs it just issued are done)
+                    if (warp == 0 && p >= 2 && p - 2 + kT_RingSlots < 18) {
+                        tc::mbar_wait(bar_consumed + (p - 2) % kT_RingSlots, ((p - 2) / kT_RingSlots) & 1);
+                        load_piece(p - 2 + kT_RingSlots);
                     }
                     tc::mbar_wait(bar_loaded + p % kT_RingSlots, (p / kT_RingSlots) & 1);
                     tc::tc_fence_after();
@@ -407,10 +438,19 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
                 }
                 tc::mma_commit_elect(bar_acc);
             }
+            if (h == 0 && warp >= kT_Issue1) {       // rows 0 and 17 of conv2's / conv3's 24 chunk images, while the tensor pipe works
+                for (int i = tid - 32 * kT_Issue1; i < 24 * 2 * 16; i += kHeadThreads - 32 * kT_Issue1) {
+                    const int cimg = i / 32, rsel = (i / 16) & 1, q = i & 15;
+                    *reinterpret_cast<float4*>(sm8 + kT_R1 + cimg * kTcAChunk + (rsel ? 17 * 256 : 0) + q * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
             tc::mbar_wait(bar_acc, h);
             tc::tc_fence_after();
+            HEAD_TRACE(12 + 3 * h);
             if (h == 1 && warp == 0) {           // conv1's operand and weight ring are dead: conv2's and conv3's weights stream into their place
-                tc::bulk_g2s_elect(sm8 + kT_R0, w.head_tc_w2, kT_W2Bytes, bar_w2);
+                tc::bulk_g2s_elect(sm8 + kT_R0, w.head_tc_w2, kT_W2Bytes / 3, bar_w2);
+                tc::bulk_g2s_elect(sm8 + kT_R0 + kT_W2Bytes / 3, w.head_tc_w2 + kT_W2Bytes / 3, kT_W2Bytes / 3, bar_w2t);
+                tc::bulk_g2s_elect(sm8 + kT_R0 + 2 * (kT_W2Bytes / 3), w.head_tc_w2 + 2 * (kT_W2Bytes / 3), kT_W2Bytes / 3, bar_w2t + 1);
                 tc::bulk_g2s_elect(sm8 + kT_W3, w.head_tc_w3, kHeadTcW3Bytes, bar_w3);
             }
             // epilogue: combine the three horizontal taps, bias, ReLU -> conv2's operand image (channels 48 h ..)
@@ -445,6 +485,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
                     }
                 }
             }
+            HEAD_TRACE(13 + 3 * h);
             tc::fence_async_smem();
             tc::tc_fence_before();
             __syncthreads();
@@ -457,7 +498,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
     if (warp < kT_Issue2) {                      // one issuing warp per (tower, M tile); N = 48 = the three horizontal taps side by side
         const uint32_t id48 = tc::instr_desc_f16(128, 48, false);
         const int tw = warp >> 1, tl = warp & 1;
-        tc::mbar_wait(bar_w2, 0);
+        tc::mbar_wait(tw == 0 ? bar_w2 : bar_w2t + (tw - 1), 0);
         tc::tc_fence_after();
         const uint32_t d = tbase + (tw * 2 + tl) * 48;
         const uint32_t wb = sbase + kT_R0 + tw * 18432;
@@ -478,6 +519,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
     }
     tc::mbar_wait(bar_acc2, 0);
     tc::tc_fence_after();
+    HEAD_TRACE(18);
     // conv2's weights are dead: their place becomes the zero-bordered fp32 planes of conv3's / conv4's outputs
     for (int i = tid * 4; i < (24 + 12) * kPlane; i += kHeadThreads * 4)
         *reinterpret_cast<float4*>(sm8 + kT_Out3 + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
