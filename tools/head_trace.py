@@ -18,6 +18,8 @@ for i, n in enumerate(names): print(f"{n:28s} {t[i+1]-t[i]:8d} cycles")
 print("total", t[6] - t[0])
 if t[10] > 0:          # head_tc_kernel's finer stamps
     print("  prologue (zero rows, biases, TMEM alloc, barriers, sync)", t[10] - t[0])
+    if t[20] > 0:
+        print("    of which: up to the TMEM allocation", t[20] - t[0], " allocation", t[21] - t[20], " barrier init + CTA barrier", t[10] - t[21])
     print("  LayerNorm rows -> operand image                         ", t[11] - t[10])
     print("  barrier                                                 ", t[1] - t[11])
     print("  conv1 half 0: MMAs (wait)", t[12] - t[1], " epilogue", t[13] - t[12])

@@ -338,19 +338,23 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
         tc::mbar_arrive_expect_tx(bar_tok, kT_TokBytes);
         tc::bulk_g2s(sm8 + kT_R1, a.tokens + ((size_t)trk * kN + kNz) * kC, kT_TokBytes, bar_tok);
     }
+    // the bias block b1[96] b2[48] b3[24] b4[12] w5[24] b5[6]: ONE load per thread (six load -> store pairs in a row cost six L2 round
+    // trips), issued first and stored last, so that its latency lies under the zeroing and the TMEM allocation
+    float bias_v = 0.f;
+    if (tid < 210) {
+        const float* p = tid < 96 ? w.head.b1 + tid : tid < 144 ? w.head.b2 + (tid - 96) : tid < 168 ? w.head.b3 + (tid - 144)
+                         : tid < 180 ? w.head.b4 + (tid - 168) : tid < 204 ? w.head.w5 + (tid - 180) : w.head.b5 + (tid - 204);
+        bias_v = __ldg(p);
+    }
     // zero rows 0 and 17 of conv1's chunk images (the vertical zero padding); conv2's / conv3's images - the staging area now - get theirs
     // while conv1's first MMAs run
     for (int i = tid; i < 12 * 2 * 16; i += kHeadThreads) {
         const int cimg = i / 32, rsel = (i / 16) & 1, q = i & 15;          // 12 chunk images (hi and lo), row 0 / 17, 16 px
         *reinterpret_cast<float4*>(sm8 + kT_R0 + cimg * kTcAChunk + (rsel ? 17 * 256 : 0) + q * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (tid < 96) sb[tid] = w.head.b1[tid];
-    if (tid < 48) sb[96 + tid] = w.head.b2[tid];
-    if (tid < 24) sb[144 + tid] = w.head.b3[tid];
-    if (tid < 12) sb[168 + tid] = w.head.b4[tid];
-    if (tid < 24) sb[180 + tid] = w.head.w5[tid];
-    if (tid < 6) sb[204 + tid] = w.head.b5[tid];
+    HEAD_TRACE(20);
     if (warp == 0) tc::tmem_alloc(tc_tmem, 512);
+    HEAD_TRACE(21);
     if (tid == 32) {
         for (int i = 0; i < kT_RingSlots; ++i) { tc::mbar_init(bar_loaded + i, 1); tc::mbar_init(bar_consumed + i, kT_Issue1); }
         tc::mbar_init(bar_acc, kT_Issue1);
@@ -362,6 +366,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
         tc::mbar_init(bar_acc3, kT_Issue2);
         tc::mbar_fence_init();
     }
+    if (tid < 210) sb[tid] = bias_v;
     __syncthreads();
     HEAD_TRACE(10);
     // the first conv1 weight pieces stream in underneath the LayerNorm
