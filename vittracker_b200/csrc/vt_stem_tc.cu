@@ -20,14 +20,35 @@ namespace vt {
 
 using namespace tc;
 
+// Optional cycle trace of the control warp and of one epilogue thread of CTA 0 of the conv4 instantiation (development aid):
+// -DVT_CONV_TRACE, read back with vt_conv_trace_read().
+#ifdef VT_CONV_TRACE
+__device__ long long g_conv_trace[3][2048];
+__device__ int g_conv_trace_n[3];
+#define CONV_TRACE(side, on)                                                                                     \
+    do {                                                                                                         \
+        if ((on) && blockIdx.x == 0 && lane == 0) { int k__ = g_conv_trace_n[side]; if (k__ < 2048) { g_conv_trace[side][k__] = clock64(); g_conv_trace_n[side] = k__ + 1; } } \
+    } while (0)
+extern "C" int vt_conv_trace_read(long long* host, int* n) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(n, g_conv_trace_n, 3 * sizeof(int));
+    cudaMemcpyFromSymbol(host, g_conv_trace, sizeof(long long) * 3 * 2048);
+    int zero[3] = {0, 0, 0};
+    cudaMemcpyToSymbol(g_conv_trace_n, zero, sizeof zero);
+    return 0;
+}
+#else
+#define CONV_TRACE(side, on) do {} while (0)
+#endif
+
 // Persistent: a CTA walks over work items (track, band of BR output rows).  in: plane images [n][tc_planes_bytes(CCH, WOUT)];
 // wt: packed fp16 hi|lo weight blob in K-step order (loaded once per CTA); bias fp32 [COUT].  OUT_PLANES: write the next
 // layer's plane image (NEXT_CCH chunks, WOUT/2 wide), else tokens [n][tok_stride_rows][COUT] + positional embedding.
-// Warp 16 = control (bulk copies of item i+1 while item i computes; single-thread MMA issue), warps 0-7 / 8-15 = the
+// Warp 17 = bulk copies (one stage ahead), warp 16 = single-thread MMA issue, warps 0-7 / 8-15 = the
 // epilogue groups of accumulator set 0 / 1; two A stages in shared memory and two accumulator sets in TMEM, handed over
 // through mbarriers.
 template <int CCH, int COUT, int NPAD, int WOUT, int BR, bool HSWISH, bool OUT_PLANES, int NEXT_CCH>
-__global__ void __launch_bounds__(544)
+__global__ void __launch_bounds__(576)
 conv_s2_tc_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wt, const float* __restrict__ bias,
                   void* __restrict__ outp, const float* __restrict__ pos, int tok_stride_rows, int tok_off, int n_items) {
     using K = TcConv<CCH, COUT, NPAD, WOUT, BR>;
@@ -37,19 +58,19 @@ conv_s2_tc_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wt
     float* sBias = reinterpret_cast<float*>(smem_tc + K::kOffBias);
     float* sXchg = reinterpret_cast<float*>(smem_tc + K::kOffXchg);
     uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem_tc + K::kOffBar);
-    uint64_t* bar_full = bar_w + 1;      // [2] A stage landed                    (kCopies expect_tx arrivals)
+    uint64_t* bar_full = bar_w + 1;      // [2] A stage landed                    (one expect_tx arrival for the stage's copies)
     uint64_t* bar_afree = bar_w + 3;     // [2] A stage consumed by the MMAs      (tcgen05.commit)
     uint64_t* bar_tfull = bar_w + 5;     // [2] accumulators complete             (tcgen05.commit)
     uint64_t* bar_tfree = bar_w + 7;     // [2] accumulators read by the epilogue (8 warp arrivals)
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_w + 9);
     const int tid = threadIdx.x, lane = tid & 31;
-    const int wid = tid >> 5;                    // 0-15 epilogue, 16 control
+    const int wid = tid >> 5;                    // 0-15 epilogue, 16 MMA issue, 17 bulk copies
     const int warp = wid & 7, group = wid >> 3;  // epilogue warp within its group; group = accumulator set it serves
 
     if (wid == 16) tmem_alloc(s_tmem, K::kTmemCols);
     if (tid == 0) {
         mbar_init(bar_w, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(bar_full + i, K::kCopies); mbar_init(bar_afree + i, 1); mbar_init(bar_tfull + i, 1); mbar_init(bar_tfree + i, 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_full + i, 1); mbar_init(bar_afree + i, 1); mbar_init(bar_tfull + i, 1); mbar_init(bar_tfree + i, 8); }
         mbar_fence_init();
     }
     if (tid < NPAD) sBias[tid] = tid < COUT ? __ldg(bias + tid) : 0.f;
@@ -58,20 +79,33 @@ conv_s2_tc_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wt
     tc_fence_after();
     const uint32_t tbase = __shfl_sync(0xffffffffu, *s_tmem, 0);
 
-    if (wid == 16) {                 // convergent; the elected lane performs copies, MMAs and commits
-        auto stage_item = [&](int item, int st) {     // plane rows [oy0, oy0 + BR + 1) of every (precision, plane, chunk)
-            const int b = item / kBands, oy0 = (item % kBands) * K::kBR;
-            const uint8_t* inb = in + (size_t)b * tc_planes_bytes(CCH, WOUT);
-            uint8_t* sA = smem_tc + K::kOffA + st * K::kStageBytes;
-#pragma unroll 1
-            for (int i = 0; i < K::kCopies; ++i) {
-                const int chunk = i % CCH, plane = (i / CCH) & 3, prec = i / (4 * CCH);
-                const size_t src = (((size_t)(prec * 4 + plane) * CCH + chunk) * (WOUT + 1) + oy0) * WOUT * 16;
-                bulk_g2s_elect(sA + prec * K::kABytes + (plane * CCH + chunk) * K::kChunkBytes, inb + src, K::kChunkBytes, bar_full + st);
-            }
-        };
+    if (wid == 17) {
+        // ---- producer warp: the bulk copies of every item, one stage ahead of the MMAs.  A stage's 8 - 24 copies are started by ONE warp
+        // instruction (a copy per lane) behind a single arming of the barrier, and by a warp of their own: issued one after the other
+        // between the MMAs they cost the control warp ~200 cycles each - more than half of an item's time in conv4.
+        static_assert(K::kCopies <= 32, "one copy per lane");
         bulk_g2s_elect(sW, wt, K::kWBytes, bar_w);
-        if ((int)blockIdx.x < n_items) stage_item(blockIdx.x, 0);
+        int it = 0;
+#pragma unroll 1
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const int st = it & 1;
+            CONV_TRACE(2, CCH == 3);
+            if (it >= 2) mbar_wait(bar_afree + st, ((it - 2) >> 1) & 1);                // the stage's previous user's MMAs are done
+            CONV_TRACE(2, CCH == 3);
+            const int b = item / kBands, oy0 = (item % kBands) * K::kBR;     // plane rows [oy0, oy0 + BR + 1) of every (precision, plane, chunk)
+            const uint8_t* inr = in + (size_t)b * tc_planes_bytes(CCH, WOUT) + (size_t)oy0 * WOUT * 16;
+            uint8_t* sA = smem_tc + K::kOffA + st * K::kStageBytes;
+            mbar_arrive_expect_tx_elect(bar_full + st, K::kCopies * K::kChunkBytes);
+            __syncwarp();
+            if (lane < K::kCopies) {
+                const int chunk = lane % CCH, plane = (lane / CCH) & 3, prec = lane / (4 * CCH);
+                const size_t src = ((size_t)(prec * 4 + plane) * CCH + chunk) * (WOUT + 1) * WOUT * 16;
+                bulk_g2s(sA + prec * K::kABytes + (plane * CCH + chunk) * K::kChunkBytes, inr + src, K::kChunkBytes, bar_full + st);
+            }
+            __syncwarp();
+            CONV_TRACE(2, CCH == 3);
+        }
+    } else if (wid == 16) {          // MMA warp; convergent, the elected lane issues MMAs and commits
         const uint32_t sbase = smem_u32(smem_tc);
         const uint32_t idesc = instr_desc_f16(128, NPAD, false);
         mbar_wait(bar_w, 0);
@@ -80,14 +114,12 @@ conv_s2_tc_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wt
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const int st = it & 1;
             const uint32_t ph = (it >> 1) & 1;
-            const int next = item + gridDim.x;
-            if (next < n_items) {                                   // prefetch the next item into the other stage
-                if (it >= 1) mbar_wait(bar_afree + (st ^ 1), ((it - 1) >> 1) & 1);      // its previous user's MMAs are done
-                stage_item(next, st ^ 1);
-            }
+            CONV_TRACE(0, CCH == 3);
             mbar_wait(bar_full + st, ph);
+            CONV_TRACE(0, CCH == 3);
             if (it >= 2) mbar_wait(bar_tfree + st, ((it - 2) >> 1) & 1);                // accumulator set st has been read
             tc_fence_after();
+            CONV_TRACE(0, CCH == 3);
             const uint32_t abase = sbase + K::kOffA + st * K::kStageBytes;
 #pragma unroll 1
             for (int tile = 0; tile < K::kTiles; ++tile) {          // rolled: the descriptors are affine in `tile`
@@ -119,6 +151,7 @@ conv_s2_tc_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wt
             }
             mma_commit_elect(bar_afree + st);
             mma_commit_elect(bar_tfull + st);
+            CONV_TRACE(0, CCH == 3);
         }
         __syncwarp();
     } else {
@@ -136,8 +169,10 @@ conv_s2_tc_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wt
             const int st = it & 1;
             if (st != group) continue;                                          // the other group's accumulator set
             const int b = item / kBands, oy0 = (item % kBands) * K::kBR;
+            CONV_TRACE(1, CCH == 3 && wid == 0);
             mbar_wait(bar_tfull + st, (it >> 1) & 1);
             tc_fence_after();
+            CONV_TRACE(1, CCH == 3 && wid == 0);
 #pragma unroll 1
             for (int pass = 0; pass < kPasses; ++pass) {
                 const int tile = (K::kTiles >= 2) ? 2 * pass + (warp >> 2) : 0;
@@ -194,6 +229,7 @@ conv_s2_tc_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wt
             }
             // the row-split exchange slots are reused by the next item: every epilogue warp is past its reads
             if constexpr (kSplitRows) asm volatile("bar.sync %0, 256;" ::"r"(1 + group) : "memory");
+            CONV_TRACE(1, CCH == 3 && wid == 0);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tfree + st);

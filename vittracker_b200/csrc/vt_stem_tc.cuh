@@ -72,7 +72,7 @@ struct TcConv {
     static constexpr int kCopies = 2 * 4 * CCH;                  // bulk copies per band: (precision, plane, chunk)
     static constexpr int kAccCols = kTiles * 2 * NPAD;           // TMEM columns of one item's accumulators (T_A | T_B per tile)
     static constexpr int kTmemCols = (2 * kAccCols <= 32) ? 32 : (2 * kAccCols <= 64) ? 64 : (2 * kAccCols <= 128) ? 128 : (2 * kAccCols <= 256) ? 256 : 512;
-    static constexpr int kThreads = 544;                         // 2 x 8 epilogue warps (one group per accumulator set) + 1 control warp
+    static constexpr int kThreads = 576;                         // 2 x 8 epilogue warps (one group per accumulator set) + MMA warp + copy warp
     static_assert(NPAD % 16 == 0 && NPAD >= COUT && 128 % WOUT == 0 && kBR % kRowsPerTile == 0, "shape");
     static_assert(kOffBar % 8 == 0 && kOffW % 128 == 0 && kStageBytes % 128 == 0 && 2 * kAccCols <= 512, "alignment");
 };
