@@ -25,9 +25,11 @@ namespace vt {
 #ifdef VT_HEAD_TRACE
 __device__ long long g_head_trace[32];
 #define HEAD_TRACE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_head_trace[i] = clock64(); } while (0)
+#define HEAD_TRACE_NS(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { long long t__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); g_head_trace[i] = t__; } } while (0)
 extern "C" int vt_head_trace_read(long long* host) { cudaDeviceSynchronize(); return (int)cudaMemcpyFromSymbol(host, g_head_trace, sizeof(long long) * 32); }
 #else
 #define HEAD_TRACE(i) do {} while (0)
+#define HEAD_TRACE_NS(i) do {} while (0)
 #endif
 
 // max that keeps NaN (fmaxf returns the other operand): the ReLUs and the running maximum of the tensor-core epilogues must not
@@ -247,8 +249,8 @@ __device__ __forceinline__ void head_finish(const HeadArgs& a, const ModelW& w, 
     decode_argmax(m_score, m_resp, red, raw_max, raw_idx, win_max, win_idx);
     HEAD_TRACE(6);
     if (tmem_to_free != 0xffffffffu && tid < 32) tc::tmem_dealloc(tmem_to_free, 512);     // all TMEM reads ended before the barriers above
-    if (tid != 0) return;
-    decode_box(a, trk, m_size, m_off, raw_max, raw_idx, win_max, win_idx, any_bad ? VT_TRACK_NUMERIC_RANGE_ : 0);
+    if (tid == 0) decode_box(a, trk, m_size, m_off, raw_max, raw_idx, win_max, win_idx, any_bad ? VT_TRACK_NUMERIC_RANGE_ : 0);
+    HEAD_TRACE(7);
 }
 
 __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(HeadArgs a, ModelW w) {
@@ -321,31 +323,48 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
     uint32_t* tc_tmem = reinterpret_cast<uint32_t*>(bar_acc + 5);
     uint64_t* bar_tok = bar_acc + 6;
     uint64_t* bar_w2t = bar_acc + 7;        // [2] conv2's weights of towers 1 and 2 (tower 0: bar_w2), so that a tower starts when ITS weights are in
-    const int trk = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int py = tid >> 4, px = tid & 15;
+
+    // ---- once per CTA: the bias block, the TMEM allocation.  The kernel is PERSISTENT (one CTA per SM walks over tracks): a CTA per
+    // track costs ~3 us of hand-over per track (tear-down, launch, cold prologue) against 21 us of work.
+    // bias block b1[96] b2[48] b3[24] b4[12] w5[24] b5[6]: ONE load per thread (six load -> store pairs in a row cost six L2 round trips)
+    if (tid < 210) {
+        const float* p = tid < 96 ? w.head.b1 + tid : tid < 144 ? w.head.b2 + (tid - 96) : tid < 168 ? w.head.b3 + (tid - 144)
+                         : tid < 180 ? w.head.b4 + (tid - 168) : tid < 204 ? w.head.w5 + (tid - 180) : w.head.b5 + (tid - 204);
+        sb[tid] = __ldg(p);
+    }
+    if (warp == 0) tc::tmem_alloc(tc_tmem, 512);
+    // A track's 256 search tokens (48 KB, contiguous) come in with ONE bulk copy into the place of conv1's output image (dead from the
+    // end of conv3's MMAs to conv1's first epilogue): read row by row from global memory (a thread per token, 192-byte stride between
+    // lanes) they cost every load 32 sectors and the LayerNorm 8 k cycles.  The first track's copy starts here, track i + 1's when
+    // conv3 of track i has read its operands; bar_tok is used once per track (phase = track parity).
+    if (tid == 0) {
+        tc::mbar_init(bar_tok, 1);
+        tc::mbar_fence_init();
+        if ((int)blockIdx.x < a.n) {
+            tc::mbar_arrive_expect_tx(bar_tok, kT_TokBytes);
+            tc::bulk_g2s(sm8 + kT_R1, a.tokens + ((size_t)blockIdx.x * kN + kNz) * kC, kT_TokBytes, bar_tok);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tbase = __shfl_sync(0xffffffffu, *tc_tmem, 0);
+    const uint32_t sbase = tc::smem_u32(smem);
+    const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
+    const int tile = warp >> 2;                                            // epilogue: pixel = tid, M tile = warp / 4
+
+    HEAD_TRACE_NS(28);
+    HEAD_TRACE(30);
+#pragma unroll 1
+    for (int trk = blockIdx.x, iter = 0; trk < a.n; trk += gridDim.x, ++iter) {
     int bad = 0;                 // fp16 operand range guard (see head_norm_row); OR-reduced over the CTA in head_finish
     float vmax = 0.f;            // largest value this thread hands to a tensor-core operand image
 
     HEAD_TRACE(0);
-    // The track's 256 search tokens (48 KB, contiguous) come in with ONE bulk copy, issued before anything else and landing under the rest
-    // of the prologue: read row by row from global memory (a thread per token, 192-byte stride between lanes) they cost every load 32
-    // sectors and the LayerNorm 8 k cycles.  They are staged where conv1's output image will be, which nothing touches before conv1's
-    // first epilogue.
-    if (tid == 0) {
-        tc::mbar_init(bar_tok, 1);
-        tc::mbar_fence_init();
-        tc::mbar_arrive_expect_tx(bar_tok, kT_TokBytes);
-        tc::bulk_g2s(sm8 + kT_R1, a.tokens + ((size_t)trk * kN + kNz) * kC, kT_TokBytes, bar_tok);
-    }
-    // the bias block b1[96] b2[48] b3[24] b4[12] w5[24] b5[6]: ONE load per thread (six load -> store pairs in a row cost six L2 round
-    // trips), issued first and stored last, so that its latency lies under the zeroing and the TMEM allocation
-    float bias_v = 0.f;
-    if (tid < 210) {
-        const float* p = tid < 96 ? w.head.b1 + tid : tid < 144 ? w.head.b2 + (tid - 96) : tid < 168 ? w.head.b3 + (tid - 144)
-                         : tid < 180 ? w.head.b4 + (tid - 168) : tid < 204 ? w.head.w5 + (tid - 180) : w.head.b5 + (tid - 204);
-        bias_v = __ldg(p);
-    }
+    // Every other barrier starts a track in phase 0: they are re-initialised per track (all of the previous track's waits are over and
+    // every asynchronous arrival has landed - the CTA barrier that ended it came after the last tcgen05.commit was waited for).
     // zero rows 0 and 17 of conv1's chunk images (the vertical zero padding); conv2's / conv3's images - the staging area now - get theirs
     // while conv1's first MMAs run
     for (int i = tid; i < 12 * 2 * 16; i += kHeadThreads) {
@@ -353,9 +372,13 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
         *reinterpret_cast<float4*>(sm8 + kT_R0 + cimg * kTcAChunk + (rsel ? 17 * 256 : 0) + q * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     HEAD_TRACE(20);
-    if (warp == 0) tc::tmem_alloc(tc_tmem, 512);
     HEAD_TRACE(21);
     if (tid == 32) {
+        uint64_t* all[] = {bar_acc, bar_w2, bar_acc2, bar_w3, bar_acc3, bar_w2t, bar_w2t + 1};
+        if (iter > 0) {
+            for (int i = 0; i < kT_RingSlots; ++i) { tc::mbar_inval(bar_loaded + i); tc::mbar_inval(bar_consumed + i); }
+            for (uint64_t* b : all) tc::mbar_inval(b);
+        }
         for (int i = 0; i < kT_RingSlots; ++i) { tc::mbar_init(bar_loaded + i, 1); tc::mbar_init(bar_consumed + i, kT_Issue1); }
         tc::mbar_init(bar_acc, kT_Issue1);
         tc::mbar_init(bar_w2, 1);
@@ -366,7 +389,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
         tc::mbar_init(bar_acc3, kT_Issue2);
         tc::mbar_fence_init();
     }
-    if (tid < 210) sb[tid] = bias_v;
+    tc::fence_async_smem();
     __syncthreads();
     HEAD_TRACE(10);
     // the first conv1 weight pieces stream in underneath the LayerNorm
@@ -378,7 +401,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
     // ---- final LayerNorm -> conv1's operand image (fp16 hi | lo, 8-channel chunks) ----------------------------------
     {
         float y[kC];
-        tc::mbar_wait(bar_tok, 0);
+        tc::mbar_wait(bar_tok, iter & 1);
         head_norm_row(a, w, trk, kNz + tid, y, bad, reinterpret_cast<const float*>(sm8 + kT_R1) + tid * kC);
         uint8_t* ab = sm8 + kT_R0 + ((py + 1) * 16 + px) * 16;
 #pragma unroll
@@ -397,11 +420,6 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
     __syncthreads();
     tc::tc_fence_after();
     HEAD_TRACE(1);
-
-    const uint32_t tbase = __shfl_sync(0xffffffffu, *tc_tmem, 0);
-    const uint32_t sbase = tc::smem_u32(smem);
-    const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
-    const int tile = warp >> 2;                                            // epilogue: pixel = tid, M tile = warp / 4
 
     // ---- conv1: 18 weight pieces p = (h * 3 + ky) * 3 + ks through the ring; D(tile, kx) = columns (tile * 3 + kx) * 48 ----
     {
@@ -591,6 +609,10 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
     }
     tc::mbar_wait(bar_acc3, 0);
     tc::tc_fence_after();
+    if (tid == 0 && trk + (int)gridDim.x < a.n) {          // conv3 has read its operands: the next track's tokens may land in their place
+        tc::mbar_arrive_expect_tx(bar_tok, kT_TokBytes);
+        tc::bulk_g2s(sm8 + kT_R1, a.tokens + ((size_t)(trk + gridDim.x) * kN + kNz) * kC, kT_TokBytes, bar_tok);
+    }
     {
         float* op = out3 + (py + 1) * 18 + px + 1;
 #pragma unroll 1
@@ -618,14 +640,31 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(HeadArgs a, Mo
     HEAD_TRACE(4);
     head_conv<8, 4, 3, true, 8>(out3, out4, w.head.w4, sb + 168, wbuf);            // 8 -> 4
     bad |= !(vmax < kF16Max);
-    head_finish(a, w, trk, out4, sb, maps, red, tbase, bad);
+    head_finish(a, w, trk, out4, sb, maps, red, 0xffffffffu, bad);
+    // end of the track: every thread is past its last read of the planes, the maps and TMEM; the next track's bulk copies (async proxy)
+    // overwrite regions this one wrote through the generic proxy
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    HEAD_TRACE(8);
+    }
+    HEAD_TRACE_NS(29);
+    HEAD_TRACE(31);
+    if (warp == 0) tc::tmem_dealloc(tbase, 512);
 }
 
 int launch_head(const HeadArgs& a, const ModelW& w, cudaStream_t st) {
     if (a.n <= 0) return 0;
     static DeviceOnce once_simt, once_tc;
     if (!ensure_dyn_smem(once_simt, head_kernel, kHeadSmemBytes) || !ensure_dyn_smem(once_tc, head_tc_kernel, kHeadTcSmemBytes)) return -1;
-    if (a.use_tc) head_tc_kernel<<<a.n, kHeadThreads, kHeadTcSmemBytes, st>>>(a, w);
+    if (a.use_tc) {
+        static int sms[kMaxDevices] = {};
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+        if (sms[dev] == 0 && cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+        head_tc_kernel<<<a.n < sms[dev] ? a.n : sms[dev], kHeadThreads, kHeadTcSmemBytes, st>>>(a, w);      // persistent: one CTA (220 KB) per SM
+    }
     else head_kernel<<<a.n, kHeadThreads, kHeadSmemBytes, st>>>(a, w);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
