@@ -121,11 +121,19 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def count(self) -> int:
+        """Samples written so far."""
+        try:
+            self.fh.flush()
+            with open(self.path) as f:
+                return sum(1 for line in f if line.count(",") >= 8)
+        except Exception:
+            return 0
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
-        time.sleep(0.25)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -406,6 +414,11 @@ class Workload:
             self.pending, out = self.sharded.gather_async(out)
         return out
 
+    def local_step(self, t):
+        """The step without its exchange (the clock sampler's load on rank 0 alone: no collective may be issued there)."""
+        self.bt.engine.tracks_set_state(self.step_boxes[t % self.nsets], first=0)
+        self.bt.track_offsets(self.pool.data, self.step_offsets[t % self.F], update_state=True)
+
     def barrier(self):
         torch.cuda.synchronize(self.dev)
         if self.world > 1:
@@ -417,9 +430,17 @@ class Workload:
         for t in range(W):
             self.step(t)
         self.finish_gather()
-        self.barrier()
         if sampler is not None:
+            # The timed region is tens of milliseconds and nvidia-smi needs longer than that to deliver its first sample: the sampler is
+            # started here and the SAME steps keep running (untimed) until it has reported once, so that its 50 ms samples bracket the
+            # timed region under the load that is being timed; the load is kept up for three more sampling periods after the region.
             sampler.start()
+            t_end = time.time() + 3.0
+            while sampler.proc is not None and sampler.count() < 1 and time.time() < t_end:
+                for t in range(8):
+                    self.local_step(t % max(1, W))
+                torch.cuda.synchronize()
+        self.barrier()
         eng = self.bt.engine
         launches0 = eng.launch_count
         eng.profile(True)
@@ -432,10 +453,18 @@ class Workload:
         e1.record()
         self.barrier()
         ms = e0.elapsed_time(e1)
-        clocks = sampler.stop() if sampler is not None else None
+        self.last_out = self.bt.out_boxes[:self.n].cpu().numpy().copy()            # boxes of the last timed step
         stages = eng.profile_read()
         eng.profile(False)
         launches = eng.launch_count - launches0 + (K if self.world > 1 else 0)
+        clocks = None
+        if sampler is not None:
+            n0, t_end = sampler.count(), time.time() + 1.0
+            while sampler.proc is not None and sampler.count() < n0 + 3 and time.time() < t_end:
+                for t in range(8):
+                    self.local_step(t % max(1, W))
+                torch.cuda.synchronize()
+            clocks = sampler.stop()
         tms = torch.tensor([ms], device=self.dev, dtype=torch.float64)
         if self.world > 1:
             self.dist.all_reduce(tms, op=self.dist.ReduceOp.MAX)
@@ -590,7 +619,7 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms, stages, launches, clocks = wl.timed(W, K, sampler)
     value = n * world * K / (ms / 1e3)
-    last_out = bt.out_boxes[:n].cpu().numpy().copy()               # boxes of the last timed step
+    last_out = wl.last_out                                          # boxes of the last timed step
     try:
         parity = wl.parity_spot(W + K - 1, last_out, k=8 if widest else 32) if rank == 0 else None
     except Exception as e:                                         # secondary: never at the expense of the line
