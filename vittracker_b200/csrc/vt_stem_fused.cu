@@ -348,7 +348,8 @@ stem12_fused_kernel(const uint8_t* __restrict__ frames, const int64_t* __restric
                     for (int j = 0; j < 8; ++j) xs[j] = __uint_as_float(rb[pass][j]);
                 }
             }
-            __syncthreads();
+            // only the two warps that share the image row meet here (named barriers 1 .. 8, 64 threads each), not the CTA
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + ((half * 2 + tsel) * 2 + (q >> 1))) : "memory");
 #pragma unroll
             for (int pass = 0; pass < F::kPasses; ++pass) {
                 const int tile = 2 * pass + tsel;

@@ -241,7 +241,7 @@ __device__ __forceinline__ void bulk_g2s_elect(void* dst_smem, const void* src_g
         : "memory");
 }
 
-// the same in two steps, for a stage that is many copies: arm the barrier ONCE with the stage's total, then start the copies
+// for a stage that is many copies: arm the barrier ONCE with the stage's total, then start the copies (bulk_g2s, a copy per lane)
 // (an mbarrier.arrive.expect_tx per copy costs the issuing warp ~200 cycles per copy: conv4's control warp spent more than half of
 // an item's time arming 24 copies)
 __device__ __forceinline__ void mbar_arrive_expect_tx_elect(uint64_t* bar, uint32_t bytes) {
@@ -250,14 +250,6 @@ __device__ __forceinline__ void mbar_arrive_expect_tx_elect(uint64_t* bar, uint3
         "@q mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
         : "memory");
 }
-__device__ __forceinline__ void bulk_g2s_elect_armed(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile(
-        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
-        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(smem_u32(dst_smem)),
-        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-
 // ---- fp32 -> fp16 hi/lo split ------------------------------------------------------------------------
 // v ~= hi + lo with hi = fp16(v), lo = fp16(v - hi): ~22 significant bits for |v| well inside fp16 range.
 // Two instructions per element: one packed conversion gives both hi halves, one mixed-precision FMA per element (sm_100
