@@ -67,6 +67,42 @@ def test_scheduler_ragged_sequences_and_result_files(tmp_path):
     assert set(res2) == {"s1"} and not be2.log            # s1 has a single frame: no box file is ever written for it
 
 
+def test_free_slots_are_initialised_together_when_the_backend_can(tmp_path):
+    """A backend with initialize_many gets every free slot in ONE call per refill round; a sequence whose initialisation fails is reported,
+    skipped and its slot offered to the next pending sequence (running.py:135-142); results equal the one-by-one path."""
+    class Batching(FakeBackend):
+        def __init__(self, slots):
+            super().__init__(slots)
+            self.batches = []
+
+        def initialize_many(self, items):
+            self.batches.append([slot for (slot, _, _) in items])
+            errors = []
+            for slot, image, box in items:
+                try:
+                    self.initialize(slot, image, box)
+                    errors.append(None)
+                except Exception as e:
+                    errors.append(e)
+            return errors
+
+    lengths = [4, 2, 6, 3, 5, 1, 4]
+    def make():
+        seqs = [Sequence(f"s{i}", _frames(n, i), [10.0 * i + 1, 5.0, 20.0, 30.0]) for i, n in enumerate(lengths)]
+        seqs.insert(2, Sequence("bad", _frames(3, 9), [1.0, 1.0, 0.0, 5.0]))            # fails inside the first batch
+        return seqs
+    be = Batching(3)
+    res = MultiSequenceRunner(be, 3).run(make())
+    ref = MultiSequenceRunner(FakeBackend(3), 3).run(make())
+    assert set(res) == set(ref) == {f"s{i}" for i in range(len(lengths))}
+    for name in ref:
+        assert res[name].get("target_bbox") == ref[name].get("target_bbox")
+        assert len(res[name]["time"]) == len(ref[name]["time"])
+    assert be.batches[0] == [0, 1, 2]                       # all three slots at once ...
+    assert be.batches[1] == [2]                             # ... and the failed one again, with the next pending sequence
+    assert all(len(b) >= 1 for b in be.batches)
+
+
 def test_threaded_frame_ingest_from_image_files(tmp_path):
     """frames given as image paths are decoded (cv.imread + BGR2RGB, tracker.py:282-289) by reader threads, the next
     step's frames while the current step runs - same frames, same order, same results as decoding on the calling thread; a sequence

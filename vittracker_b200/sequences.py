@@ -150,6 +150,7 @@ class BatchedBackend:
         self._out_pin = torch.zeros((slots, 5), dtype=torch.float64).pin_memory()
         self._state: List[Optional[list]] = [None] * slots          # host copy of every slot's box (what the device holds)
         self._pool = ThreadPoolExecutor(max_workers=stage_workers, thread_name_prefix="vt-stage") if stage_workers > 0 else None
+        self._workers = max(1, stage_workers)
         self.bytes_uploaded = 0
         # idle slots keep tracking a small black frame so that a step can always cover a contiguous slot range
         self._dummy = np.zeros((64, 64, 3), dtype=np.uint8)
@@ -184,7 +185,7 @@ class BatchedBackend:
                 pin[o:o + nbytes] = np.ascontiguousarray(frames[i][ya:yb]).reshape(-1)
 
         n = len(frames)
-        workers = self._pool._max_workers if self._pool is not None else 1
+        workers = self._workers if self._pool is not None else 1
         # Up to four groups of frames, >= 8 MB each: a group is packed by all workers (one task per worker - a task per frame costs more in
         # hand-over than the copy of a small ROI; NumPy's copy releases the GIL) and its bytes cross the link while the next group is packed.
         groups = max(1, min(4, total // (8 << 20), n))
