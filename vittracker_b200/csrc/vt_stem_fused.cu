@@ -189,8 +189,12 @@ stem12_fused_kernel(const uint8_t* __restrict__ frames, const int64_t* __restric
                         const unsigned q0 = colx[j] + (unsigned)rt.x, q1 = colx[j] + (unsigned)rt.y;
                         const uint32_t* p0 = imw + (q0 >> 2);
                         const uint32_t* p1 = imw + (q1 >> 2);
-                        r.wd[j][0] = __ldg(p0); r.wd[j][1] = __ldg(p0 + 1); r.wd[j][2] = __ldg(p0 + 2);
-                        r.wd[j][3] = __ldg(p1); r.wd[j][4] = __ldg(p1 + 1); r.wd[j][5] = __ldg(p1 + 2);
+                        // the pair's six bytes reach into the third word only when they start at byte 3 of the first: that load is predicated
+                        // per lane (a quarter of the lanes on average - fewer sectors through L1, the front's busiest unit)
+                        r.wd[j][0] = __ldg(p0); r.wd[j][1] = __ldg(p0 + 1); r.wd[j][2] = 0u;
+                        r.wd[j][3] = __ldg(p1); r.wd[j][4] = __ldg(p1 + 1); r.wd[j][5] = 0u;
+                        if ((q0 & 3u) == 3u) r.wd[j][2] = __ldg(p0 + 2);
+                        if ((q1 & 3u) == 3u) r.wd[j][5] = __ldg(p1 + 2);
                         r.sh[j][0] = q0 << 3; r.sh[j][1] = q1 << 3;                       // the funnel shift takes the amount mod 32
                     }
                 }
