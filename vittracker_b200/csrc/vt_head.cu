@@ -15,6 +15,9 @@
 // one accumulator T_kx[y][x'] = sum_{ky,ci} in[y+ky-1][x'][ci] W[ci][ky][kx][co] is built in TMEM over the
 // UNSHIFTED columns, and the epilogue adds T_0[y][x-1] + T_1[y][x] + T_2[y][x+1] with warp shuffles (a
 // warp's 32 TMEM lanes are two complete image rows).  Products are hi*hi + lo*hi + hi*lo as in the blocks.
+// head_tc_kernel is PERSISTENT (one CTA per SM walks over tracks: TMEM and the bias block are set up once, the mbarriers are
+// re-initialised per track); a track's 256 search tokens arrive with one bulk copy - the next track's while the current one runs
+// its last layers - and are normalised out of shared memory.
 #include "vt_geom.cuh"
 #include "vt_internal.h"
 #include "vt_tc.cuh"
@@ -55,8 +58,8 @@ static_assert(kHeadSmemBytes <= 227 * 1024, "head smem");
 
 // ---- tensor-core head (head_tc_kernel): shared-memory plan, byte offsets ---------------------------------------
 //   R0   conv1 A operand: LayerNorm output, fp16 hi | lo, [chunk 0..5][row 0..17][x 0..15][8 ch]; later conv2's weights
-//   RING conv1 weight pieces (3 x 9216 B ring); later the cp.async ring of the CUDA-core layers
-//   R1   conv2 A operand: conv1 output (96 ch = 12 chunks), same chunk-image layout, hi | lo;
+//   RING conv1 weight pieces (5 x 9216 B ring, refilled two pieces behind the issue point); later the cp.async ring of the CUDA-core layers
+//   R1   first the staged search tokens (48 KB, bulk copy); then conv2 A operand: conv1 output (96 ch = 12 chunks), same chunk-image layout, hi | lo;
 //        later the zero-bordered fp32 planes of conv2 / conv3 / conv4 outputs
 constexpr int kTcAChunk = 18 * 16 * 16;                 // bytes of one 8-channel chunk image: 18 rows x 16 px x 16 B
 constexpr int kT_R0 = 0, kT_R0Bytes = 2 * 6 * kTcAChunk;                   // 55296
