@@ -219,6 +219,38 @@ def test_crop_rows_cover_what_sample_target_reads():
     assert crop_rows([10, 10, 0, 0], 4.0, H) is None
 
 
+def test_crop_rect_covers_what_sample_target_reads():
+    """The batch-1 tracker uploads rows [ya, yb) x columns [xa, xb) of a frame (vt_upload_frame_rect): everything sample_target reads
+    (processing_utils.py:34-48) lies inside, for search and template crops, boxes over every border, up-scaling crops and .5 rounding."""
+    from oracle import vt_oracle as O
+    from vittracker_b200.sequences import crop_rect
+    H, W = 240, 320
+    rng = np.random.default_rng(4)
+    im = rng.integers(1, 255, size=(H, W, 3), dtype=np.uint8)
+    checked = 0
+    for k in range(400):
+        factor, S = ((4.0, 256), (2.0, 128))[k % 2]
+        w, h = rng.uniform(2, 200), rng.uniform(2, 200)
+        box = [rng.uniform(-60, W + 20), rng.uniform(-40, H + 20), w, h]
+        if rng.random() < 0.2:
+            box = [float(round(v)) for v in box]
+        if not O.crop_in_domain(box, factor, H, W):
+            continue
+        r = crop_rect(box, factor, H, W)
+        assert r is not None, box
+        ya, yb, xa, xb = r
+        assert 0 <= ya < yb <= H and 0 <= xa < xb <= W
+        masked = np.zeros_like(im)
+        masked[ya:yb, xa:xb] = im[ya:yb, xa:xb]
+        a = O.sample_target_cv(im, box, factor, S)[0]
+        b = O.sample_target_cv(masked, box, factor, S)[0]
+        assert np.array_equal(a, b), (box, r)
+        checked += 1
+    assert checked > 150
+    assert crop_rect([10, 10, 0, 0], 4.0, H, W) is None
+    assert crop_rect([W + 500.0, 10, 20, 20], 4.0, H, W) is None          # the crop misses the frame horizontally
+
+
 def test_save_tracker_output_truncates_like_astype_int(tmp_path):
     s = Sequence("q", _frames(2, 0), [1, 2, 3, 4])
     save_tracker_output(str(tmp_path), s, {"target_bbox": [[1.9, 2.1, 3.999, 4.5], [10.2, -0.5, 7.7, 8.0]], "time": [0.25, 0.5]})

@@ -119,6 +119,21 @@ def crop_rows(box, factor: float, H: int) -> Optional[tuple]:
     return (ya, yb) if yb > ya else None
 
 
+def crop_rect(box, factor: float, H: int, W: int) -> Optional[tuple]:
+    """Rows [ya, yb) x columns [xa, xb) of an H x W frame that sample_target(im, box, factor, .) can read: crop_rows for the rows, and
+    x1 = round(x + w/2 - crop_sz/2) .. x1 + crop_sz for the columns (processing_utils.py:34-48), widened by one spare column on either
+    side so that a boundary pixel never depends on the host's and the device's rounding of x1 agreeing; None when the crop is degenerate
+    or misses the frame."""
+    rows = crop_rows(box, factor, H)
+    if rows is None:
+        return None
+    x, y, w, h = [float(v) for v in box]
+    crop_sz = math.ceil(math.sqrt(w * h) * factor)
+    x1 = round(x + 0.5 * w - crop_sz * 0.5)
+    xa, xb = max(0, x1 - 1), min(W, x1 + crop_sz + 1)
+    return (rows[0], rows[1], xa, xb) if xb > xa else None
+
+
 class BatchedBackend:
     """The device side of the driver: per-slot initialise, one step for a prefix of slots.  Split from the scheduler so
     that the scheduling logic is testable without a GPU.

@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from .model import build_ostrack_dist
+from .sequences import crop_rect
 from .weights import load_checkpoint
 
 
@@ -113,14 +114,11 @@ class Vit_dist(BaseTracker):
         crop_sz = math.ceil(math.sqrt(w * h) * factor)          # processing_utils.py:30
         if crop_sz < 1:
             raise Exception('Too small bounding box.')          # processing_utils.py:32-33
-        # only the rectangle sample_target slices (processing_utils.py:34-48: im[y1:y2, x1:x2]) is staged and sent; one spare column
-        # on either side keeps the host's and the device's rounding of x1 from ever disagreeing about a boundary pixel
-        x1 = round(x + 0.5 * w - crop_sz * 0.5)
-        y1 = round(y + 0.5 * h - crop_sz * 0.5)
-        ya, yb = max(0, y1), min(H, y1 + crop_sz)
-        xa, xb = max(0, x1 - 1), min(W, x1 + crop_sz + 1)
-        if yb <= ya or xb <= xa:
+        # only the rectangle sample_target slices (processing_utils.py:34-48: im[y1:y2, x1:x2]) is staged and sent (crop_rect)
+        rect = crop_rect(box, factor, H, W)
+        if rect is None:
             raise ValueError("crop lies outside the image (undefined in the reference)")
+        ya, yb, xa, xb = rect
         if self._dev.type == "cuda":
             with torch.cuda.device(self._dev):
                 rc = self.engine.lib.vt_upload_frame_rect(image.ctypes.data, H, W, ya, yb, xa, xb, self._frame_pin.data_ptr(),
